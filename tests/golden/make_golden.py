@@ -1,0 +1,203 @@
+"""Generate the golden fixtures in tests/golden/ from the UNMODIFIED reference.
+
+Run in the build container, where /root/reference exists:
+    python oracle/build_ref.py && python tests/golden/make_golden.py
+It imports the reference compiled into oracle/_ref/ (never the oracle restatement,
+never modl_b200) and records inputs -> outputs of the hot-path functions for fixed
+seeds.  The .npz files are committed; the GPU box has no /root/reference.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+
+from modl.decomposition.dict_fact import DictFact  # noqa: E402
+from modl.decomposition.dict_fact_fast import (  # noqa: E402
+    _batch_weight, _enet_regression_multi_gram, _enet_regression_single_gram,
+    _update_G_average)
+from modl.utils.math.enet import enet_norm, enet_projection, enet_scale  # noqa: E402
+from modl.utils.randomkit import RandomState, Sampler  # noqa: E402
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **arrays)
+    print("%-28s %8.1f KB" % (name, os.path.getsize(path) / 1024.))
+
+
+def gold_rng():
+    out = {}
+    for seed in (0, 42, 2 ** 35 + 11):
+        rs = RandomState(seed)
+        out["randint10_%d" % seed] = np.array([rs.randint(10) for _ in range(64)])
+        out["randint_big_%d" % seed] = np.array([rs.randint(2 ** 40) for _ in range(32)])
+        for n, p in ((1000, 0.8), (100, 0.1), (10000, 0.125), (200000, 1. / 12), (50, 0.3)):
+            out["binom_%d_%d_%g" % (seed, n, p)] = np.array(
+                [rs.binomial(n, p) for _ in range(48)])
+        out["perm_%d" % seed] = np.asarray(rs.permutation(37)).copy()
+        a = np.arange(23)
+        b = np.arange(22, -1, -1)
+        out["trace_%d" % seed] = rs.shuffle_with_trace([a, b])
+        out["trace_a_%d" % seed] = a
+        out["trace_b_%d" % seed] = b
+    for rand_size in (0, 1):
+        for repl in (0, 1):
+            for rng_, red in ((100, 10), (1000, 8), (57, 3.5), (20, 1), (20, 2)):
+                s = Sampler(rng_, bool(rand_size), bool(repl), 5)
+                subs = [np.asarray(s.yield_subset(red)).copy() for _ in range(40)]
+                tag = "samp_%d_%d_%d_%g" % (rand_size, repl, rng_, red)
+                out[tag + "_len"] = np.array([len(x) for x in subs])
+                out[tag + "_cat"] = np.concatenate(subs) if subs else np.zeros(0, int)
+    out["batch_weight"] = np.array(
+        [_batch_weight(c, b, lr, off) for c, b, lr, off in
+         ((512, 512, 1., 0.), (1024, 512, .9, 0.), (30, 10, .95, 0.), (5000, 7, .92, 0.), (70, 10, 1., 3.))])
+    save("rng.npz", **out)
+
+
+def gold_enet():
+    rng = np.random.RandomState(0)
+    out = {}
+    for dt in (np.float32, np.float64):
+        v = rng.randn(6, 300).astype(dt)
+        v[3] *= 0.01
+        out["v_%s" % dt.__name__] = v
+        for l1 in (0., 0.15, 0.5, 1.):
+            for radius in (0.5, 1., 40.):
+                res = np.zeros_like(v)
+                for i in range(v.shape[0]):
+                    enet_projection(v[i], res[i], radius, l1)
+                out["proj_%s_%g_%g" % (dt.__name__, l1, radius)] = res
+            out["norm_%s_%g" % (dt.__name__, l1)] = np.array(
+                [enet_norm(v[i], l1) for i in range(v.shape[0])], dtype=dt)
+            sc = v.copy()
+            for i in range(v.shape[0]):
+                enet_scale(sc[i], l1, 1.)
+            out["scale_%s_%g" % (dt.__name__, l1)] = sc
+    save("enet.npz", **out)
+
+
+def gold_regression():
+    rng = np.random.RandomState(1)
+    out = {}
+    k, b, p, n = 48, 20, 150, 30
+    for dt in (np.float32, np.float64):
+        D = (rng.randn(k, p) / np.sqrt(p)).astype(dt)
+        X = rng.randn(b, p).astype(dt)
+        G = np.ascontiguousarray(D @ D.T)
+        Dx = np.ascontiguousarray(X @ D.T)
+        idx = rng.permutation(n)[:b].astype(np.int64)
+        code0 = (rng.randn(n, k) * (rng.rand(n, k) < 0.5)).astype(dt)
+        Gm = (np.tile(G, (b, 1, 1)) * (1 + 0.02 * np.arange(b)[:, None, None])).astype(dt)
+        w_s = rng.rand(b).astype(dt)
+        tag = dt.__name__
+        out.update({"G_" + tag: G, "Dx_" + tag: Dx, "X_" + tag: X, "idx_" + tag: idx,
+                    "code0_" + tag: code0, "Gm_" + tag: Gm, "ws_" + tag: w_s})
+        cases = ((1., .1, False, 1e-3), (1., .05, True, 1e-2), (.5, .05, False, 1e-3),
+                 (.9, .3, False, 1e-2), (0., .1, False, 1e-2))
+        for ci, (l1, alpha, pos, tol) in enumerate(cases):
+            c = code0.copy()
+            _enet_regression_single_gram(G, Dx.copy(), X, c, idx, l1, alpha, pos, tol, 100)
+            out["single_%s_%d" % (tag, ci)] = c
+            c = code0.copy()
+            _enet_regression_multi_gram(Gm.copy(), Dx.copy(), X, c, idx, l1, alpha, pos, tol, 100)
+            out["multi_%s_%d" % (tag, ci)] = c
+        out["cases"] = np.array([(l1, a, float(pos), tol) for l1, a, pos, tol in cases])
+        ga = Gm.copy()
+        _update_G_average(ga, G, w_s)
+        out["gavg_" + tag] = ga
+    save("regression.npz", **out)
+
+
+def gold_update_dict():
+    """One dictionary BCD step with hand-set statistics (dict_fact.py:650-715)."""
+    out = {}
+    k, p, n = 24, 120, 40
+    cases = (dict(comp_l1_ratio=0., comp_pos=False), dict(comp_l1_ratio=1., comp_pos=False),
+             dict(comp_l1_ratio=.3, comp_pos=False), dict(comp_l1_ratio=0., comp_pos=True),
+             dict(comp_l1_ratio=.5, comp_pos=True, G_agg='full'))
+    for dt in (np.float32, np.float64):
+        for ci, kw in enumerate(cases):
+            rng = np.random.RandomState(10 + ci)
+            X = rng.randn(n, p).astype(dt)
+            est = DictFact(n_components=k, random_state=3, reduction=3, **kw)
+            est.prepare(n_samples=n, X=X)
+            A = rng.randn(60, k) * (rng.rand(60, k) < 0.6)
+            est.C_[:] = (A.T @ A / 60).astype(dt)
+            est.C_[5, :] = 0
+            est.C_[:, 5] = 0          # exercises the C[k,k] <= 1e-20 skip rule
+            est.B_[:] = (A.T @ (A @ rng.randn(k, p) * .3 + rng.randn(60, p)) / 60).astype(dt)
+            est.comp_norm_[:] = (rng.rand(k) * .05).astype(dt)
+            subset = np.asarray(est.feature_sampler_.yield_subset(3)).copy()
+            est.gradient_[:, subset] = est.B_[:, subset]
+            state = est.random_state.get_state()
+            order = np.random.RandomState(0)
+            order.set_state(state)
+            order = order.permutation(k)
+            tag = "%s_%d" % (dt.__name__, ci)
+            out.update({"D0_" + tag: est.components_.copy(), "C_" + tag: est.C_.copy(),
+                        "B_" + tag: est.B_.copy(), "norm0_" + tag: est.comp_norm_.copy(),
+                        "subset_" + tag: subset, "order_" + tag: order})
+            if kw.get('G_agg') == 'full':
+                out["G0_" + tag] = est.G_.copy()
+            est._update_dict(subset, 0.5)
+            out["D1_" + tag] = est.components_.copy()
+            out["norm1_" + tag] = est.comp_norm_.copy()
+            if kw.get('G_agg') == 'full':
+                out["G1_" + tag] = est.G_.copy()
+    out["cases"] = np.array([(c['comp_l1_ratio'], float(c['comp_pos']), float(c.get('G_agg') == 'full'))
+                             for c in cases])
+    save("update_dict.npz", **out)
+
+
+FIT_CASES = (
+    dict(reduction=2, batch_size=16, n_epochs=2),
+    dict(reduction=3, batch_size=16, n_epochs=2, code_l1_ratio=0., comp_l1_ratio=1., code_alpha=.1),
+    dict(reduction=2, batch_size=16, n_epochs=2, comp_pos=True, code_pos=True, code_alpha=.01),
+    dict(reduction=2, batch_size=16, n_epochs=2, G_agg='full', Dx_agg='full', comp_l1_ratio=.5),
+    dict(reduction=2, batch_size=16, n_epochs=2, G_agg='average', Dx_agg='average'),
+    dict(reduction=2, batch_size=16, n_epochs=2, G_agg='full', Dx_agg='average',
+         rand_size=False, replacement=False),
+    dict(batch_size=16, n_epochs=2, optimizer='sgd', step_size=.1),
+    dict(reduction=1, batch_size=10, n_epochs=1, code_l1_ratio=0.),
+)
+
+
+def fit_data(dt):
+    rng = np.random.RandomState(7)
+    n, p, k = 96, 40, 6
+    X = (rng.randn(n, k) @ rng.randn(k, p) + 0.1 * rng.randn(n, p)).astype(dt)
+    return X, k
+
+
+def gold_fit():
+    """Whole fits on a tiny problem: final state after n_epochs (dict_fact.py:286-311)."""
+    out = {}
+    for dt in (np.float32, np.float64):
+        X, k = fit_data(dt)
+        for ci, kw in enumerate(FIT_CASES):
+            est = DictFact(n_components=k, random_state=0, **kw).fit(X)
+            tag = "%s_%d" % (dt.__name__, ci)
+            out["D_" + tag] = est.components_
+            out["code_" + tag] = est.code_
+            out["C_" + tag] = est.C_
+            out["B_" + tag] = est.B_
+            out["norm_" + tag] = est.comp_norm_
+            out["labels_" + tag] = est.labels_
+            out["sni_" + tag] = est.sample_n_iter_
+            out["T_" + tag] = est.transform(X)
+            out["score_" + tag] = np.array(est.score(X))
+            if hasattr(est, 'G_'):
+                out["G_" + tag] = est.G_
+    save("fit.npz", **out)
+
+
+if __name__ == "__main__":
+    gold_rng()
+    gold_enet()
+    gold_regression()
+    gold_update_dict()
+    gold_fit()
