@@ -1,0 +1,260 @@
+/*
+ * modl_b200.h -- C ABI of the B200-native MODL minibatch hot path.
+ *
+ * Every entry point replaces one piece of the reference's per-minibatch inner loop
+ * (DictFact._single_batch_fit, modl/decomposition/dict_fact.py:495-526) or one of the
+ * compiled helpers that loop imports (dict_fact.py:13-18).  The reference interface each
+ * function stands in for is cited as  [ref: file:line].  Paths are relative to the
+ * reference checkout (arthurmensch/modl).
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, scalars.  No torch / C++ types.
+ *   - `_f32` / `_f64` suffix = element type of every floating array of that call
+ *     (the reference's Cython `floating` fused type).
+ *   - all array arguments of the device entry points are DEVICE pointers unless the
+ *     parameter name starts with `h_` (host).  Matrices are row-major ("C order") with
+ *     the leading dimension passed explicitly (`ld*`, in elements).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Calls are asynchronous with respect to the host unless stated otherwise.
+ *   - return value: 0 = MODL_OK, otherwise a MODL_E* code; modl_last_error() gives
+ *     the text.  The library never throws and never falls back to a CPU path.
+ *   - buffers are caller-owned and updated in place, exactly like the ndarray
+ *     attributes the reference mutates.
+ */
+#ifndef MODL_B200_H_
+#define MODL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MODL_OK 0
+#define MODL_EINVAL 1      /* bad shape / null pointer / unsupported option   */
+#define MODL_ECUDA 2       /* a CUDA runtime call or kernel launch failed      */
+#define MODL_ENOTSPD 3     /* Cholesky hit a non-positive pivot (posv info>0)  */
+#define MODL_ENOMEM 4
+
+typedef struct modl_ctx modl_ctx;         /* per-device context: workspace, SM count     */
+typedef struct modl_rng modl_rng;         /* host MT19937 stream                          */
+typedef struct modl_sampler modl_sampler; /* host feature-subset sampler                  */
+
+int modl_version(void);
+const char *modl_last_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * Host-side bookkeeping: bit-exact with the reference (integer streams).
+ * ---------------------------------------------------------------------------------- */
+
+/* [ref: modl/utils/randomkit/random_fast.pyx:49-74  RandomState(seed), .seed()] */
+modl_rng *modl_rs_create(uint64_t seed);
+void modl_rs_destroy(modl_rng *rs);
+void modl_rs_seed(modl_rng *rs, uint64_t seed);
+/* [ref: random_fast.pyx:76-77  RandomState.randint(high) -> uniform integer in [0, high]] */
+int64_t modl_rs_randint(modl_rng *rs, uint64_t high);
+/* [ref: random_fast.pyx:146-147  RandomState.binomial(n, p)] */
+int64_t modl_rs_binomial(modl_rng *rs, int64_t n, double p);
+/* [ref: random_fast.pyx:79-85  RandomState.permutation(size)] */
+void modl_rs_permutation(modl_rng *rs, int64_t *h_out, int64_t size);
+/* [ref: random_fast.pyx:87-125  RandomState.shuffle(x) for a 1-D integer array] */
+void modl_rs_shuffle(modl_rng *rs, int64_t *h_x, int64_t n);
+/* [ref: random_fast.pyx:127-144  RandomState.shuffle_with_trace(list)]: draws the swap
+ * list once; h_trace[i] = original position of the row that ends at position i, so
+ * every array of the list becomes x[h_trace].  h_swap may be NULL. */
+void modl_rs_shuffle_with_trace(modl_rng *rs, int64_t n, int64_t *h_swap, int64_t *h_trace);
+
+/* [ref: modl/utils/randomkit/sampler.pyx:10-39  Sampler(range, rand_size, replacement, seed)] */
+modl_sampler *modl_sampler_create(int64_t range, int rand_size, int replacement, uint64_t seed);
+void modl_sampler_destroy(modl_sampler *s);
+/* [ref: sampler.pyx:41-69  Sampler.yield_subset(reduction)]: writes the (unsorted) subset
+ * into h_out (capacity >= range) and returns its length. */
+int64_t modl_sampler_yield_subset(modl_sampler *s, double reduction, int64_t *h_out);
+
+/* [ref: modl/decomposition/dict_fact_fast.pyx:115-122  _batch_weight] */
+double modl_batch_weight(int64_t count, int64_t batch_size, double learning_rate, double offset);
+
+/* ------------------------------------------------------------------------------------
+ * Device context
+ * ---------------------------------------------------------------------------------- */
+int modl_ctx_create(int device, modl_ctx **out);
+void modl_ctx_destroy(modl_ctx *ctx);
+int modl_ctx_sm_count(const modl_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t modl_ctx_launch_count(const modl_ctx *ctx);
+/* tunables: "bcd_cluster" (largest thread-block cluster the dictionary update may use, 0 = none),
+ * "cd_warps" (warps per CTA of the CD kernel, 0 = auto), "force_global_gram" (debug). */
+int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value);
+/* Synchronises `stream`, then returns MODL_ENOTSPD if a Cholesky pivot was non-positive since
+ * the last check (LAPACK posv info > 0, which the reference ignores:
+ * dict_fact_fast.pyx:88-92, 188-192), else MODL_OK.  Clears the flag. */
+int modl_ctx_check_info(modl_ctx *ctx, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Elastic-net ball helpers   [ref: modl/utils/math/enet.pxd:10-16]
+ * ---------------------------------------------------------------------------------- */
+/* enet_norm(v, l1_ratio) for `rows` vectors of length n (row r at v + r*ld); out[rows].
+ * [ref: modl/utils/math/enet.pyx:125-148] */
+int modl_enet_norm_f32(modl_ctx *, const float *v, int64_t rows, int64_t n, int64_t ld,
+                       float l1_ratio, float *out, void *stream);
+int modl_enet_norm_f64(modl_ctx *, const double *v, int64_t rows, int64_t n, int64_t ld,
+                       double l1_ratio, double *out, void *stream);
+/* enet_projection(v, out, radius, l1_ratio) per row; radius[rows] is a device array.
+ * `out` may alias `v`.  [ref: enet.pyx:38-122] */
+int modl_enet_projection_f32(modl_ctx *, const float *v, float *out, int64_t rows, int64_t n,
+                             int64_t ld, const float *radius, float l1_ratio, void *stream);
+int modl_enet_projection_f64(modl_ctx *, const double *v, double *out, int64_t rows, int64_t n,
+                             int64_t ld, const double *radius, double l1_ratio, void *stream);
+/* enet_scale(X[r], l1_ratio, radius) in place for every row.  [ref: enet.pyx:150-168] */
+int modl_enet_scale_f32(modl_ctx *, float *X, int64_t rows, int64_t n, int64_t ld,
+                        float l1_ratio, float radius, void *stream);
+int modl_enet_scale_f64(modl_ctx *, double *X, int64_t rows, int64_t n, int64_t ld,
+                        double l1_ratio, double radius, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Code computation   [ref: DictFact._compute_code, dict_fact.py:577-648]
+ * ---------------------------------------------------------------------------------- */
+/* Gathered Gram / correlation products [ref: dict_fact.py:589-604, and :67-71 for the
+ * un-subsampled transform case]:
+ *     G  (k x k, ld k) = scale * D[:, subset] . D[:, subset]^T      (if G  != NULL)
+ *     Dx (b x k, ld k) = scale * X[:, subset] . D[:, subset]^T      (if Dx != NULL)
+ *     xnorm2[b]        = squared L2 norm of every FULL row of X     (if xnorm2 != NULL)
+ * subset: device int64[s]; NULL means "all p features" (s is ignored).
+ * D is k x p (ldd), X is b x p (ldx). */
+int modl_gram_dx_f32(modl_ctx *, const float *D, int64_t ldd, const float *X, int64_t ldx,
+                     const int64_t *subset, int64_t s, int64_t k, int64_t b, int64_t p,
+                     float scale, float *G, float *Dx, float *xnorm2, void *stream);
+int modl_gram_dx_f64(modl_ctx *, const double *D, int64_t ldd, const double *X, int64_t ldx,
+                     const int64_t *subset, int64_t s, int64_t k, int64_t b, int64_t p,
+                     double scale, double *G, double *Dx, double *xnorm2, void *stream);
+
+/* Batched elastic-net regression over ONE shared Gram matrix
+ * [ref: _enet_regression_single_gram, dict_fact_fast.pyx:125-215].
+ *   G k x k (symmetric; its lower triangle is read), Dx b x k (OVERWRITTEN by the ridge
+ *   branch, like the reference :188-197), code n x k (rows indices[ii] are read as the warm
+ *   start and written), indices int64[b] (NULL = arange(b)).
+ *   The CD stop test needs |x_i|^2 of the full data row [ref: :334-336]: pass either the
+ *   rows X (b x p, ldx) or precomputed xnorm2[b]; X may be NULL when xnorm2 is given.
+ *   l1_ratio == 0 -> Cholesky ridge branch [ref: :174-197]; else cyclic coordinate descent
+ *   [ref: :198-214 -> enet_coordinate_descent_gram :270-427].
+ *   sweeps (int32[b], optional): sweeps executed per sample (diagnostic; 0 for ridge). */
+int modl_enet_regression_single_gram_f32(modl_ctx *, const float *G, float *Dx, const float *X,
+                                         int64_t ldx, int64_t p, const float *xnorm2, float *code,
+                                         const int64_t *indices, int64_t b, int64_t k,
+                                         float l1_ratio, float alpha, int positive, float tol,
+                                         int max_iter, int32_t *sweeps, void *stream);
+int modl_enet_regression_single_gram_f64(modl_ctx *, const double *G, double *Dx, const double *X,
+                                         int64_t ldx, int64_t p, const double *xnorm2, double *code,
+                                         const int64_t *indices, int64_t b, int64_t k,
+                                         double l1_ratio, double alpha, int positive, double tol,
+                                         int max_iter, int32_t *sweeps, void *stream);
+
+/* Same with one Gram matrix per sample, G is b x k x k
+ * [ref: _enet_regression_multi_gram, dict_fact_fast.pyx:33-113].  The ridge branch works on
+ * a copy (the reference destroys the upper triangle of G[ii], :82-94; we leave G intact). */
+int modl_enet_regression_multi_gram_f32(modl_ctx *, const float *G, float *Dx, const float *X,
+                                        int64_t ldx, int64_t p, const float *xnorm2, float *code,
+                                        const int64_t *indices, int64_t b, int64_t k,
+                                        float l1_ratio, float alpha, int positive, float tol,
+                                        int max_iter, int32_t *sweeps, void *stream);
+int modl_enet_regression_multi_gram_f64(modl_ctx *, const double *G, double *Dx, const double *X,
+                                        int64_t ldx, int64_t p, const double *xnorm2, double *code,
+                                        const int64_t *indices, int64_t b, int64_t k,
+                                        double l1_ratio, double alpha, int positive, double tol,
+                                        int max_iter, int32_t *sweeps, void *stream);
+
+/* G_average[ii] = (1 - w[ii]) * G_average[ii] + w[ii] * G for the rows `indices` of the
+ * n x k x k array [ref: _update_G_average, dict_fact_fast.pyx:217-228 and its caller
+ * dict_fact.py:605-618 which gathers/scatters the rows; indices NULL = rows 0..b-1]. */
+int modl_update_G_average_f32(modl_ctx *, float *G_average, const float *G, const float *w_sample,
+                              const int64_t *indices, int64_t b, int64_t k, void *stream);
+int modl_update_G_average_f64(modl_ctx *, double *G_average, const double *G, const double *w_sample,
+                              const int64_t *indices, int64_t b, int64_t k, void *stream);
+/* Dx_average[idx] = (1-w)*Dx_average[idx] + w*Dx ; Dx <- Dx_average[idx]
+ * [ref: dict_fact.py:596-601]. */
+int modl_update_Dx_average_f32(modl_ctx *, float *Dx_average, float *Dx, const float *w_sample,
+                               const int64_t *indices, int64_t b, int64_t k, void *stream);
+int modl_update_Dx_average_f64(modl_ctx *, double *Dx_average, double *Dx, const double *w_sample,
+                               const int64_t *indices, int64_t b, int64_t k, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Surrogate statistics   [ref: DictFact._update_C / _update_B, dict_fact.py:559-575]
+ *   C_ = (1-w) C_ + (w/b) code^T code   (k x k)
+ *   B_ = (1-w) B_ + (w/b) code^T X      (k x p, all p columns)
+ * `code` is the b x k batch code (rows gathered from code_[indices] when indices != NULL,
+ * code then being the full n x k array).  overwrite != 0 selects the 'sgd' branch
+ * (C_ = code^T code / b, :574-575, :565-566).
+ * ---------------------------------------------------------------------------------- */
+int modl_update_stats_f32(modl_ctx *, const float *code, const int64_t *indices, const float *X,
+                          int64_t ldx, float *C, float *B, int64_t ldb, double w, int64_t b,
+                          int64_t k, int64_t p, int overwrite, void *stream);
+int modl_update_stats_f64(modl_ctx *, const double *code, const int64_t *indices, const double *X,
+                          int64_t ldx, double *C, double *B, int64_t ldb, double w, int64_t b,
+                          int64_t k, int64_t p, int overwrite, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Dictionary update   [ref: DictFact._update_dict, dict_fact.py:650-715]
+ * Block coordinate descent over the atoms in `h_order` (host int64[k], the permutation the
+ * caller drew from its NumPy RandomState, :672) restricted to the feature `subset`
+ * (device int64[s]):  gathers components_[:, subset] and B_[:, subset] (the reference's
+ * gradient_[:, subset] = B_[:, subset], :532), runs the sequential atom updates with the
+ * elastic-net-ball projection and comp_norm_ slack accounting (:675-694), scatters the
+ * panel back (:709) and, when G_full != NULL (G_agg == 'full'), down/up-dates G_ (:667-668,
+ * :711-715).
+ *   mode 0 = 'variational' (:675-694); mode 1 = 'sgd' (:695-708) using w and step_size.
+ * ---------------------------------------------------------------------------------- */
+int modl_update_dict_f32(modl_ctx *, float *components, int64_t ldd, const float *B, int64_t ldb,
+                         const float *C, float *comp_norm, float *G_full,
+                         const int64_t *subset, int64_t s, const int64_t *h_order,
+                         int64_t k, int64_t p, float comp_l1_ratio, int comp_pos,
+                         int mode, double w, double step_size, void *stream);
+int modl_update_dict_f64(modl_ctx *, double *components, int64_t ldd, const double *B, int64_t ldb,
+                         const double *C, double *comp_norm, double *G_full,
+                         const int64_t *subset, int64_t s, const int64_t *h_order,
+                         int64_t k, int64_t p, double comp_l1_ratio, int comp_pos,
+                         int mode, double w, double step_size, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * The fused minibatch step   [ref: DictFact._single_batch_fit, dict_fact.py:507-522]
+ * One call = subset upload, gathers + Gram products, optional running averages, code
+ * solve, statistics update, dictionary update.  Host bookkeeping (sampler draw, n_iter_,
+ * sample_n_iter_, w, w_sample, atom order) is done by the caller with the host entry
+ * points above and passed in.
+ * ---------------------------------------------------------------------------------- */
+enum { MODL_AGG_MASKED = 0, MODL_AGG_FULL = 1, MODL_AGG_AVERAGE = 2 };
+
+typedef struct modl_step_params {
+    /* shapes */
+    int64_t n_samples, n_features, n_components, batch_size;
+    /* batch inputs */
+    const void *X;             /* device b x p */
+    int64_t ldx;
+    const int64_t *indices;    /* device int64[b] (rows of code_/averages), NULL = arange */
+    const int64_t *h_subset;   /* HOST int64[s]: sampler output for this batch           */
+    int64_t subset_len;
+    const int64_t *h_order;    /* HOST int64[k]: atom permutation                        */
+    const void *w_sample;      /* device real[b] (only read by the 'average' modes)      */
+    double w;                  /* batch weight                                            */
+    /* estimator state (device, in place) */
+    void *components;          /* k x p */
+    void *code;                /* n x k */
+    void *C;                   /* k x k */
+    void *B;                   /* k x p */
+    void *comp_norm;           /* k     */
+    void *G_full;              /* k x k, G_agg == 'full' only                            */
+    void *Dx_average;          /* n x k, Dx_agg == 'average' only                        */
+    void *G_average;           /* n x k x k, G_agg == 'average' only                     */
+    /* hyper-parameters (DictFact.__init__, dict_fact.py:128-153) */
+    double reduction, code_alpha, code_l1_ratio, comp_l1_ratio, tol, step_size;
+    int max_iter, code_pos, comp_pos, Dx_agg, G_agg, optimizer_sgd;
+    /* diagnostics (optional, device int32[b]) */
+    int32_t *sweeps;
+} modl_step_params;
+
+int modl_batch_fit_f32(modl_ctx *, const modl_step_params *prm, void *stream);
+int modl_batch_fit_f64(modl_ctx *, const modl_step_params *prm, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MODL_B200_H_ */

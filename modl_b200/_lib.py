@@ -1,0 +1,158 @@
+"""ctypes binding of libmodl_b200.so (the C ABI declared in include/modl_b200.h).
+
+The library is built in-tree by `python -m modl_b200.build` (or __graft_entry__.build()).
+There is no CPU fallback: if the shared object is missing this module raises, and every
+device entry point returns an error code that is turned into an exception here.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmodl_b200.so")
+
+MODL_OK, MODL_EINVAL, MODL_ECUDA, MODL_ENOTSPD, MODL_ENOMEM = 0, 1, 2, 3, 4
+AGG = {"masked": 0, "full": 1, "average": 2}
+
+vp, i64, u64, f64, f32, ci = C.c_void_p, C.c_int64, C.c_uint64, C.c_double, C.c_float, C.c_int
+
+
+class StepParams(C.Structure):
+    """struct modl_step_params (include/modl_b200.h)."""
+    _fields_ = [
+        ("n_samples", i64), ("n_features", i64), ("n_components", i64), ("batch_size", i64),
+        ("X", vp), ("ldx", i64), ("indices", vp), ("h_subset", vp), ("subset_len", i64),
+        ("h_order", vp), ("w_sample", vp), ("w", f64),
+        ("components", vp), ("code", vp), ("C", vp), ("B", vp), ("comp_norm", vp),
+        ("G_full", vp), ("Dx_average", vp), ("G_average", vp),
+        ("reduction", f64), ("code_alpha", f64), ("code_l1_ratio", f64), ("comp_l1_ratio", f64),
+        ("tol", f64), ("step_size", f64),
+        ("max_iter", ci), ("code_pos", ci), ("comp_pos", ci), ("Dx_agg", ci), ("G_agg", ci),
+        ("optimizer_sgd", ci),
+        ("sweeps", vp),
+    ]
+
+
+class ModlError(RuntimeError):
+    def __init__(self, status, message):
+        RuntimeError.__init__(self, "modl_b200 error %d: %s" % (status, message))
+        self.status = status
+
+
+def _declare(L):
+    def fn(name, res, args):
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+        return f
+
+    fn("modl_version", ci, [])
+    fn("modl_last_error", C.c_char_p, [])
+    fn("modl_rs_create", vp, [u64])
+    fn("modl_rs_destroy", None, [vp])
+    fn("modl_rs_seed", None, [vp, u64])
+    fn("modl_rs_randint", i64, [vp, u64])
+    fn("modl_rs_binomial", i64, [vp, i64, f64])
+    fn("modl_rs_permutation", None, [vp, vp, i64])
+    fn("modl_rs_shuffle", None, [vp, vp, i64])
+    fn("modl_rs_shuffle_with_trace", None, [vp, i64, vp, vp])
+    fn("modl_sampler_create", vp, [i64, ci, ci, u64])
+    fn("modl_sampler_destroy", None, [vp])
+    fn("modl_sampler_yield_subset", i64, [vp, f64, vp])
+    fn("modl_batch_weight", f64, [i64, i64, f64, f64])
+    fn("modl_ctx_create", ci, [ci, C.POINTER(vp)])
+    fn("modl_ctx_destroy", None, [vp])
+    fn("modl_ctx_sm_count", ci, [vp])
+    fn("modl_ctx_launch_count", i64, [vp])
+    fn("modl_ctx_set_option", ci, [vp, C.c_char_p, ci])
+    fn("modl_ctx_check_info", ci, [vp, vp])
+    for sfx, real in (("f32", f32), ("f64", f64)):
+        fn("modl_enet_norm_" + sfx, ci, [vp, vp, i64, i64, i64, real, vp, vp])
+        fn("modl_enet_projection_" + sfx, ci, [vp, vp, vp, i64, i64, i64, vp, real, vp])
+        fn("modl_enet_scale_" + sfx, ci, [vp, vp, i64, i64, i64, real, real, vp])
+        fn("modl_gram_dx_" + sfx, ci, [vp, vp, i64, vp, i64, vp, i64, i64, i64, i64, real, vp, vp, vp, vp])
+        for nm in ("modl_enet_regression_single_gram_", "modl_enet_regression_multi_gram_"):
+            fn(nm + sfx, ci, [vp, vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, real, real, ci, real, ci, vp, vp])
+        fn("modl_update_G_average_" + sfx, ci, [vp, vp, vp, vp, vp, i64, i64, vp])
+        fn("modl_update_Dx_average_" + sfx, ci, [vp, vp, vp, vp, vp, i64, i64, vp])
+        fn("modl_update_stats_" + sfx, ci, [vp, vp, vp, vp, i64, vp, vp, i64, f64, i64, i64, i64, ci, vp])
+        fn("modl_update_dict_" + sfx, ci, [vp, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, i64, i64,
+                                           real, ci, ci, f64, f64, vp])
+        fn("modl_batch_fit_" + sfx, ci, [vp, C.POINTER(StepParams), vp])
+
+
+# every symbol include/modl_b200.h declares (tests check the library exports them all)
+EXPORTED = (
+    ["modl_version", "modl_last_error", "modl_rs_create", "modl_rs_destroy", "modl_rs_seed",
+     "modl_rs_randint", "modl_rs_binomial", "modl_rs_permutation", "modl_rs_shuffle",
+     "modl_rs_shuffle_with_trace", "modl_sampler_create", "modl_sampler_destroy",
+     "modl_sampler_yield_subset", "modl_batch_weight", "modl_ctx_create", "modl_ctx_destroy",
+     "modl_ctx_sm_count", "modl_ctx_launch_count", "modl_ctx_set_option", "modl_ctx_check_info"]
+    + [n + s for s in ("f32", "f64") for n in (
+        "modl_enet_norm_", "modl_enet_projection_", "modl_enet_scale_", "modl_gram_dx_",
+        "modl_enet_regression_single_gram_", "modl_enet_regression_multi_gram_",
+        "modl_update_G_average_", "modl_update_Dx_average_", "modl_update_stats_",
+        "modl_update_dict_", "modl_batch_fit_")])
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises ImportError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "modl_b200: %s is missing -- build the CUDA extension first with "
+                "`python -m modl_b200.build` (there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != MODL_OK:
+        raise ModlError(status, lib().modl_last_error().decode("utf-8", "replace"))
+
+
+_contexts = {}
+
+
+class Context(object):
+    """One modl_ctx per CUDA device (workspace arena + launch geometry)."""
+
+    def __init__(self, device_index):
+        h = vp()
+        check(lib().modl_ctx_create(int(device_index), C.byref(h)))
+        self.handle = h
+        self.device_index = int(device_index)
+
+    @property
+    def sm_count(self):
+        return lib().modl_ctx_sm_count(self.handle)
+
+    @property
+    def launch_count(self):
+        return int(lib().modl_ctx_launch_count(self.handle))
+
+    def set_option(self, name, value):
+        check(lib().modl_ctx_set_option(self.handle, name.encode(), int(value)))
+
+    def check_info(self, stream):
+        check(lib().modl_ctx_check_info(self.handle, vp(stream)))
+
+
+def get_context(device_index):
+    ctx = _contexts.get(device_index)
+    if ctx is None:
+        ctx = _contexts[device_index] = Context(device_index)
+    return ctx
+
+
+def sfx_of(dtype):
+    import torch
+    if dtype == torch.float32:
+        return "f32"
+    if dtype == torch.float64:
+        return "f64"
+    raise TypeError("modl_b200 supports float32 and float64, got %s" % (dtype,))

@@ -1,0 +1,701 @@
+// api.cu -- C-ABI entry points (include/modl_b200.h): context, launch geometry, and the
+// fused minibatch step that mirrors DictFact._single_batch_fit
+// [ref: modl/decomposition/dict_fact.py:495-526].
+#include <cstdarg>
+#include <cstdlib>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "basic_kernels.cuh"
+#include "bcd_kernels.cuh"
+#include "cd_kernels.cuh"
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "ridge_kernels.cuh"
+
+namespace modl {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace modl
+
+using namespace modl;
+
+int modl_ctx::reserve(WsSlot slot, size_t bytes, void **out)
+{
+    if (bytes == 0) bytes = 16;
+    if (slot_bytes[slot] < bytes) {
+        // grow-only; freeing is stream-ordered-safe because cudaFree synchronises the device
+        if (slot_ptr[slot]) MODL_CUDA_TRY(cudaFree(slot_ptr[slot]));
+        slot_ptr[slot] = nullptr;
+        slot_bytes[slot] = 0;
+        size_t cap = bytes + bytes / 4 + 256;
+        MODL_CUDA_TRY(cudaMalloc(&slot_ptr[slot], cap));
+        slot_bytes[slot] = cap;
+    }
+    *out = slot_ptr[slot];
+    return MODL_OK;
+}
+
+extern "C" {
+
+int modl_version(void) { return 100; }
+const char *modl_last_error(void) { return modl::g_err; }
+
+int modl_ctx_create(int device, modl_ctx **out)
+{
+    MODL_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    MODL_CUDA_TRY(cudaGetDeviceCount(&count));
+    MODL_REQUIRE(device >= 0 && device < count, "no such CUDA device");
+    MODL_CUDA_TRY(cudaSetDevice(device));
+    modl_ctx *c = new (std::nothrow) modl_ctx();
+    if (!c) return MODL_ENOMEM;
+    c->device = device;
+    MODL_CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    MODL_CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    MODL_CUDA_TRY(cudaDeviceGetAttribute(&c->cluster_ok, cudaDevAttrClusterLaunch, device));
+    if (const char *e = getenv("MODL_BCD_CLUSTER")) c->opt_bcd_cluster = atoi(e);
+    if (const char *e = getenv("MODL_CD_WARPS")) c->opt_cd_warps = atoi(e);
+    if (const char *e = getenv("MODL_FORCE_GLOBAL_GRAM")) c->opt_force_global_gram = atoi(e);
+    int *info = nullptr;
+    if (ws<int>(c, WS_INFO, 4, &info) != MODL_OK) { delete c; return MODL_ECUDA; }
+    MODL_CUDA_TRY(cudaMemset(info, 0, 4 * sizeof(int)));
+    *out = c;
+    return MODL_OK;
+}
+
+void modl_ctx_destroy(modl_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < WS_COUNT; ++i)
+        if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
+    delete ctx;
+}
+
+int modl_ctx_sm_count(const modl_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+int64_t modl_ctx_launch_count(const modl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value)
+{
+    MODL_REQUIRE(ctx && name, "null");
+    if (!strcmp(name, "bcd_cluster")) ctx->opt_bcd_cluster = value;
+    else if (!strcmp(name, "cd_warps")) ctx->opt_cd_warps = value;
+    else if (!strcmp(name, "force_global_gram")) ctx->opt_force_global_gram = value;
+    else { set_error("unknown option %s", name); return MODL_EINVAL; }
+    return MODL_OK;
+}
+
+// Synchronises `stream` and reports (then clears) the sticky numerical status:
+// MODL_ENOTSPD if a Cholesky pivot was non-positive since the last check.
+int modl_ctx_check_info(modl_ctx *ctx, void *stream)
+{
+    MODL_REQUIRE(ctx, "null ctx");
+    int h[4] = {0, 0, 0, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    MODL_CUDA_TRY(cudaMemcpyAsync(h, ctx->slot_ptr[WS_INFO], sizeof(h), cudaMemcpyDeviceToHost, st));
+    MODL_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h[0] != 0) {
+        MODL_CUDA_TRY(cudaMemsetAsync(ctx->slot_ptr[WS_INFO], 0, sizeof(h), st));
+        set_error("Cholesky: leading minor of order %d is not positive definite", h[0]);
+        return MODL_ENOTSPD;
+    }
+    return MODL_OK;
+}
+
+}  // extern "C"
+
+namespace modl {
+
+static inline int grid_for(modl_ctx *ctx, int64_t work, int per_sm = 8)
+{
+    int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    int64_t g = work < cap ? work : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+// ---------------------------------------------------------------------------------------
+// gathers
+// ---------------------------------------------------------------------------------------
+template <typename T>
+static int gather_cols(modl_ctx *ctx, const T *src, int64_t ld, int64_t rows, int64_t p,
+                       const int64_t *subset, int64_t s, T *dst, int64_t ldd, T *norm2, cudaStream_t st)
+{
+    if (rows <= 0) return MODL_OK;
+    gather_cols_kernel<T><<<grid_for(ctx, rows, 16), 256, 0, st>>>(src, ld, (int)rows, (int)p, subset, (int)s,
+                                                                    dst, ldd, norm2);
+    MODL_LAUNCH_CHECK(ctx);
+    return MODL_OK;
+}
+
+template <typename T>
+static int scatter_cols(modl_ctx *ctx, const T *src, int64_t lds, int64_t rows, const int64_t *subset,
+                        int64_t s, T *dst, int64_t ldd, cudaStream_t st)
+{
+    if (rows <= 0 || s <= 0) return MODL_OK;
+    dim3 grid((unsigned)ceil_div(s, 256), (unsigned)(rows < 65535 ? rows : 65535));
+    scatter_cols_kernel<T><<<grid, 256, 0, st>>>(src, lds, (int)rows, subset, (int)s, dst, ldd);
+    MODL_LAUNCH_CHECK(ctx);
+    return MODL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// coordinate descent launch
+// ---------------------------------------------------------------------------------------
+template <typename T, int TILES, bool PACKED>
+static int cd_launch_inst(modl_ctx *ctx, const T *G, int64_t g_stride, const T *Dx, const T *xnorm2, T *code,
+                          const int64_t *indices, T *code_batch, int64_t b, int64_t k, T alpha, T beta, T tol,
+                          int max_iter, int positive, int32_t *sweeps, cudaStream_t st)
+{
+    auto kern = cd_regression_kernel<T, TILES, PACKED>;
+    size_t smem = PACKED ? cd_packed_elems(TILES) * sizeof(T) : 0;
+    int warps, grid;
+    if (PACKED) {
+        warps = ctx->opt_cd_warps > 0 ? ctx->opt_cd_warps : (int)ceil_div(b, ctx->sm_count);
+        if (warps < 4) warps = 4;
+        if (warps > 16) warps = 16;
+        grid = (int)ceil_div(b, warps);
+        if (grid > ctx->sm_count) grid = ctx->sm_count;
+        MODL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else {
+        warps = ctx->opt_cd_warps > 0 ? ctx->opt_cd_warps : 4;
+        if (warps > 8) warps = 8;
+        grid = (int)ceil_div(b, warps);
+        if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
+    }
+    kern<<<grid, warps * 32, smem, st>>>(G, g_stride, Dx, xnorm2, code, indices, code_batch, (int)b, (int)k,
+                                         alpha, beta, tol, max_iter, positive, sweeps);
+    MODL_LAUNCH_CHECK(ctx);
+    return MODL_OK;
+}
+
+template <typename T>
+static int cd_launch(modl_ctx *ctx, const T *G, int64_t g_stride, const T *Dx, const T *xnorm2, T *code,
+                     const int64_t *indices, T *code_batch, int64_t b, int64_t k, T alpha, T beta, T tol,
+                     int max_iter, int positive, int32_t *sweeps, cudaStream_t st)
+{
+    if (b <= 0) return MODL_OK;
+    MODL_REQUIRE(k >= 1 && k <= 1024, "n_components must be in [1, 1024]");
+    const int tiles = (int)ceil_div(k, 32);
+    const bool packed = g_stride == 0 && !ctx->opt_force_global_gram && tiles <= 10 &&
+                        cd_packed_elems(tiles) * sizeof(T) + 1024 <= (size_t)ctx->max_smem_optin;
+#define MODL_CD_CASE(TL, PK)                                                                              \
+    return cd_launch_inst<T, TL, PK>(ctx, G, g_stride, Dx, xnorm2, code, indices, code_batch, b, k, alpha, \
+                                     beta, tol, max_iter, positive, sweeps, st)
+    if (packed) {
+        switch (tiles) {
+            case 1: MODL_CD_CASE(1, true);
+            case 2: MODL_CD_CASE(2, true);
+            case 3: MODL_CD_CASE(3, true);
+            case 4: MODL_CD_CASE(4, true);
+            case 5: MODL_CD_CASE(5, true);
+            case 6: MODL_CD_CASE(6, true);
+            case 7: MODL_CD_CASE(7, true);
+            case 8: MODL_CD_CASE(8, true);
+            case 9: MODL_CD_CASE(9, true);
+            default: MODL_CD_CASE(10, true);
+        }
+    }
+    if (tiles <= 1) MODL_CD_CASE(1, false);
+    if (tiles <= 2) MODL_CD_CASE(2, false);
+    if (tiles <= 4) MODL_CD_CASE(4, false);
+    if (tiles <= 8) MODL_CD_CASE(8, false);
+    if (tiles <= 16) MODL_CD_CASE(16, false);
+    MODL_CD_CASE(32, false);
+#undef MODL_CD_CASE
+}
+
+// ---------------------------------------------------------------------------------------
+// ridge launch
+// ---------------------------------------------------------------------------------------
+template <typename T>
+static int ridge_solve(modl_ctx *ctx, const T *G, int64_t g_stride, T *Dx, T *code, const int64_t *indices,
+                       T *code_batch, int64_t b, int64_t k, T alpha, cudaStream_t st)
+{
+    if (b <= 0) return MODL_OK;
+    MODL_REQUIRE(k >= 1 && k <= 1024, "n_components must be in [1, 1024]");
+    const int64_t nfac = g_stride == 0 ? 1 : b;
+    T *F = nullptr;
+    MODL_TRY(ws<T>(ctx, WS_CHOL, (size_t)(nfac * k * k), &F));
+    int *info = static_cast<int *>(ctx->slot_ptr[WS_INFO]);
+    chol_factor_kernel<T><<<(unsigned)nfac, 1024, 0, st>>>(G, g_stride, alpha, F, (int)k, info);
+    MODL_LAUNCH_CHECK(ctx);
+    const int tiles = (int)ceil_div(k, 32);
+    const int warps = 4;
+    int grid = (int)ceil_div(b, warps);
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    const int64_t fs = g_stride == 0 ? 0 : k * k;
+#define MODL_RS_CASE(TL) \
+    chol_solve_kernel<T, TL><<<grid, warps * 32, 0, st>>>(F, fs, Dx, code, indices, code_batch, (int)b, (int)k)
+    if (tiles <= 1) MODL_RS_CASE(1);
+    else if (tiles <= 2) MODL_RS_CASE(2);
+    else if (tiles <= 4) MODL_RS_CASE(4);
+    else if (tiles <= 8) MODL_RS_CASE(8);
+    else if (tiles <= 16) MODL_RS_CASE(16);
+    else MODL_RS_CASE(32);
+#undef MODL_RS_CASE
+    MODL_LAUNCH_CHECK(ctx);
+    return MODL_OK;
+}
+
+// regression front: CD or ridge.  xnorm2 is required for CD.
+template <typename T>
+static int regression(modl_ctx *ctx, const T *G, int64_t g_stride, T *Dx, const T *xnorm2, T *code,
+                      const int64_t *indices, T *code_batch, int64_t b, int64_t k, T l1_ratio, T alpha,
+                      int positive, T tol, int max_iter, int32_t *sweeps, cudaStream_t st)
+{
+    if (l1_ratio == T(0)) {
+        if (sweeps) MODL_CUDA_TRY(cudaMemsetAsync(sweeps, 0, sizeof(int32_t) * (size_t)b, st));
+        return ridge_solve<T>(ctx, G, g_stride, Dx, code, indices, code_batch, b, k, alpha, st);
+    }
+    return cd_launch<T>(ctx, G, g_stride, Dx, xnorm2, code, indices, code_batch, b, k, alpha * l1_ratio,
+                        alpha * (T(1) - l1_ratio), tol, max_iter, positive, sweeps, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// dictionary update
+// ---------------------------------------------------------------------------------------
+template <typename T>
+static int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *comp_norm,
+                      const int32_t *d_order, int64_t k, int64_t s, T l1_ratio, int positive, cudaStream_t st)
+{
+    if (s <= 0 || k <= 0) return MODL_OK;
+    auto kern = bcd_update_kernel<T>;
+    const size_t budget = (size_t)ctx->max_smem_optin - 1024;
+    auto base_smem = [&](int64_t ncp) {
+        return (size_t)(round_up(k, 32) + BCD_THREADS + ncp + 40) * sizeof(T) + 40 * sizeof(double);
+    };
+    BcdParams<T> P;
+    P.Dp = Dp; P.Bp = Bp; P.C = C; P.comp_norm = comp_norm; P.order = d_order;
+    P.k = (int)k; P.s = (int)s; P.lds = (int)lds; P.l1_ratio = l1_ratio; P.positive = positive;
+
+    int nblk = 0, use_cluster = 0, d_in_smem = 0;
+    int64_t cols = 0;
+    size_t smem = 0;
+    // 1) a single thread-block cluster with the panel resident in shared memory
+    if (ctx->cluster_ok && ctx->opt_bcd_cluster >= 2) {
+        for (int cs = 16; cs >= 2 && !nblk; cs >>= 1) {
+            if (cs > ctx->opt_bcd_cluster) continue;
+            const int64_t c = ceil_div(s, cs), ncp = round_up(c, 32);
+            const size_t need = base_smem(ncp) + (size_t)k * ncp * sizeof(T);
+            if (need > budget) continue;
+            if (cs > 8) {
+                if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+                    cudaGetLastError();
+                    continue;
+                }
+            }
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(cs); cfg.blockDim = dim3(BCD_THREADS); cfg.dynamicSmemBytes = need; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
+                cudaGetLastError();
+                continue;
+            }
+            nblk = cs; use_cluster = 1; d_in_smem = 1; cols = c; smem = need;
+        }
+    }
+    // 2) cooperative launch over the SMs with a global barrier
+    if (!nblk) {
+        int64_t want = ceil_div(s, 32);
+        if (want > ctx->sm_count) want = ctx->sm_count;
+        if (want < 1) want = 1;
+        cols = ceil_div(s, want);
+        const int64_t ncp = round_up(cols, 32);
+        size_t need = base_smem(ncp) + (size_t)k * ncp * sizeof(T);
+        d_in_smem = need <= budget;
+        if (!d_in_smem) need = base_smem(ncp);
+        MODL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        int per_sm = 0;
+        MODL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BCD_THREADS, need));
+        MODL_REQUIRE(per_sm >= 1, "dictionary-update kernel does not fit on an SM");
+        nblk = (int)ceil_div(s, cols);
+        MODL_REQUIRE(nblk <= per_sm * ctx->sm_count, "cooperative grid too large");
+        smem = need;
+    }
+    const int64_t nchunks = ceil_div(cols, 128);
+    int64_t cw = round_up(ceil_div(cols, nchunks), 32);
+    if (cw > 128) cw = 128;
+    P.cols_per_cta = (int)cols; P.chunk = (int)cw; P.d_in_smem = d_in_smem; P.use_cluster = use_cluster;
+
+    // exchange workspace: [barrier 256 B][part 2*nblk*4][vrow 2*s][na_part nblk*k][radius k]
+    const size_t n_t = (size_t)(2 * nblk * BCD_NPART) + 2 * (size_t)s + (size_t)nblk * k + (size_t)k;
+    unsigned char *base = nullptr;
+    MODL_TRY(ws<unsigned char>(ctx, WS_BCD_SYNC, 256 + n_t * sizeof(T), &base));
+    P.bar = reinterpret_cast<unsigned *>(base);
+    T *tb = reinterpret_cast<T *>(base + 256);
+    P.part = tb; tb += 2 * nblk * BCD_NPART;
+    P.vrow = tb; tb += 2 * s;
+    P.na_part = tb; tb += (size_t)nblk * k;
+    P.radius_log = tb;
+    MODL_CUDA_TRY(cudaMemsetAsync(P.bar, 0, 256, st));
+
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(BCD_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    if (use_cluster) {
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = nblk; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    } else {
+        at[0].id = cudaLaunchAttributeCooperative;
+        at[0].val.cooperative = 1;
+    }
+    cfg.attrs = at; cfg.numAttrs = 1;
+    MODL_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P));
+    MODL_LAUNCH_CHECK(ctx);
+    return MODL_OK;
+}
+
+// upload the atom order as int32
+static int upload_order(modl_ctx *ctx, const int64_t *h_order, int64_t k, int32_t **d_order, cudaStream_t st)
+{
+    MODL_TRY(ws<int32_t>(ctx, WS_ORDER, (size_t)k, d_order));
+    std::vector<int32_t> tmp((size_t)k);
+    for (int64_t i = 0; i < k; ++i) {
+        MODL_REQUIRE(h_order[i] >= 0 && h_order[i] < k, "order is not a permutation of range(k)");
+        tmp[(size_t)i] = (int32_t)h_order[i];
+    }
+    // pageable source: the runtime stages the bytes before returning, so `tmp` may die here
+    MODL_CUDA_TRY(cudaMemcpyAsync(*d_order, tmp.data(), sizeof(int32_t) * (size_t)k, cudaMemcpyHostToDevice, st));
+    return MODL_OK;
+}
+
+// Dictionary update given an already-gathered (or to-be-gathered) D panel.
+//   Dpanel: k x s (ld = s) workspace holding components_[:, subset] if panel_ready, else filled here.
+template <typename T>
+static int update_dict_impl(modl_ctx *ctx, T *components, int64_t ldd, const T *B, int64_t ldb, const T *C,
+                            T *comp_norm, T *G_full, const int64_t *subset, int64_t s, const int64_t *h_order,
+                            int64_t k, int64_t p, T comp_l1_ratio, int comp_pos, int mode, double w,
+                            double step_size, T *Dpanel, bool panel_ready, cudaStream_t st)
+{
+    MODL_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (variational) or 1 (sgd)");
+    if (k <= 0) return MODL_OK;
+    const int64_t lds = s > 0 ? s : 1;
+    T *Bp = nullptr;
+    MODL_TRY(ws<T>(ctx, WS_PANEL_B, (size_t)(k * lds), &Bp));
+    if (!panel_ready) MODL_TRY(gather_cols<T>(ctx, components, ldd, k, p, subset, s, Dpanel, lds, nullptr, st));
+    MODL_TRY(gather_cols<T>(ctx, B, ldb, k, p, subset, s, Bp, lds, nullptr, st));   // gradient_[:, subset] = B_[:, subset]
+    const bool small_subset = (double)s < (double)p / 2.;
+    if (G_full && small_subset && s > 0)        // G_ -= D_sub D_sub^T   [ref: :667-668]
+        MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, k, k, s, T(-1), Dpanel, lds, Dpanel, lds, T(1), G_full, k, st));
+
+    int32_t *d_order = nullptr;
+    MODL_TRY(upload_order(ctx, h_order, k, &d_order, st));
+    if (mode == 0) {
+        MODL_TRY(bcd_update<T>(ctx, Dpanel, Bp, lds, C, comp_norm, d_order, k, s, comp_l1_ratio, comp_pos, st));
+    } else if (s > 0) {
+        // 'sgd' branch [ref: :695-708]: no sequential dependency between atoms
+        enet_norm_rows_kernel<T><<<grid_for(ctx, k, 16), 256, 0, st>>>(Dpanel, (int)k, (int)s, lds, comp_l1_ratio,
+                                                                        nullptr, T(1), comp_norm);
+        MODL_LAUNCH_CHECK(ctx);
+        // grad = B_sub - C . D_sub
+        MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_NMAJOR, k, s, k, T(-1), C, k, Dpanel, lds, T(1), Bp, lds, st));
+        axpy_kernel<T><<<grid_for(ctx, ceil_div(k * lds, 256), 8), 256, 0, st>>>(Dpanel, Bp, k * lds,
+                                                                                 (T)(w * step_size));
+        MODL_LAUNCH_CHECK(ctx);
+        enet_projection_rows_kernel<T><<<grid_for(ctx, k, 16), 256, 0, st>>>(Dpanel, Dpanel, (int)k, (int)s, lds,
+                                                                              comp_norm, comp_l1_ratio);
+        MODL_LAUNCH_CHECK(ctx);
+        enet_norm_rows_kernel<T><<<grid_for(ctx, k, 16), 256, 0, st>>>(Dpanel, (int)k, (int)s, lds, comp_l1_ratio,
+                                                                        nullptr, T(-1), comp_norm);
+        MODL_LAUNCH_CHECK(ctx);
+    }
+    MODL_TRY(scatter_cols<T>(ctx, Dpanel, lds, k, subset, s, components, ldd, st));   // [ref: :709]
+    if (G_full) {                                                                       // [ref: :711-715]
+        if (small_subset) {
+            if (s > 0)
+                MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, k, k, s, T(1), Dpanel, lds, Dpanel, lds, T(1), G_full, k, st));
+        } else {
+            MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, k, k, p, T(1), components, ldd, components, ldd, T(0), G_full, k, st));
+        }
+    }
+    return MODL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// typed implementations behind the C entry points
+// ---------------------------------------------------------------------------------------
+template <typename T>
+static int enet_norm_impl(modl_ctx *ctx, const T *v, int64_t rows, int64_t n, int64_t ld, T l1_ratio, T *out, void *stream)
+{
+    MODL_REQUIRE(ctx && v && out && rows >= 0 && n >= 0, "enet_norm arguments");
+    if (rows == 0) return MODL_OK;
+    enet_norm_rows_kernel<T><<<grid_for(ctx, rows, 16), 256, 0, (cudaStream_t)stream>>>(v, (int)rows, (int)n, ld, l1_ratio,
+                                                                                         out, T(0), nullptr);
+    MODL_LAUNCH_CHECK(ctx);
+    return MODL_OK;
+}
+
+template <typename T>
+static int enet_projection_impl(modl_ctx *ctx, const T *v, T *out, int64_t rows, int64_t n, int64_t ld, const T *radius,
+                                T l1_ratio, void *stream)
+{
+    MODL_REQUIRE(ctx && v && out && radius && rows >= 0 && n >= 0, "enet_projection arguments");
+    if (rows == 0) return MODL_OK;
+    enet_projection_rows_kernel<T><<<grid_for(ctx, rows, 16), 256, 0, (cudaStream_t)stream>>>(v, out, (int)rows, (int)n, ld,
+                                                                                               radius, l1_ratio);
+    MODL_LAUNCH_CHECK(ctx);
+    return MODL_OK;
+}
+
+template <typename T>
+static int enet_scale_impl(modl_ctx *ctx, T *X, int64_t rows, int64_t n, int64_t ld, T l1_ratio, T radius, void *stream)
+{
+    MODL_REQUIRE(ctx && X && rows >= 0 && n >= 0, "enet_scale arguments");
+    if (rows == 0) return MODL_OK;
+    enet_scale_rows_kernel<T><<<grid_for(ctx, rows, 16), 256, 0, (cudaStream_t)stream>>>(X, (int)rows, (int)n, ld, l1_ratio, radius);
+    MODL_LAUNCH_CHECK(ctx);
+    return MODL_OK;
+}
+
+// G / Dx / xnorm2 products; panel (optional out): where D_sub (k x s) was left
+template <typename T>
+static int gram_dx_impl(modl_ctx *ctx, const T *D, int64_t ldd, const T *X, int64_t ldx, const int64_t *subset, int64_t s,
+                        int64_t k, int64_t b, int64_t p, T scale, T *G, T *Dx, T *xnorm2, T **panel_out, cudaStream_t st)
+{
+    MODL_REQUIRE(ctx && D && k >= 1 && p >= 1 && b >= 0, "gram_dx arguments");
+    MODL_REQUIRE(X != nullptr || (Dx == nullptr && xnorm2 == nullptr), "X required for Dx / xnorm2");
+    if (subset == nullptr) {
+        if (xnorm2 && b > 0) MODL_TRY(gather_cols<T>(ctx, X, ldx, b, p, nullptr, 0, (T *)nullptr, 0, xnorm2, st));
+        if (G) MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, k, k, p, scale, D, ldd, D, ldd, T(0), G, k, st));
+        if (Dx && b > 0) MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, b, k, p, scale, X, ldx, D, ldd, T(0), Dx, k, st));
+        if (panel_out) *panel_out = nullptr;
+        return MODL_OK;
+    }
+    MODL_REQUIRE(s >= 0 && s <= p, "subset length");
+    const int64_t lds = s > 0 ? s : 1;
+    T *panel = nullptr;
+    MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)((k + b) * lds), &panel));
+    T *Dsub = panel, *Xsub = panel + k * lds;
+    MODL_TRY(gather_cols<T>(ctx, D, ldd, k, p, subset, s, Dsub, lds, nullptr, st));
+    if (b > 0 && (Dx || xnorm2))
+        MODL_TRY(gather_cols<T>(ctx, X, ldx, b, p, subset, s, Dx ? Xsub : (T *)nullptr, lds, xnorm2, st));
+    if (G) MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, k, k, s, scale, Dsub, lds, Dsub, lds, T(0), G, k, st));
+    if (Dx && b > 0) MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, b, k, s, scale, Xsub, lds, Dsub, lds, T(0), Dx, k, st));
+    if (panel_out) *panel_out = Dsub;
+    return MODL_OK;
+}
+
+template <typename T>
+static int regression_entry(modl_ctx *ctx, const T *G, int64_t g_stride, T *Dx, const T *X, int64_t ldx, int64_t p,
+                            const T *xnorm2, T *code, const int64_t *indices, int64_t b, int64_t k, T l1_ratio, T alpha,
+                            int positive, T tol, int max_iter, int32_t *sweeps, void *stream)
+{
+    MODL_REQUIRE(ctx && G && Dx && code && b >= 0 && k >= 1, "regression arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const T *norms = xnorm2;
+    if (l1_ratio != T(0) && norms == nullptr && b > 0) {
+        MODL_REQUIRE(X != nullptr && p >= 1, "CD needs the data rows X (or xnorm2) for its stop test");
+        T *tmp = nullptr;
+        MODL_TRY(ws<T>(ctx, WS_XNORM, (size_t)b, &tmp));
+        MODL_TRY(gather_cols<T>(ctx, X, ldx, b, p, nullptr, 0, (T *)nullptr, 0, tmp, st));
+        norms = tmp;
+    }
+    return regression<T>(ctx, G, g_stride, Dx, norms, code, indices, nullptr, b, k, l1_ratio, alpha, positive, tol,
+                         max_iter, sweeps, st);
+}
+
+template <typename T>
+static int update_stats_impl(modl_ctx *ctx, const T *code, const int64_t *indices, const T *X, int64_t ldx, T *C, T *B,
+                             int64_t ldb, double w, int64_t b, int64_t k, int64_t p, int overwrite, cudaStream_t st)
+{
+    MODL_REQUIRE(ctx && code && b >= 1 && k >= 1, "update_stats arguments");
+    const T *cb = code;
+    if (indices) {
+        T *tmp = nullptr;
+        MODL_TRY(ws<T>(ctx, WS_CODE_BATCH, (size_t)(b * k), &tmp));
+        gather_rows_kernel<T><<<grid_for(ctx, b, 16), 128, 0, st>>>(code, k, indices, (int)b, (int)k, tmp, k);
+        MODL_LAUNCH_CHECK(ctx);
+        cb = tmp;
+    }
+    const T a = overwrite ? (T)(1.0 / (double)b) : (T)(w / (double)b);
+    const T be = overwrite ? T(0) : (T)(1.0 - w);
+    if (C) MODL_TRY(gemm_simt<T>(ctx, A_MMAJOR, B_NMAJOR, k, k, b, a, cb, k, cb, k, be, C, k, st));
+    if (B) {
+        MODL_REQUIRE(X != nullptr && p >= 1, "X required for the B_ update");
+        MODL_TRY(gemm_simt<T>(ctx, A_MMAJOR, B_NMAJOR, k, p, b, a, cb, k, X, ldx, be, B, ldb, st));
+    }
+    return MODL_OK;
+}
+
+template <typename T>
+static int update_dict_entry(modl_ctx *ctx, T *components, int64_t ldd, const T *B, int64_t ldb, const T *C, T *comp_norm,
+                             T *G_full, const int64_t *subset, int64_t s, const int64_t *h_order, int64_t k, int64_t p,
+                             T comp_l1_ratio, int comp_pos, int mode, double w, double step_size, void *stream)
+{
+    MODL_REQUIRE(ctx && components && B && C && comp_norm && subset && h_order, "update_dict arguments");
+    MODL_REQUIRE(s >= 0 && s <= p, "subset length");
+    T *panel = nullptr;
+    MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)(k * (s > 0 ? s : 1)), &panel));
+    return update_dict_impl<T>(ctx, components, ldd, B, ldb, C, comp_norm, G_full, subset, s, h_order, k, p, comp_l1_ratio,
+                               comp_pos, mode, w, step_size, panel, false, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------
+// the fused step  [ref: dict_fact.py:507-533, 577-648]
+// ---------------------------------------------------------------------------------------
+template <typename T>
+static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream)
+{
+    MODL_REQUIRE(ctx && q, "null arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t k = q->n_components, b = q->batch_size, p = q->n_features, s = q->subset_len;
+    MODL_REQUIRE(k >= 1 && b >= 1 && p >= 1 && q->n_samples >= 1, "shapes");
+    MODL_REQUIRE(q->X && q->components && q->code && q->C && q->B && q->comp_norm, "state pointers");
+    MODL_REQUIRE(q->h_subset && q->h_order && s >= 0 && s <= p, "subset / order");
+    MODL_REQUIRE(q->Dx_agg >= 0 && q->Dx_agg <= 2 && q->G_agg >= 0 && q->G_agg <= 2, "aggregation mode");
+    MODL_REQUIRE(q->G_agg != MODL_AGG_FULL || q->G_full, "G_agg='full' needs G_full");
+    MODL_REQUIRE(q->G_agg != MODL_AGG_AVERAGE || (q->G_average && q->w_sample), "G_agg='average' needs G_average, w_sample");
+    MODL_REQUIRE(q->Dx_agg != MODL_AGG_AVERAGE || (q->Dx_average && q->w_sample), "Dx_agg='average' needs Dx_average, w_sample");
+    const T *X = static_cast<const T *>(q->X);
+    T *D = static_cast<T *>(q->components);
+    T *code = static_cast<T *>(q->code);
+    const T r = (T)q->reduction;
+
+    // subset -> device
+    int64_t *d_subset = nullptr;
+    MODL_TRY(ws<int64_t>(ctx, WS_SUBSET, (size_t)(s > 0 ? s : 1), &d_subset));
+    if (s > 0)
+        MODL_CUDA_TRY(cudaMemcpyAsync(d_subset, q->h_subset, sizeof(int64_t) * (size_t)s, cudaMemcpyHostToDevice, st));
+
+    T *xnorm2 = nullptr, *Gw = nullptr, *Dxw = nullptr, *cb = nullptr, *panel = nullptr;
+    MODL_TRY(ws<T>(ctx, WS_XNORM, (size_t)b, &xnorm2));
+    MODL_TRY(ws<T>(ctx, WS_G, (size_t)(k * k), &Gw));
+    MODL_TRY(ws<T>(ctx, WS_DX, (size_t)(b * k), &Dxw));
+    MODL_TRY(ws<T>(ctx, WS_CODE_BATCH, (size_t)(b * k), &cb));
+
+    // ---- _compute_code [ref: :577-648] ----
+    const bool need_sub = q->Dx_agg != MODL_AGG_FULL || q->G_agg != MODL_AGG_FULL;
+    const bool dx_sub = q->Dx_agg != MODL_AGG_FULL;
+    const bool g_sub = q->G_agg != MODL_AGG_FULL;
+    if (need_sub) {
+        MODL_TRY(gram_dx_impl<T>(ctx, D, p, X, q->ldx, d_subset, s, k, b, p, r, g_sub ? Gw : (T *)nullptr,
+                                 dx_sub ? Dxw : (T *)nullptr, xnorm2, &panel, st));
+    }
+    if (!dx_sub) {   // Dx = X . D^T over all features [ref: :592]
+        MODL_TRY(gram_dx_impl<T>(ctx, D, p, X, q->ldx, nullptr, 0, k, b, p, T(1), (T *)nullptr, Dxw,
+                                 need_sub ? (T *)nullptr : xnorm2, nullptr, st));
+    }
+    if (q->Dx_agg == MODL_AGG_AVERAGE) {
+        update_dx_average_kernel<T><<<grid_for(ctx, b, 16), 128, 0, st>>>(static_cast<T *>(q->Dx_average), Dxw,
+                                                                          static_cast<const T *>(q->w_sample), q->indices, (int)b, (int)k);
+        MODL_LAUNCH_CHECK(ctx);
+    }
+    const T *Guse = Gw;
+    int64_t g_stride = 0;
+    T *g_rows = nullptr;
+    if (q->G_agg == MODL_AGG_FULL) {
+        Guse = static_cast<const T *>(q->G_full);
+    } else if (q->G_agg == MODL_AGG_AVERAGE) {
+        T *Gav = static_cast<T *>(q->G_average);
+        dim3 grid((unsigned)grid_for(ctx, ceil_div(k * k, 256), 2), (unsigned)(b < 65535 ? b : 65535));
+        update_g_average_kernel<T><<<grid, 256, 0, st>>>(Gav, Gw, static_cast<const T *>(q->w_sample), q->indices, (int)b, k * k);
+        MODL_LAUNCH_CHECK(ctx);
+        if (q->indices) {   // the solver wants the batch's matrices contiguous: gather the rows
+            MODL_TRY(ws<T>(ctx, WS_GROWS, (size_t)(b * k * k), &g_rows));
+            gather_rows_kernel<T><<<grid_for(ctx, b, 16), 256, 0, st>>>(Gav, k * k, q->indices, (int)b, (int)(k * k), g_rows, k * k);
+            MODL_LAUNCH_CHECK(ctx);
+            Guse = g_rows;
+        } else {
+            Guse = Gav;
+        }
+        g_stride = k * k;
+    }
+    MODL_TRY(regression<T>(ctx, Guse, g_stride, Dxw, xnorm2, code, q->indices, cb, b, k, (T)q->code_l1_ratio,
+                           (T)q->code_alpha, q->code_pos, (T)q->tol, q->max_iter, q->sweeps, st));
+
+    // ---- _update_C / _update_B [ref: :559-575] ----
+    MODL_TRY(update_stats_impl<T>(ctx, cb, nullptr, X, q->ldx, static_cast<T *>(q->C), static_cast<T *>(q->B), p, q->w, b, k,
+                                  p, q->optimizer_sgd, st));
+
+    // ---- _update_dict [ref: :650-715] ----
+    T *Dpanel = panel;
+    bool ready = panel != nullptr;
+    if (!ready) MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)(k * (s > 0 ? s : 1)), &Dpanel));
+    MODL_TRY(update_dict_impl<T>(ctx, D, p, static_cast<const T *>(q->B), p, static_cast<const T *>(q->C),
+                                 static_cast<T *>(q->comp_norm), q->G_agg == MODL_AGG_FULL ? static_cast<T *>(q->G_full) : (T *)nullptr,
+                                 d_subset, s, q->h_order, k, p, (T)q->comp_l1_ratio, q->comp_pos, q->optimizer_sgd ? 1 : 0, q->w,
+                                 q->step_size, Dpanel, ready, st));
+    return MODL_OK;
+}
+
+}  // namespace modl
+
+// ---------------------------------------------------------------------------------------
+// extern "C" shims
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+#define MODL_DEFINE_TYPED(SFX, T)                                                                                           \
+    int modl_enet_norm_##SFX(modl_ctx *c, const T *v, int64_t rows, int64_t n, int64_t ld, T l1, T *out, void *st)          \
+    { return enet_norm_impl<T>(c, v, rows, n, ld, l1, out, st); }                                                           \
+    int modl_enet_projection_##SFX(modl_ctx *c, const T *v, T *out, int64_t rows, int64_t n, int64_t ld, const T *radius,   \
+                                   T l1, void *st)                                                                          \
+    { return enet_projection_impl<T>(c, v, out, rows, n, ld, radius, l1, st); }                                             \
+    int modl_enet_scale_##SFX(modl_ctx *c, T *X, int64_t rows, int64_t n, int64_t ld, T l1, T radius, void *st)             \
+    { return enet_scale_impl<T>(c, X, rows, n, ld, l1, radius, st); }                                                       \
+    int modl_gram_dx_##SFX(modl_ctx *c, const T *D, int64_t ldd, const T *X, int64_t ldx, const int64_t *subset, int64_t s, \
+                           int64_t k, int64_t b, int64_t p, T scale, T *G, T *Dx, T *xnorm2, void *st)                      \
+    { return gram_dx_impl<T>(c, D, ldd, X, ldx, subset, s, k, b, p, scale, G, Dx, xnorm2, nullptr, (cudaStream_t)st); }     \
+    int modl_enet_regression_single_gram_##SFX(modl_ctx *c, const T *G, T *Dx, const T *X, int64_t ldx, int64_t p,          \
+                                               const T *xnorm2, T *code, const int64_t *indices, int64_t b, int64_t k,      \
+                                               T l1, T alpha, int positive, T tol, int max_iter, int32_t *sweeps, void *st) \
+    { return regression_entry<T>(c, G, 0, Dx, X, ldx, p, xnorm2, code, indices, b, k, l1, alpha, positive, tol, max_iter,   \
+                                 sweeps, st); }                                                                             \
+    int modl_enet_regression_multi_gram_##SFX(modl_ctx *c, const T *G, T *Dx, const T *X, int64_t ldx, int64_t p,           \
+                                              const T *xnorm2, T *code, const int64_t *indices, int64_t b, int64_t k,       \
+                                              T l1, T alpha, int positive, T tol, int max_iter, int32_t *sweeps, void *st)  \
+    { return regression_entry<T>(c, G, k * k, Dx, X, ldx, p, xnorm2, code, indices, b, k, l1, alpha, positive, tol,         \
+                                 max_iter, sweeps, st); }                                                                   \
+    int modl_update_G_average_##SFX(modl_ctx *c, T *Gav, const T *G, const T *w, const int64_t *indices, int64_t b,         \
+                                    int64_t k, void *st)                                                                    \
+    {                                                                                                                       \
+        MODL_REQUIRE(c && Gav && G && w && b >= 0 && k >= 1, "update_G_average arguments");                                 \
+        if (b == 0) return MODL_OK;                                                                                         \
+        dim3 grid((unsigned)grid_for(c, ceil_div(k * k, 256), 2), (unsigned)(b < 65535 ? b : 65535));                       \
+        update_g_average_kernel<T><<<grid, 256, 0, (cudaStream_t)st>>>(Gav, G, w, indices, (int)b, k * k);                  \
+        MODL_LAUNCH_CHECK(c);                                                                                               \
+        return MODL_OK;                                                                                                     \
+    }                                                                                                                       \
+    int modl_update_Dx_average_##SFX(modl_ctx *c, T *Dav, T *Dx, const T *w, const int64_t *indices, int64_t b, int64_t k,  \
+                                     void *st)                                                                              \
+    {                                                                                                                       \
+        MODL_REQUIRE(c && Dav && Dx && w && b >= 0 && k >= 1, "update_Dx_average arguments");                               \
+        if (b == 0) return MODL_OK;                                                                                         \
+        update_dx_average_kernel<T><<<grid_for(c, b, 16), 128, 0, (cudaStream_t)st>>>(Dav, Dx, w, indices, (int)b, (int)k); \
+        MODL_LAUNCH_CHECK(c);                                                                                               \
+        return MODL_OK;                                                                                                     \
+    }                                                                                                                       \
+    int modl_update_stats_##SFX(modl_ctx *c, const T *code, const int64_t *indices, const T *X, int64_t ldx, T *C, T *B,    \
+                                int64_t ldb, double w, int64_t b, int64_t k, int64_t p, int overwrite, void *st)            \
+    { return update_stats_impl<T>(c, code, indices, X, ldx, C, B, ldb, w, b, k, p, overwrite, (cudaStream_t)st); }          \
+    int modl_update_dict_##SFX(modl_ctx *c, T *comp, int64_t ldd, const T *B, int64_t ldb, const T *C, T *comp_norm,        \
+                               T *G_full, const int64_t *subset, int64_t s, const int64_t *h_order, int64_t k, int64_t p,   \
+                               T l1, int pos, int mode, double w, double step, void *st)                                    \
+    { return update_dict_entry<T>(c, comp, ldd, B, ldb, C, comp_norm, G_full, subset, s, h_order, k, p, l1, pos, mode, w,   \
+                                  step, st); }                                                                              \
+    int modl_batch_fit_##SFX(modl_ctx *c, const modl_step_params *prm, void *st) { return batch_fit_impl<T>(c, prm, st); }
+
+MODL_DEFINE_TYPED(f32, float)
+MODL_DEFINE_TYPED(f64, double)
+
+}  // extern "C"

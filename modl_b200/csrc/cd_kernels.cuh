@@ -1,0 +1,233 @@
+// cd_kernels.cuh -- batched elastic-net regression by cyclic coordinate descent over a Gram
+// matrix: one warp per sample.
+//
+// Replaces enet_coordinate_descent_gram [ref: modl/decomposition/dict_fact_fast.pyx:270-427]
+// and the per-sample loops that call it (:198-214 shared Gram, :95-112 per-sample Gram).
+//
+// Mapping to the hardware
+//   * A sample's state lives in the registers of ONE warp: lane l holds coordinates
+//     {32 J + l}, J = 0..TILES-1, of w (code), q (= Dx row) and H (= Q w).  k <= 32*TILES.
+//   * Coordinates are visited in the reference's cyclic order (:354-355).  The owner lane
+//     computes the soft-thresholded update; two warp shuffles broadcast (w_old, w_new) and all
+//     lanes apply the rank-1 corrections  H -= w_old Q[c,:],  H += w_new Q[c,:]  as two
+//     separate FMAs, like the reference's two axpy calls (:359-363, :374-377).
+//   * Shared-Gram variant: the k x k Gram is kept in shared memory as its lower triangle of
+//     32 x 32 tiles (k = 256 -> 36 tiles = 144 KB, fits where the full 256 KB matrix does
+//     not).  A tile stores element (a, c) at a*32 + ((a + c) & 31): rows AND
+//     columns of a tile are bank-conflict free, so row c of the symmetric matrix is read as
+//     tile rows left of the diagonal and tile columns below it.
+//   * Per-sample-Gram / large-k variant: rows stream from global memory (coalesced 128 B per
+//     tile column), strided per sample.
+//   * The stop test mirrors the reference arithmetic [ref: :388-427]: sums in the working
+//     precision, the duality-gap combination in double exactly where the Cython float
+//     specialisation promotes (R_norm2, const, A_norm2).
+#pragma once
+#include "common.cuh"
+
+namespace modl {
+
+constexpr int CD_TILE = 32;
+constexpr int CD_TILE_ELEMS = CD_TILE * CD_TILE;
+
+__host__ __device__ inline int cd_tri(int I) { return I * (I + 1) / 2; }
+inline size_t cd_packed_elems(int tiles) { return (size_t)cd_tri(tiles) * CD_TILE_ELEMS; }
+
+// Fill the packed lower-triangular tile image of G in shared memory (whole CTA).
+template <typename T>
+__device__ void cd_load_packed_gram(T *sG, const T *__restrict__ G, int k, int tiles)
+{
+    const int total = cd_tri(tiles) * CD_TILE_ELEMS;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int t = e / CD_TILE_ELEMS, within = e % CD_TILE_ELEMS;
+        int I = 0;
+        while (cd_tri(I + 1) <= t) ++I;
+        const int J = t - cd_tri(I);
+        const int a = within / CD_TILE, c = within % CD_TILE;
+        const int gi = I * CD_TILE + a, gj = J * CD_TILE + c;
+        T v = T(0);
+        if (gi < k && gj < k) v = G[(int64_t)gi * k + gj];
+        sG[t * CD_TILE_ELEMS + a * CD_TILE + ((a + c) & 31)] = v;
+    }
+}
+
+// Row `c = 32*Jc + l` of the symmetric matrix from the packed image; lane gets columns 32*JJ+lane.
+template <typename T, int TILES>
+__device__ __forceinline__ void cd_row_packed(const T *sG, int Jc, int l, int lane, T (&r)[TILES])
+{
+#pragma unroll
+    for (int JJ = 0; JJ < TILES; ++JJ) {
+        if (JJ <= Jc) {
+            r[JJ] = sG[(cd_tri(Jc) + JJ) * CD_TILE_ELEMS + l * CD_TILE + ((l + lane) & 31)];
+        } else {
+            r[JJ] = sG[(cd_tri(JJ) + Jc) * CD_TILE_ELEMS + lane * CD_TILE + ((lane + l) & 31)];
+        }
+    }
+}
+
+template <typename T, int TILES>
+__device__ __forceinline__ void cd_row_global(const T *__restrict__ Gs, int k, int c, int lane, T (&r)[TILES])
+{
+    const T *row = Gs + (int64_t)c * k;
+#pragma unroll
+    for (int JJ = 0; JJ < TILES; ++JJ) {
+        const int col = JJ * CD_TILE + lane;
+        r[JJ] = col < k ? row[col] : T(0);
+    }
+}
+
+template <typename T> struct CdWide { typedef double type; };
+
+// One coordinate-descent solve for the sample owned by this warp.
+template <typename T, int TILES, bool PACKED>
+__device__ __forceinline__ int cd_solve_warp(const T *sG, const T *__restrict__ Gs, int k, int lane,
+                                             T (&w)[TILES], const T (&q)[TILES], T ynorm2, T alpha,
+                                             T beta, T tol, int max_iter, bool positive)
+{
+    T h[TILES], r[TILES];
+    unsigned zmask[TILES];
+    // ---- H = Q w accumulated column by column (Q symmetric)  [ref: :340-347] ----
+#pragma unroll
+    for (int J = 0; J < TILES; ++J) h[J] = T(0);
+#pragma unroll
+    for (int J = 0; J < TILES; ++J) {
+        unsigned zm = 0;
+        for (int l = 0; l < CD_TILE; ++l) {
+            const int c = J * CD_TILE + l;
+            if (c >= k) { zm |= (0xffffffffu << l); break; }
+            const T wc = __shfl_sync(kFullMask, w[J], l);
+            if (PACKED) cd_row_packed<T, TILES>(sG, J, l, lane, r);
+            else        cd_row_global<T, TILES>(Gs, k, c, lane, r);
+            const T diag = __shfl_sync(kFullMask, r[J], l);
+            if (diag == T(0)) zm |= (1u << l);
+            if (wc != T(0)) {
+#pragma unroll
+                for (int JJ = 0; JJ < TILES; ++JJ) h[JJ] = fma(wc, r[JJ], h[JJ]);
+            }
+        }
+        zmask[J] = zm;
+    }
+
+    const T d_w_tol = tol;
+    const T tolv = tol * ynorm2;                         // [ref: :336]
+    int sweeps = 0;
+    for (int it = 0; it < max_iter; ++it) {
+        sweeps = it + 1;
+        T w_max = T(0), d_w_max = T(0);
+#pragma unroll
+        for (int J = 0; J < TILES; ++J) {
+            if (zmask[J] == 0xffffffffu) continue;        // tile entirely padding / zero diagonal
+#pragma unroll 2
+            for (int l = 0; l < CD_TILE; ++l) {
+                if ((zmask[J] >> l) & 1u) continue;       // Q[c,c] == 0 -> skip  [ref: :357-358]
+                const int c = J * CD_TILE + l;
+                if (PACKED) cd_row_packed<T, TILES>(sG, J, l, lane, r);
+                else        cd_row_global<T, TILES>(Gs, k, c, lane, r);
+                const T w_old = __shfl_sync(kFullMask, w[J], l);
+                if (w_old != T(0)) {
+#pragma unroll
+                    for (int JJ = 0; JJ < TILES; ++JJ) h[JJ] = fma(-w_old, r[JJ], h[JJ]);
+                }
+                // candidate for "my" coordinate of tile J; only lane l's value is consumed
+                const T tmp = q[J] - h[J];
+                T cand;
+                if (positive && tmp < T(0)) {
+                    cand = T(0);
+                } else {
+                    const T mag = t_abs(tmp) - alpha;
+                    const T m = mag > T(0) ? mag : T(0);
+                    cand = (tmp < T(0) ? -m : m) / (r[J] + beta);      // r[J] on lane l is Q[c,c]
+                }
+                const T w_new = __shfl_sync(kFullMask, cand, l);
+                if (lane == l) w[J] = w_new;
+                if (w_new != T(0)) {
+#pragma unroll
+                    for (int JJ = 0; JJ < TILES; ++JJ) h[JJ] = fma(w_new, r[JJ], h[JJ]);
+                }
+                const T d = t_abs(w_new - w_old);
+                if (d > d_w_max) d_w_max = d;
+                const T aw = t_abs(w_new);
+                if (aw > w_max) w_max = aw;
+            }
+        }
+        if (w_max == T(0) || d_w_max / w_max < d_w_tol || it == max_iter - 1) {
+            // ---- duality gap  [ref: :388-427] ----
+            T qw = T(0), wh = T(0), w2 = T(0), l1 = T(0);
+            T dual = positive ? -INFINITY : T(0);
+#pragma unroll
+            for (int J = 0; J < TILES; ++J) {
+                const bool real = (J * CD_TILE + lane) < k;
+                qw = fma(w[J], q[J], qw);
+                wh = fma(w[J], h[J], wh);
+                w2 = fma(w[J], w[J], w2);
+                l1 += t_abs(w[J]);
+                const T xta = q[J] - h[J] - beta * w[J];
+                if (real) {
+                    const T cmp = positive ? xta : t_abs(xta);
+                    if (cmp > dual) dual = cmp;
+                }
+            }
+            qw = warp_sum(qw); wh = warp_sum(wh); w2 = warp_sum(w2); l1 = warp_sum(l1);
+            dual = warp_max(dual);
+            const double R_norm2 = (double)(ynorm2 + wh) - 2.0 * (double)qw;
+            double cst;
+            T gap;
+            if (dual > alpha) {
+                cst = (double)alpha / (double)dual;
+                const double A_norm2 = R_norm2 * (cst * cst);
+                gap = (T)(0.5 * (R_norm2 + A_norm2));
+            } else {
+                cst = 1.0;
+                gap = (T)R_norm2;
+            }
+            gap = (T)((double)gap + ((((double)(alpha * l1) - cst * (double)ynorm2) + cst * (double)qw)
+                                     + ((0.5 * (double)beta) * (1.0 + cst * cst)) * (double)w2));
+            if (gap < tolv) break;
+        }
+    }
+    return sweeps;
+}
+
+// grid: any; block: 32 * warps.  Dynamic smem (PACKED): cd_packed_elems(TILES) * sizeof(T).
+// g_stride: elements between consecutive per-sample Gram matrices (0 = one shared Gram).
+template <typename T, int TILES, bool PACKED>
+__global__ void cd_regression_kernel(const T *__restrict__ G, int64_t g_stride, const T *__restrict__ Dx,
+                                     const T *__restrict__ xnorm2, T *__restrict__ code,
+                                     const int64_t *__restrict__ indices, T *__restrict__ code_batch,
+                                     int b, int k, T alpha, T beta, T tol, int max_iter, int positive,
+                                     int32_t *__restrict__ sweeps_out)
+{
+    extern __shared__ __align__(16) unsigned char cd_smem_raw[];
+    T *sG = reinterpret_cast<T *>(cd_smem_raw);
+    if (PACKED) {
+        cd_load_packed_gram<T>(sG, G, k, TILES);
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int warps = blockDim.x >> 5;
+    for (int ii = blockIdx.x * warps + (threadIdx.x >> 5); ii < b; ii += gridDim.x * warps) {
+        const int64_t row = indices ? indices[ii] : (int64_t)ii;
+        T *wrow = code + row * k;
+        const T *qrow = Dx + (int64_t)ii * k;
+        T w[TILES], q[TILES];
+#pragma unroll
+        for (int J = 0; J < TILES; ++J) {
+            const int c = J * CD_TILE + lane;
+            w[J] = c < k ? wrow[c] : T(0);
+            q[J] = c < k ? qrow[c] : T(0);
+        }
+        const T *Gs = G + (int64_t)ii * g_stride;
+        const int sw = cd_solve_warp<T, TILES, PACKED>(sG, Gs, k, lane, w, q, xnorm2[ii], alpha, beta, tol,
+                                                       max_iter, positive != 0);
+#pragma unroll
+        for (int J = 0; J < TILES; ++J) {
+            const int c = J * CD_TILE + lane;
+            if (c < k) {
+                wrow[c] = w[J];
+                if (code_batch) code_batch[(int64_t)ii * k + c] = w[J];
+            }
+        }
+        if (sweeps_out && lane == 0) sweeps_out[ii] = sw;
+    }
+}
+
+}  // namespace modl

@@ -1,0 +1,153 @@
+// common.cuh -- shared plumbing of the sm_100a kernels: context, workspace arena, error
+// reporting, warp/block reduction helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/modl_b200.h"
+
+namespace modl {
+
+void set_error(const char *fmt, ...);
+
+#define MODL_CUDA_TRY(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ::modl::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,              \
+                              cudaGetErrorString(_e));                                   \
+            return MODL_ECUDA;                                                           \
+        }                                                                                \
+    } while (0)
+
+#define MODL_TRY(expr)                  \
+    do {                                \
+        int _s = (expr);                \
+        if (_s != MODL_OK) return _s;   \
+    } while (0)
+
+#define MODL_REQUIRE(cond, msg)                                                 \
+    do {                                                                        \
+        if (!(cond)) {                                                          \
+            ::modl::set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, msg); \
+            return MODL_EINVAL;                                                 \
+        }                                                                       \
+    } while (0)
+
+// check the launch that was just issued
+#define MODL_LAUNCH_CHECK(ctx)                \
+    do {                                      \
+        (ctx)->launches += 1;                 \
+        MODL_CUDA_TRY(cudaGetLastError());    \
+    } while (0)
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// Named, grow-only device scratch slots.  A slot keeps its allocation across calls, so the
+// steady-state minibatch loop performs no cudaMalloc.  All work is stream-ordered on the
+// caller's stream; slots are reused call after call on that same stream.
+enum WsSlot {
+    WS_SUBSET = 0,   // int64[s]
+    WS_ORDER,        // int32[k]
+    WS_PANEL_DX,     // [D_sub ; X_sub]  (k+b) x s_pad
+    WS_PANEL_B,      // B_sub / gradient panel  k x s_pad
+    WS_XNORM,        // real[b]
+    WS_G,            // k x k
+    WS_DX,           // b x k
+    WS_CODE_BATCH,   // b x k
+    WS_GEMM_PART,    // split-K partials
+    WS_BCD_SYNC,     // barrier counter + partial sums + v rows
+    WS_CHOL,         // k x k factor (x b for per-sample Grams)
+    WS_GROWS,        // gathered per-sample Gram matrices
+    WS_MISC,         // small scalars
+    WS_INFO,         // int status flags
+    WS_COUNT
+};
+
+}  // namespace modl
+
+struct modl_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    int cluster_ok = 0;
+    int64_t launches = 0;
+    // tunables (modl_ctx_set_option)
+    int opt_bcd_cluster = 16;     // largest thread-block cluster tried by the dictionary update (0 = never)
+    int opt_cd_warps = 0;         // warps per CTA of the CD kernel (0 = auto)
+    int opt_force_global_gram = 0;// debug: never keep the Gram in shared memory
+    void *slot_ptr[modl::WS_COUNT] = {};
+    size_t slot_bytes[modl::WS_COUNT] = {};
+
+    // returns a device pointer with at least `bytes` capacity (grow-only)
+    int reserve(modl::WsSlot slot, size_t bytes, void **out);
+};
+
+namespace modl {
+
+template <typename T>
+inline int ws(modl_ctx *ctx, WsSlot slot, size_t count, T **out) {
+    void *p = nullptr;
+    int st = ctx->reserve(slot, count * sizeof(T), &p);
+    *out = static_cast<T *>(p);
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T u = __shfl_xor_sync(kFullMask, v, o);
+        v = u > v ? u : v;
+    }
+    return v;
+}
+
+// Block-wide sum; every thread gets the result.  `scratch` holds >= 33 elements of T.
+// Deterministic (fixed tree).  Contains __syncthreads().
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T *scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();   // protect scratch from a previous use
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        T t = lane < nw ? scratch[lane] : T(0);
+        t = warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+template <typename T> __device__ __forceinline__ T t_abs(T x);
+template <> __device__ __forceinline__ float t_abs<float>(float x) { return fabsf(x); }
+template <> __device__ __forceinline__ double t_abs<double>(double x) { return fabs(x); }
+template <typename T> __device__ __forceinline__ T t_sqrt(T x);
+template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
+template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
+template <typename T> __device__ __forceinline__ T t_max(T a, T b) { return a > b ? a : b; }
+
+#endif  // __CUDACC__
+
+}  // namespace modl
