@@ -90,6 +90,24 @@ int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value);
  * dict_fact_fast.pyx:88-92, 188-192), else MODL_OK.  Clears the flag. */
 int modl_ctx_check_info(modl_ctx *ctx, void *stream);
 
+/* Per-phase device timing of modl_batch_fit_* (CUDA events on the caller's stream; while
+ * enabled every step ends with a host synchronisation, so use it in a dedicated pass).
+ * modl_ctx_profile(ctx, 1) resets the counters; modl_ctx_profile_read copies the accumulated
+ * milliseconds per phase (h_ms[MODL_PROF_PHASES]) and the number of steps measured. */
+enum {
+    MODL_PROF_GATHER = 0,   /* subset upload, column gathers, row norms          */
+    MODL_PROF_GRAM = 1,     /* G and Dx products                                  */
+    MODL_PROF_AVERAGE = 2,  /* Dx_average_/G_average_ running averages            */
+    MODL_PROF_CODE = 3,     /* coordinate descent / Cholesky code solve           */
+    MODL_PROF_STATS = 4,    /* C_ and B_ accumulation                             */
+    MODL_PROF_DICT_PREP = 5,/* B_[:, subset] gather, G_ downdate, order upload    */
+    MODL_PROF_DICT_BCD = 6, /* sequential atom update kernel                      */
+    MODL_PROF_DICT_POST = 7,/* scatter into components_, G_ update                */
+    MODL_PROF_PHASES = 8
+};
+int modl_ctx_profile(modl_ctx *ctx, int enable);
+int modl_ctx_profile_read(modl_ctx *ctx, double *h_ms, int64_t *h_steps);
+
 /* ------------------------------------------------------------------------------------
  * Elastic-net ball helpers   [ref: modl/utils/math/enet.pxd:10-16]
  * ---------------------------------------------------------------------------------- */

@@ -65,6 +65,8 @@ def _declare(L):
     fn("modl_ctx_launch_count", i64, [vp])
     fn("modl_ctx_set_option", ci, [vp, C.c_char_p, ci])
     fn("modl_ctx_check_info", ci, [vp, vp])
+    fn("modl_ctx_profile", ci, [vp, ci])
+    fn("modl_ctx_profile_read", ci, [vp, vp, vp])
     for sfx, real in (("f32", f32), ("f64", f64)):
         fn("modl_enet_norm_" + sfx, ci, [vp, vp, i64, i64, i64, real, vp, vp])
         fn("modl_enet_projection_" + sfx, ci, [vp, vp, vp, i64, i64, i64, vp, real, vp])
@@ -86,7 +88,8 @@ EXPORTED = (
      "modl_rs_randint", "modl_rs_binomial", "modl_rs_permutation", "modl_rs_shuffle",
      "modl_rs_shuffle_with_trace", "modl_sampler_create", "modl_sampler_destroy",
      "modl_sampler_yield_subset", "modl_batch_weight", "modl_ctx_create", "modl_ctx_destroy",
-     "modl_ctx_sm_count", "modl_ctx_launch_count", "modl_ctx_set_option", "modl_ctx_check_info"]
+     "modl_ctx_sm_count", "modl_ctx_launch_count", "modl_ctx_set_option", "modl_ctx_check_info",
+     "modl_ctx_profile", "modl_ctx_profile_read"]
     + [n + s for s in ("f32", "f64") for n in (
         "modl_enet_norm_", "modl_enet_projection_", "modl_enet_scale_", "modl_gram_dx_",
         "modl_enet_regression_single_gram_", "modl_enet_regression_multi_gram_",
@@ -137,6 +140,18 @@ class Context(object):
 
     def set_option(self, name, value):
         check(lib().modl_ctx_set_option(self.handle, name.encode(), int(value)))
+
+    PHASES = ("gather", "gram", "average", "code", "stats", "dict_prep", "dict_bcd", "dict_post")
+
+    def profile(self, enable):
+        check(lib().modl_ctx_profile(self.handle, int(bool(enable))))
+
+    def profile_read(self):
+        """-> ({phase: total_ms}, steps) accumulated since profile(True)."""
+        ms = (C.c_double * len(self.PHASES))()
+        steps = C.c_int64(0)
+        check(lib().modl_ctx_profile_read(self.handle, ms, C.byref(steps)))
+        return dict(zip(self.PHASES, list(ms))), int(steps.value)
 
     def check_info(self, stream):
         check(lib().modl_ctx_check_info(self.handle, vp(stream)))

@@ -97,6 +97,29 @@ int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value)
     return MODL_OK;
 }
 
+int modl_ctx_profile(modl_ctx *ctx, int enable)
+{
+    MODL_REQUIRE(ctx, "null ctx");
+    if (enable && !ctx->prof_ev[0]) {
+        for (int i = 0; i < 33; ++i) MODL_CUDA_TRY(cudaEventCreate(&ctx->prof_ev[i]));
+    }
+    ctx->prof_on = enable ? 1 : 0;
+    ctx->prof_n = 0;
+    if (enable) {
+        for (int i = 0; i < MODL_PROF_PHASES; ++i) ctx->prof_ms[i] = 0;
+        ctx->prof_steps = 0;
+    }
+    return MODL_OK;
+}
+
+int modl_ctx_profile_read(modl_ctx *ctx, double *h_ms, int64_t *h_steps)
+{
+    MODL_REQUIRE(ctx && h_ms && h_steps, "null");
+    for (int i = 0; i < MODL_PROF_PHASES; ++i) h_ms[i] = ctx->prof_ms[i];
+    *h_steps = ctx->prof_steps;
+    return MODL_OK;
+}
+
 // Synchronises `stream` and reports (then clears) the sticky numerical status:
 // MODL_ENOTSPD if a Cholesky pivot was non-positive since the last check.
 int modl_ctx_check_info(modl_ctx *ctx, void *stream)
@@ -391,6 +414,7 @@ static int update_dict_impl(modl_ctx *ctx, T *components, int64_t ldd, const T *
     if (k <= 0) return MODL_OK;
     const int64_t lds = s > 0 ? s : 1;
     T *Bp = nullptr;
+    prof_mark(ctx, st, MODL_PROF_DICT_PREP);
     MODL_TRY(ws<T>(ctx, WS_PANEL_B, (size_t)(k * lds), &Bp));
     if (!panel_ready) MODL_TRY(gather_cols<T>(ctx, components, ldd, k, p, subset, s, Dpanel, lds, nullptr, st));
     MODL_TRY(gather_cols<T>(ctx, B, ldb, k, p, subset, s, Bp, lds, nullptr, st));   // gradient_[:, subset] = B_[:, subset]
@@ -400,6 +424,7 @@ static int update_dict_impl(modl_ctx *ctx, T *components, int64_t ldd, const T *
 
     int32_t *d_order = nullptr;
     MODL_TRY(upload_order(ctx, h_order, k, &d_order, st));
+    prof_mark(ctx, st, MODL_PROF_DICT_BCD);
     if (mode == 0) {
         MODL_TRY(bcd_update<T>(ctx, Dpanel, Bp, lds, C, comp_norm, d_order, k, s, comp_l1_ratio, comp_pos, st));
     } else if (s > 0) {
@@ -419,6 +444,7 @@ static int update_dict_impl(modl_ctx *ctx, T *components, int64_t ldd, const T *
                                                                         nullptr, T(-1), comp_norm);
         MODL_LAUNCH_CHECK(ctx);
     }
+    prof_mark(ctx, st, MODL_PROF_DICT_POST);
     MODL_TRY(scatter_cols<T>(ctx, Dpanel, lds, k, subset, s, components, ldd, st));   // [ref: :709]
     if (G_full) {                                                                       // [ref: :711-715]
         if (small_subset) {
@@ -475,7 +501,9 @@ static int gram_dx_impl(modl_ctx *ctx, const T *D, int64_t ldd, const T *X, int6
     MODL_REQUIRE(ctx && D && k >= 1 && p >= 1 && b >= 0, "gram_dx arguments");
     MODL_REQUIRE(X != nullptr || (Dx == nullptr && xnorm2 == nullptr), "X required for Dx / xnorm2");
     if (subset == nullptr) {
+        prof_mark(ctx, st, MODL_PROF_GATHER);
         if (xnorm2 && b > 0) MODL_TRY(gather_cols<T>(ctx, X, ldx, b, p, nullptr, 0, (T *)nullptr, 0, xnorm2, st));
+        prof_mark(ctx, st, MODL_PROF_GRAM);
         if (G) MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, k, k, p, scale, D, ldd, D, ldd, T(0), G, k, st));
         if (Dx && b > 0) MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, b, k, p, scale, X, ldx, D, ldd, T(0), Dx, k, st));
         if (panel_out) *panel_out = nullptr;
@@ -486,9 +514,11 @@ static int gram_dx_impl(modl_ctx *ctx, const T *D, int64_t ldd, const T *X, int6
     T *panel = nullptr;
     MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)((k + b) * lds), &panel));
     T *Dsub = panel, *Xsub = panel + k * lds;
+    prof_mark(ctx, st, MODL_PROF_GATHER);
     MODL_TRY(gather_cols<T>(ctx, D, ldd, k, p, subset, s, Dsub, lds, nullptr, st));
     if (b > 0 && (Dx || xnorm2))
         MODL_TRY(gather_cols<T>(ctx, X, ldx, b, p, subset, s, Dx ? Xsub : (T *)nullptr, lds, xnorm2, st));
+    prof_mark(ctx, st, MODL_PROF_GRAM);
     if (G) MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, k, k, s, scale, Dsub, lds, Dsub, lds, T(0), G, k, st));
     if (Dx && b > 0) MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, b, k, s, scale, Xsub, lds, Dsub, lds, T(0), Dx, k, st));
     if (panel_out) *panel_out = Dsub;
@@ -566,6 +596,8 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     MODL_REQUIRE(q->G_agg != MODL_AGG_FULL || q->G_full, "G_agg='full' needs G_full");
     MODL_REQUIRE(q->G_agg != MODL_AGG_AVERAGE || (q->G_average && q->w_sample), "G_agg='average' needs G_average, w_sample");
     MODL_REQUIRE(q->Dx_agg != MODL_AGG_AVERAGE || (q->Dx_average && q->w_sample), "Dx_agg='average' needs Dx_average, w_sample");
+    ctx->prof_n = 0;
+    prof_mark(ctx, st, MODL_PROF_GATHER);
     const T *X = static_cast<const T *>(q->X);
     T *D = static_cast<T *>(q->components);
     T *code = static_cast<T *>(q->code);
@@ -595,6 +627,7 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
         MODL_TRY(gram_dx_impl<T>(ctx, D, p, X, q->ldx, nullptr, 0, k, b, p, T(1), (T *)nullptr, Dxw,
                                  need_sub ? (T *)nullptr : xnorm2, nullptr, st));
     }
+    prof_mark(ctx, st, MODL_PROF_AVERAGE);
     if (q->Dx_agg == MODL_AGG_AVERAGE) {
         update_dx_average_kernel<T><<<grid_for(ctx, b, 16), 128, 0, st>>>(static_cast<T *>(q->Dx_average), Dxw,
                                                                           static_cast<const T *>(q->w_sample), q->indices, (int)b, (int)k);
@@ -620,10 +653,12 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
         }
         g_stride = k * k;
     }
+    prof_mark(ctx, st, MODL_PROF_CODE);
     MODL_TRY(regression<T>(ctx, Guse, g_stride, Dxw, xnorm2, code, q->indices, cb, b, k, (T)q->code_l1_ratio,
                            (T)q->code_alpha, q->code_pos, (T)q->tol, q->max_iter, q->sweeps, st));
 
     // ---- _update_C / _update_B [ref: :559-575] ----
+    prof_mark(ctx, st, MODL_PROF_STATS);
     MODL_TRY(update_stats_impl<T>(ctx, cb, nullptr, X, q->ldx, static_cast<T *>(q->C), static_cast<T *>(q->B), p, q->w, b, k,
                                   p, q->optimizer_sgd, st));
 
@@ -635,6 +670,17 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
                                  static_cast<T *>(q->comp_norm), q->G_agg == MODL_AGG_FULL ? static_cast<T *>(q->G_full) : (T *)nullptr,
                                  d_subset, s, q->h_order, k, p, (T)q->comp_l1_ratio, q->comp_pos, q->optimizer_sgd ? 1 : 0, q->w,
                                  q->step_size, Dpanel, ready, st));
+    if (ctx->prof_on && ctx->prof_n > 0) {
+        cudaEventRecord(ctx->prof_ev[ctx->prof_n], st);
+        MODL_CUDA_TRY(cudaEventSynchronize(ctx->prof_ev[ctx->prof_n]));
+        for (int i = 0; i < ctx->prof_n; ++i) {
+            float ms = 0;
+            MODL_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->prof_ev[i], ctx->prof_ev[i + 1]));
+            ctx->prof_ms[ctx->prof_phase[i]] += ms;
+        }
+        ctx->prof_steps += 1;
+    }
+    ctx->prof_n = 0;
     return MODL_OK;
 }
 

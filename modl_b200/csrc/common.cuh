@@ -81,6 +81,13 @@ struct modl_ctx {
     int opt_bcd_cluster = 16;     // largest thread-block cluster tried by the dictionary update (0 = never)
     int opt_cd_warps = 0;         // warps per CTA of the CD kernel (0 = auto)
     int opt_force_global_gram = 0;// debug: never keep the Gram in shared memory
+    // optional per-phase device timing of the fused step (modl_ctx_profile)
+    int prof_on = 0;
+    int prof_n = 0;                       // marks recorded in the current step
+    int prof_phase[32] = {};
+    cudaEvent_t prof_ev[33] = {};
+    double prof_ms[MODL_PROF_PHASES] = {};
+    int64_t prof_steps = 0;
     void *slot_ptr[modl::WS_COUNT] = {};
     size_t slot_bytes[modl::WS_COUNT] = {};
 
@@ -89,6 +96,14 @@ struct modl_ctx {
 };
 
 namespace modl {
+
+// "phase `ph` starts now" (no-op unless profiling is on)
+inline void prof_mark(modl_ctx *ctx, cudaStream_t st, int ph) {
+    if (!ctx->prof_on || ctx->prof_n >= 32) return;
+    ctx->prof_phase[ctx->prof_n] = ph;
+    cudaEventRecord(ctx->prof_ev[ctx->prof_n], st);
+    ctx->prof_n += 1;
+}
 
 template <typename T>
 inline int ws(modl_ctx *ctx, WsSlot slot, size_t count, T **out) {
