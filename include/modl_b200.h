@@ -267,7 +267,20 @@ typedef struct modl_step_params {
     int max_iter, code_pos, comp_pos, Dx_agg, G_agg, optimizer_sgd;
     /* diagnostics (optional, device int32[b]) */
     int32_t *sweeps;
+    /* Sample-sharded data parallelism (one process per GPU).  `phases` selects which parts of
+     * the step this call runs (0 = all four, the single-GPU case).  With stats_inc != NULL the
+     * STATS phase does not touch C_/B_ but writes this rank's share of the increments
+     *     stats_inc[0 : k*k]      = (w / global_batch) code^T code
+     *     stats_inc[k*k : k*k+k*p] = (w / global_batch) code^T X
+     * which the caller sums over ranks (NCCL all-reduce over NVLink) before the APPLY phase
+     * folds them in:  C_ = (1-w) C_ + sum,  B_ = (1-w) B_ + sum.  batch_size is the number of
+     * rows THIS rank holds; global_batch (0 = batch_size) the rows of the whole minibatch. */
+    int phases;
+    int64_t global_batch;
+    void *stats_inc;           /* device real[k*k + k*p]                                  */
 } modl_step_params;
+
+enum { MODL_PHASE_CODE = 1, MODL_PHASE_STATS = 2, MODL_PHASE_APPLY = 4, MODL_PHASE_DICT = 8 };
 
 int modl_batch_fit_f32(modl_ctx *, const modl_step_params *prm, void *stream);
 int modl_batch_fit_f64(modl_ctx *, const modl_step_params *prm, void *stream);

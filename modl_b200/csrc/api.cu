@@ -546,7 +546,8 @@ static int regression_entry(modl_ctx *ctx, const T *G, int64_t g_stride, T *Dx, 
 
 template <typename T>
 static int update_stats_impl(modl_ctx *ctx, const T *code, const int64_t *indices, const T *X, int64_t ldx, T *C, T *B,
-                             int64_t ldb, double w, int64_t b, int64_t k, int64_t p, int overwrite, cudaStream_t st)
+                             int64_t ldb, double w, int64_t b, int64_t k, int64_t p, int overwrite, cudaStream_t st,
+                             int64_t global_batch = 0, bool increments_only = false)
 {
     MODL_REQUIRE(ctx && code && b >= 1 && k >= 1, "update_stats arguments");
     const T *cb = code;
@@ -557,8 +558,9 @@ static int update_stats_impl(modl_ctx *ctx, const T *code, const int64_t *indice
         MODL_LAUNCH_CHECK(ctx);
         cb = tmp;
     }
-    const T a = overwrite ? (T)(1.0 / (double)b) : (T)(w / (double)b);
-    const T be = overwrite ? T(0) : (T)(1.0 - w);
+    const double bt = (double)(global_batch > 0 ? global_batch : b);
+    const T a = overwrite ? (T)(1.0 / bt) : (T)(w / bt);
+    const T be = (overwrite || increments_only) ? T(0) : (T)(1.0 - w);
     if (C) MODL_TRY(gemm_simt<T>(ctx, A_MMAJOR, B_NMAJOR, k, k, b, a, cb, k, cb, k, be, C, k, st));
     if (B) {
         MODL_REQUIRE(X != nullptr && p >= 1, "X required for the B_ update");
@@ -602,6 +604,11 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     T *D = static_cast<T *>(q->components);
     T *code = static_cast<T *>(q->code);
     const T r = (T)q->reduction;
+    const int phases = q->phases ? q->phases : (MODL_PHASE_CODE | MODL_PHASE_STATS | MODL_PHASE_APPLY | MODL_PHASE_DICT);
+    T *inc = static_cast<T *>(q->stats_inc);
+    MODL_REQUIRE(!(phases & MODL_PHASE_STATS) || (phases & MODL_PHASE_CODE), "STATS phase needs CODE in the same call");
+    MODL_REQUIRE(inc != nullptr || q->phases == 0 || !(phases & MODL_PHASE_APPLY) || (phases & MODL_PHASE_STATS),
+                 "APPLY without stats_inc");
 
     // subset -> device
     int64_t *d_subset = nullptr;
@@ -615,6 +622,8 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     MODL_TRY(ws<T>(ctx, WS_DX, (size_t)(b * k), &Dxw));
     MODL_TRY(ws<T>(ctx, WS_CODE_BATCH, (size_t)(b * k), &cb));
 
+    T *panel_keep = nullptr;
+    if (phases & MODL_PHASE_CODE) {
     // ---- _compute_code [ref: :577-648] ----
     const bool need_sub = q->Dx_agg != MODL_AGG_FULL || q->G_agg != MODL_AGG_FULL;
     const bool dx_sub = q->Dx_agg != MODL_AGG_FULL;
@@ -657,19 +666,36 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     MODL_TRY(regression<T>(ctx, Guse, g_stride, Dxw, xnorm2, code, q->indices, cb, b, k, (T)q->code_l1_ratio,
                            (T)q->code_alpha, q->code_pos, (T)q->tol, q->max_iter, q->sweeps, st));
 
+    panel_keep = panel;
     // ---- _update_C / _update_B [ref: :559-575] ----
-    prof_mark(ctx, st, MODL_PROF_STATS);
-    MODL_TRY(update_stats_impl<T>(ctx, cb, nullptr, X, q->ldx, static_cast<T *>(q->C), static_cast<T *>(q->B), p, q->w, b, k,
-                                  p, q->optimizer_sgd, st));
-
+    if (phases & MODL_PHASE_STATS) {
+        prof_mark(ctx, st, MODL_PROF_STATS);
+        if (inc)
+            MODL_TRY(update_stats_impl<T>(ctx, cb, nullptr, X, q->ldx, inc, inc + k * k, p, q->w, b, k, p, q->optimizer_sgd,
+                                          st, q->global_batch, true));
+        else
+            MODL_TRY(update_stats_impl<T>(ctx, cb, nullptr, X, q->ldx, static_cast<T *>(q->C), static_cast<T *>(q->B), p,
+                                          q->w, b, k, p, q->optimizer_sgd, st, q->global_batch, false));
+    }
+    }   // MODL_PHASE_CODE
+    if ((phases & MODL_PHASE_APPLY) && inc) {
+        prof_mark(ctx, st, MODL_PROF_STATS);
+        const T keep = q->optimizer_sgd ? T(0) : (T)(1.0 - q->w);
+        xpby_kernel<T><<<grid_for(ctx, ceil_div(k * k, 256), 4), 256, 0, st>>>(static_cast<T *>(q->C), inc, k * k, keep);
+        MODL_LAUNCH_CHECK(ctx);
+        xpby_kernel<T><<<grid_for(ctx, ceil_div(k * p, 256), 8), 256, 0, st>>>(static_cast<T *>(q->B), inc + k * k, k * p, keep);
+        MODL_LAUNCH_CHECK(ctx);
+    }
+    if (phases & MODL_PHASE_DICT) {
     // ---- _update_dict [ref: :650-715] ----
-    T *Dpanel = panel;
-    bool ready = panel != nullptr;
+    T *Dpanel = panel_keep;
+    bool ready = panel_keep != nullptr;
     if (!ready) MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)(k * (s > 0 ? s : 1)), &Dpanel));
     MODL_TRY(update_dict_impl<T>(ctx, D, p, static_cast<const T *>(q->B), p, static_cast<const T *>(q->C),
                                  static_cast<T *>(q->comp_norm), q->G_agg == MODL_AGG_FULL ? static_cast<T *>(q->G_full) : (T *)nullptr,
                                  d_subset, s, q->h_order, k, p, (T)q->comp_l1_ratio, q->comp_pos, q->optimizer_sgd ? 1 : 0, q->w,
                                  q->step_size, Dpanel, ready, st));
+    }   // MODL_PHASE_DICT
     if (ctx->prof_on && ctx->prof_n > 0) {
         cudaEventRecord(ctx->prof_ev[ctx->prof_n], st);
         MODL_CUDA_TRY(cudaEventSynchronize(ctx->prof_ev[ctx->prof_n]));

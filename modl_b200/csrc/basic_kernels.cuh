@@ -77,6 +77,14 @@ __global__ void axpy_kernel(T *y, const T *x, int64_t n, T a)
         y[i] = fma(a, x[i], y[i]);
 }
 
+// y = b * y + x  (flat): folds the all-reduced statistics increments into C_ / B_
+template <typename T>
+__global__ void xpby_kernel(T *y, const T *x, int64_t n, T b)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = (b != T(0)) ? fma(b, y[i], x[i]) : x[i];
+}
+
 // ---------------------------------------------------------------------------------------
 // Running averages of the 'average' estimators.
 //   G_average[row] = (1 - w) G_average[row] + w G        [ref: dict_fact_fast.pyx:217-228]

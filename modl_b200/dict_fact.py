@@ -472,48 +472,45 @@ class DictFact(CodingMixin, BaseEstimator):
             self.callback(self)
 
     # ------------------------------------------------------------------ the hot path
-    def _single_batch_fit(self, X, sample_indices):
-        """One minibatch step; X is a (batch x n_features) CUDA tensor of the estimator dtype
-        [ref: dict_fact.py:495-526]."""
-        if self.verbose and self.verbose_iter_ and self.n_iter_ >= self.verbose_iter_[0]:
-            print('Iteration %i' % self.n_iter_)
-            self.verbose_iter_ = self.verbose_iter_[1:]
-            self._callback()
+    def _host_bookkeeping(self, batch_rows, sample_indices):
+        """The integer / scalar statements of a step, on the host, in the reference's order
+        [ref: dict_fact.py:507-515, :672].  `batch_rows` is the size of the WHOLE minibatch
+        (it differs from len(sample_indices) only under sample sharding)."""
+        subset = self.feature_sampler_.yield_subset(self.reduction)            # [ref: :507]
+        sample_indices = np.ascontiguousarray(sample_indices, dtype=np.int64)
+        self.n_iter_ += batch_rows
+        self.sample_n_iter_[sample_indices] += 1
+        w = _batch_weight(self.n_iter_, batch_rows, self.learning_rate, 0)    # [ref: :515]
+        order = np.ascontiguousarray(self.random_state.permutation(self.n_components), dtype=np.int64)  # [ref: :672]
+        w_sample = None
+        if self.G_agg == 'average' or self.Dx_agg == 'average':
+            this_n_iter = self.sample_n_iter_[sample_indices]
+            w_sample = np.power(this_n_iter, -self.sample_learning_rate).astype(self._np_dtype)   # [ref: :513]
+        return subset, sample_indices, w, order, w_sample
+
+    def _launch_step(self, X, sample_indices, subset, order, w, w_sample, phases=0, stats_inc=None,
+                     global_batch=0):
+        """One call into the C ABI (`modl_batch_fit_*`): all device work of the step."""
         dev = self._device
         D = self._d_components_
         k, p = D.shape
         b = X.shape[0]
         if X.stride(1) != 1:
             X = X.contiguous()
-
-        subset = self.feature_sampler_.yield_subset(self.reduction)            # [ref: :507]
-        sample_indices = np.ascontiguousarray(sample_indices, dtype=np.int64)
-        self.n_iter_ += b
-        self.sample_n_iter_[sample_indices] += 1
-        w = _batch_weight(self.n_iter_, b, self.learning_rate, 0)             # [ref: :515]
-        order = np.ascontiguousarray(self.random_state.permutation(k), dtype=np.int64)   # [ref: :672]
-
-        need_avg = self.G_agg == 'average' or self.Dx_agg == 'average'
-        w_sample = None
-        if need_avg:
-            this_n_iter = self.sample_n_iter_[sample_indices]
-            w_sample = torch.from_numpy(
-                np.power(this_n_iter, -self.sample_learning_rate).astype(self._np_dtype)).to(dev)   # [ref: :513]
+        w_dev = torch.from_numpy(w_sample).to(dev) if w_sample is not None else None
         idx_dev = torch.from_numpy(sample_indices).to(dev, non_blocking=True)
-
         prm = _lib.StepParams()
         prm.n_samples, prm.n_features, prm.n_components, prm.batch_size = self._d_code_.shape[0], p, k, b
         prm.X, prm.ldx = X.data_ptr(), X.stride(0)
         prm.indices = idx_dev.data_ptr()
         prm.h_subset, prm.subset_len = subset.ctypes.data, subset.shape[0]
         prm.h_order = order.ctypes.data
-        prm.w_sample = w_sample.data_ptr() if w_sample is not None else None
+        prm.w_sample = w_dev.data_ptr() if w_dev is not None else None
         prm.w = w
         prm.components, prm.code = D.data_ptr(), self._d_code_.data_ptr()
         prm.C, prm.B, prm.comp_norm = self._d_C_.data_ptr(), self._d_B_.data_ptr(), self._d_comp_norm_.data_ptr()
-        for name in ("G_full", "Dx_average", "G_average"):
-            t = self.__dict__.get({"G_full": "_d_G_", "Dx_average": "_d_Dx_average_",
-                                   "G_average": "_d_G_average_"}[name])
+        for name, slot in (("G_full", "_d_G_"), ("Dx_average", "_d_Dx_average_"), ("G_average", "_d_G_average_")):
+            t = self.__dict__.get(slot)
             setattr(prm, name, t.data_ptr() if t is not None else None)
         prm.reduction, prm.code_alpha = float(self.reduction), float(self.code_alpha)
         prm.code_l1_ratio, prm.comp_l1_ratio = float(self.code_l1_ratio), float(self.comp_l1_ratio)
@@ -521,6 +518,8 @@ class DictFact(CodingMixin, BaseEstimator):
         prm.code_pos, prm.comp_pos = int(bool(self.code_pos)), int(bool(self.comp_pos))
         prm.Dx_agg, prm.G_agg = _lib.AGG[self.Dx_agg], _lib.AGG[self.G_agg]
         prm.optimizer_sgd = int(self.optimizer == 'sgd')
+        prm.phases, prm.global_batch = int(phases), int(global_batch)
+        prm.stats_inc = stats_inc.data_ptr() if stats_inc is not None else None
         sw = self.__dict__.get("_d_sweeps")
         if self.__dict__.get("record_sweeps", False):
             if sw is None or sw.shape[0] < b:
@@ -531,7 +530,17 @@ class DictFact(CodingMixin, BaseEstimator):
         fn = getattr(_lib.lib(), "modl_batch_fit_" + _lib.sfx_of(D.dtype))
         _lib.check(fn(self._ctx().handle, C.byref(prm), stream_of(dev)))
         # keep the small device inputs alive until the (asynchronous) step has consumed them
-        self.__dict__["_keepalive"] = (idx_dev, w_sample, X)
+        self.__dict__["_keepalive"] = (idx_dev, w_dev, X)
+
+    def _single_batch_fit(self, X, sample_indices):
+        """One minibatch step; X is a (batch x n_features) CUDA tensor of the estimator dtype
+        [ref: dict_fact.py:495-526]."""
+        if self.verbose and self.verbose_iter_ and self.n_iter_ >= self.verbose_iter_[0]:
+            print('Iteration %i' % self.n_iter_)
+            self.verbose_iter_ = self.verbose_iter_[1:]
+            self._callback()
+        subset, sample_indices, w, order, w_sample = self._host_bookkeeping(X.shape[0], sample_indices)
+        self._launch_step(X, sample_indices, subset, order, w, w_sample)
         self.__dict__["last_subset_"] = subset
         self.__dict__["last_order_"] = order
 

@@ -1,0 +1,99 @@
+"""Sample-sharded data parallelism of the minibatch step: one process per GPU.
+
+A minibatch shards naturally over its samples (the reference's own thread
+pool splits the batch the same way, dict_fact.py:584-586, 621-635): every rank holds replicas
+of `components_`, `C_`, `B_`, `comp_norm_` and identically seeded host RNG streams (same
+subset, same atom order on every rank), solves the codes of ITS rows, and contributes its
+share of the statistics increments.  The one exchange step is a sum of those increments over
+ranks -- `torch.distributed.all_reduce` (NCCL over NVLink 5 / NVSwitch on B200) of a single
+k x (k + p) buffer -- after which every rank applies the decay and runs the same deterministic
+dictionary update on bit-identical inputs, so the replicas never diverge and no dictionary
+broadcast is needed.
+
+    dist.init_process_group("nccl")
+    est = ShardedDictFact(n_components=256, batch_size=512, ...)   # batch_size = rows PER RANK
+    est.prepare(n_samples=n, X=X0)            # same X0 on every rank
+    est.partial_fit(X_local, sample_indices_local)
+
+The result equals the single-process estimator run with batch_size * world_size and the ranks'
+rows concatenated in rank order (up to floating-point summation order of the all-reduce).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .dict_fact import DictFact
+
+__all__ = ["ShardedStepMixin", "ShardedDictFact"]
+
+
+class ShardedStepMixin(object):
+    """Host-side orchestration of the sharded step; the two device phases are provided by the
+    concrete class (`_phase_code_and_increments`, `_phase_apply_and_dict`)."""
+
+    process_group = None
+
+    def _world(self):
+        if not dist.is_available() or not dist.is_initialized():
+            return 1, 0
+        return dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
+
+    def _single_batch_fit(self, X, sample_indices):
+        world, rank = self._world()
+        if self.G_agg == 'full' and self.optimizer != 'sgd' and world > 1:
+            pass   # G_ is updated inside the (replicated) dictionary phase: nothing to exchange
+        if self.verbose and self.verbose_iter_ and self.n_iter_ >= self.verbose_iter_[0]:
+            if rank == 0:
+                print('Iteration %i' % self.n_iter_)
+            self.verbose_iter_ = self.verbose_iter_[1:]
+            self._callback()
+        b_local = X.shape[0]
+        b_global = b_local * world          # equal shards: every rank passes the same row count
+        subset, sample_indices, w, order, w_sample = self._host_bookkeeping(b_global, sample_indices)
+        inc = self._phase_code_and_increments(X, sample_indices, subset, order, w, w_sample, b_global)
+        if world > 1:
+            dist.all_reduce(inc, op=dist.ReduceOp.SUM, group=self.process_group)
+        self._phase_apply_and_dict(X, sample_indices, subset, order, w, w_sample, inc, b_global)
+        self.__dict__["last_subset_"] = subset
+        self.__dict__["last_order_"] = order
+
+    def check_replicas(self):
+        """Debug helper: max abs difference of the dictionary across ranks (should be 0.0)."""
+        world, _ = self._world()
+        D = self.components_dev.clone()
+        lo, hi = D.clone(), D.clone()
+        if world > 1:
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.process_group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.process_group)
+        return float((hi - lo).abs().max().item())
+
+
+class ShardedDictFact(ShardedStepMixin, DictFact):
+    """DictFact whose minibatches are sharded over the ranks of a torch.distributed group."""
+
+    def __init__(self, process_group=None, **kwargs):
+        DictFact.__init__(self, **kwargs)
+        self.process_group = process_group
+
+    @classmethod
+    def _get_param_names(cls):
+        return sorted(set(DictFact._get_param_names()) | {"process_group"})
+
+    def _inc_buffer(self):
+        D = self._d_components_
+        k, p = D.shape
+        buf = self.__dict__.get("_d_inc")
+        if buf is None or buf.numel() != k * (k + p) or buf.dtype != D.dtype:
+            buf = self.__dict__["_d_inc"] = torch.empty(k * (k + p), dtype=D.dtype, device=D.device)
+        return buf
+
+    def _phase_code_and_increments(self, X, sample_indices, subset, order, w, w_sample, b_global):
+        inc = self._inc_buffer()
+        self._launch_step(X, sample_indices, subset, order, w, w_sample,
+                          phases=_lib.PHASE_CODE | _lib.PHASE_STATS, stats_inc=inc, global_batch=b_global)
+        return inc
+
+    def _phase_apply_and_dict(self, X, sample_indices, subset, order, w, w_sample, inc, b_global):
+        self._launch_step(X, sample_indices, subset, order, w, w_sample,
+                          phases=_lib.PHASE_APPLY | _lib.PHASE_DICT, stats_inc=inc, global_batch=b_global)
