@@ -145,8 +145,15 @@ def run_reference(args, rank):
         return
     steps, warmup = args.steps, args.warmup
     X = make_data((steps + warmup) * B)
-    val, ms, kind = time_reference(X, steps, warmup)
-    cores = blas_threads()
+    best = None
+    for nt in (1, min(32, os.cpu_count() or 1)):
+        v_, ms_, kind = time_reference(X, steps, warmup, n_threads=nt)
+        if best is None or v_ > best[0]:
+            best = (v_, ms_, nt)
+        if kind != "reference":
+            break
+    val, ms, nt_best = best
+    cores = max(blas_threads(), nt_best)
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
@@ -155,7 +162,8 @@ def run_reference(args, rank):
                    "n_components": K, "n_features": P, "batch_size": B, "reduction": R},
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": kind,
                          "sample": "%d timed minibatches of 512 rows after %d warm-up, reference DictFact.partial_fit, "
-                                   "n_threads=1, BLAS threads=%d of %d host cores" % (steps, warmup, cores, os.cpu_count() or 1)},
+                                   "best of n_threads in {1, 32} (n_threads=%d), BLAS threads=%d, %d host cores"
+                                   % (steps, warmup, nt_best, blas_threads(), os.cpu_count() or 1)},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -322,11 +330,18 @@ def run_b200(args, rank, world):
     if rank == 0 and world == 1 and not args.no_cpu:
         nb_cpu, warm_cpu = args.cpu_steps, 1
         Xc = X[:(nb_cpu + warm_cpu) * B] if X.shape[0] >= (nb_cpu + warm_cpu) * B else make_data((nb_cpu + warm_cpu) * B)
-        v, ms_c, kind = time_reference(Xc, nb_cpu, warm_cpu)
-        cpu = {"value": v, "unit": "samples/s", "cores": blas_threads(), "kind": kind, "ms_per_step": ms_c,
+        best = None
+        for nt in (1, min(32, os.cpu_count() or 1)):
+            v_, ms_, kind = time_reference(Xc, nb_cpu, warm_cpu, n_threads=nt)
+            if best is None or v_ > best[0]:
+                best = (v_, ms_, nt)
+            if kind != "reference":
+                break
+        v, ms_c, nt_best = best
+        cpu = {"value": v, "unit": "samples/s", "cores": max(blas_threads(), nt_best), "kind": kind, "ms_per_step": ms_c,
                "sample": "%d timed minibatches of 512 rows (same data, same seeds) after %d warm-up; reference "
-                         "DictFact.partial_fit, n_threads=1, BLAS threads as configured (%d host cores)"
-                         % (nb_cpu, warm_cpu, os.cpu_count() or 1)}
+                         "DictFact.partial_fit, best of n_threads in {1, 32} (n_threads=%d), BLAS threads=%d, "
+                         "%d host cores" % (nb_cpu, warm_cpu, nt_best, blas_threads(), os.cpu_count() or 1)}
 
     if rank == 0:
         out = {

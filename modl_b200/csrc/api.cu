@@ -191,6 +191,12 @@ static int cd_launch_inst(modl_ctx *ctx, const T *G, int64_t g_stride, const T *
         grid = (int)ceil_div(b, warps);
         if (grid > ctx->sm_count) grid = ctx->sm_count;
         MODL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // tile-packed lower triangle of G in global memory, pulled by TMA bulk copies
+        T *packed = nullptr;
+        MODL_TRY(ws<T>(ctx, WS_GPACK, cd_packed_elems(TILES), &packed));
+        cd_pack_gram_kernel<T><<<cd_tri(TILES), 256, 0, st>>>(G, (int)k, TILES, packed);
+        MODL_LAUNCH_CHECK(ctx);
+        G = packed;
     } else {
         warps = ctx->opt_cd_warps > 0 ? ctx->opt_cd_warps : 4;
         if (warps > 8) warps = 8;
@@ -297,7 +303,8 @@ static int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C
     auto kern = bcd_update_kernel<T>;
     const size_t budget = (size_t)ctx->max_smem_optin - 1024;
     auto base_smem = [&](int64_t ncp) {
-        return (size_t)(round_up(k, 32) + BCD_THREADS + ncp + 40) * sizeof(T) + 40 * sizeof(double);
+        return (size_t)(4 * round_up(k, 32) + BCD_THREADS + 4 * ncp + 2 * BCD_MAX_CLUSTER * BCD_NPART + 64) * sizeof(T) +
+               40 * sizeof(double);
     };
     BcdParams<T> P;
     P.Dp = Dp; P.Bp = Bp; P.C = C; P.comp_norm = comp_norm; P.order = d_order;
@@ -360,16 +367,14 @@ static int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C
     if (cw > 128) cw = 128;
     P.cols_per_cta = (int)cols; P.chunk = (int)cw; P.d_in_smem = d_in_smem; P.use_cluster = use_cluster;
 
-    // exchange workspace: [barrier 256 B][part 2*nblk*4][vrow 2*s][na_part nblk*k][radius k]
-    const size_t n_t = (size_t)(2 * nblk * BCD_NPART) + 2 * (size_t)s + (size_t)nblk * k + (size_t)k;
+    // exchange workspace: [barrier 256 B][part 2*nblk*4][vrow 2*s]
+    const size_t n_t = (size_t)(2 * nblk * BCD_NPART) + 2 * (size_t)s;
     unsigned char *base = nullptr;
     MODL_TRY(ws<unsigned char>(ctx, WS_BCD_SYNC, 256 + n_t * sizeof(T), &base));
     P.bar = reinterpret_cast<unsigned *>(base);
     T *tb = reinterpret_cast<T *>(base + 256);
     P.part = tb; tb += 2 * nblk * BCD_NPART;
-    P.vrow = tb; tb += 2 * s;
-    P.na_part = tb; tb += (size_t)nblk * k;
-    P.radius_log = tb;
+    P.vrow = tb;
     MODL_CUDA_TRY(cudaMemsetAsync(P.bar, 0, 256, st));
 
     cudaLaunchConfig_t cfg = {};

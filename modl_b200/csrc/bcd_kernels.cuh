@@ -13,20 +13,36 @@
 // Parallelisation.  The s subset columns are split over the CTAs of ONE launch; every CTA
 // keeps its column slice of D_sub in shared memory (when it fits) and walks the atoms in the
 // same order.  The only cross-CTA dependency per atom is the projection radius test, which
-// needs sums over all s columns: each CTA publishes partial sums (and, for the elastic-net
-// ball, its slice of the candidate row), all CTAs meet at ONE barrier per atom, then every
-// CTA reduces the partials in the same fixed order (bitwise identical decision everywhere,
-// no atomics) and finishes its own columns.  The barrier is a thread-block-cluster hardware
-// barrier when the launch is a single cluster (<= 16 CTAs; ~0.2 us), else a global-memory
-// sense barrier under a cooperative launch.
+// needs sums over all s columns: each CTA publishes three partial sums (and, for the
+// elastic-net ball, its slice of the candidate row), all CTAs meet at ONE barrier per atom,
+// then every CTA reduces the partials in the same fixed order (bitwise identical decision
+// everywhere, no atomics) and finishes its own columns.
+//
+// Latency engineering (the kernel is a chain of k dependent atom steps):
+//   * single thread-block cluster (<= 16 CTAs): partial sums are PUSHED into every peer's
+//     shared memory (DSMEM stores) and the hardware cluster barrier is split into
+//     arrive.release ... wait.acquire;
+//   * between arrive and wait every CTA already computes the next atom's row product
+//     C[a',:] . D_sub over all rows except the one being updated, so that after the barrier
+//     only a rank-1 fix-up remains on the critical path;
+//   * the C rows (two atoms ahead) and B_sub rows (one atom ahead) are prefetched with
+//     cp.async into shared-memory rings; comp_norm_ is staged in shared memory once;
+//   * enet_norm of the new atom is reduced together with the next atom's partial sums.
+// Larger panels fall back to a cooperative launch over all SMs with the same code and a
+// global-memory exchange + sense barrier.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "basic_kernels.cuh"
 #include "common.cuh"
 
 namespace modl {
 
+namespace cg = cooperative_groups;
+
 constexpr int BCD_THREADS = 512;
-constexpr int BCD_NPART = 4;     // partial sums exchanged per atom and CTA
+constexpr int BCD_NPART = 4;     // partial sums exchanged per atom and CTA (3 used)
+constexpr int BCD_MAX_CLUSTER = 16;
 
 template <typename T>
 struct BcdParams {
@@ -41,25 +57,41 @@ struct BcdParams {
     int cols_per_cta;    // columns owned by each CTA (last one may own fewer / none)
     int chunk;           // column-lane width (multiple of 32, <= BCD_THREADS)
     int d_in_smem;       // keep the CTA's D slice in shared memory
-    int use_cluster;     // 1: hardware cluster barrier, 0: global sense barrier
+    int use_cluster;     // 1: DSMEM exchange + hardware cluster barrier, 0: global memory + sense barrier
     unsigned *bar;       // global barrier counter (zero on entry)
-    T *part;             // [2][nblk][BCD_NPART]
+    T *part;             // [2][nblk][BCD_NPART]       (global exchange, use_cluster == 0)
     T *vrow;             // [2][s]   candidate rows (elastic-net ball only)
-    T *na_part;          // [nblk][k] per-CTA partial of enet_norm(new atom)
-    T *radius_log;       // [k] radius used for atom a (written by CTA 0)
 };
 
-__device__ __forceinline__ void bcd_barrier(bool use_cluster, unsigned *bar, unsigned nblk, unsigned &epoch)
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T *smem_dst, const T *gmem_src)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(sa), "l"(gmem_src), "n"(sizeof(T)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+__device__ __forceinline__ void bcd_arrive(bool use_cluster, unsigned *bar, unsigned &epoch)
 {
     if (use_cluster) {
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     } else {
         __syncthreads();
         if (threadIdx.x == 0) {
             epoch += 1;
             __threadfence();
             atomicAdd(bar, 1u);
+        }
+    }
+}
+
+__device__ __forceinline__ void bcd_wait(bool use_cluster, unsigned *bar, unsigned nblk, unsigned epoch)
+{
+    if (use_cluster) {
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    } else {
+        if (threadIdx.x == 0) {
             const unsigned target = epoch * nblk;
             while (true) {
                 unsigned cur;
@@ -68,6 +100,47 @@ __device__ __forceinline__ void bcd_barrier(bool use_cluster, unsigned *bar, uns
                 __nanosleep(20);
             }
             __threadfence();
+        }
+        __syncthreads();
+    }
+}
+
+// dotn[c] = sum_{i != skip} crow[i] * D[i][c] for the CTA's columns (all threads cooperate).
+template <typename T>
+__device__ __forceinline__ void bcd_row_product(const T *crow, const T *Ds, const T *Dg, int64_t lds, bool d_in_smem,
+                                                int k, int nc, int ncp, int CW, int IG, int skip, T *red, T *dotn)
+{
+    const int tid = threadIdx.x;
+    const int cl = tid % CW, ig = tid / CW;
+    for (int cb = 0; cb < nc; cb += CW) {
+        const int c = cb + cl;
+        T a0 = T(0), a1 = T(0);
+        if (ig < IG && c < nc) {
+            if (d_in_smem) {
+                int i = ig;
+#pragma unroll 4
+                for (; i + IG < k; i += 2 * IG) {
+                    const T x0 = (i != skip) ? crow[i] : T(0);
+                    const T x1 = (i + IG != skip) ? crow[i + IG] : T(0);
+                    a0 = fma(x0, Ds[i * ncp + c], a0);
+                    a1 = fma(x1, Ds[(i + IG) * ncp + c], a1);
+                }
+                if (i < k && i != skip) a0 = fma(crow[i], Ds[i * ncp + c], a0);
+            } else {
+                const T *col = Dg + c;
+#pragma unroll 4
+                for (int i = ig; i < k; i += IG) {
+                    const T x0 = (i != skip) ? crow[i] : T(0);
+                    a0 = fma(x0, col[(int64_t)i * lds], a0);
+                }
+            }
+        }
+        if (ig < IG) red[ig * CW + cl] = a0 + a1;
+        __syncthreads();
+        if (ig == 0 && c < nc) {
+            T dot = T(0);
+            for (int gi = 0; gi < IG; ++gi) dot += red[gi * CW + cl];
+            dotn[c] = dot;
         }
         __syncthreads();
     }
@@ -84,127 +157,165 @@ bcd_update_kernel(BcdParams<T> P)
     const int c1 = min(s, c0 + P.cols_per_cta);
     const int nc = c1 - c0;                       // columns owned (may be 0)
     const int ncp = (int)round_up(P.cols_per_cta, 32);
-    const int tid = threadIdx.x;
+    const int kp = (int)round_up(k, 32);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int CW = P.chunk, IG = BCD_THREADS / CW;
-    const int cl = tid % CW, ig = tid / CW;       // column lane / row group (ig >= IG: idle)
     const bool enet = P.l1_ratio != T(0);
+    const bool use_cluster = P.use_cluster != 0;
+    const bool d_in_smem = P.d_in_smem != 0;
 
-    // ---- shared memory carve-up ----
-    T *Ca = reinterpret_cast<T *>(bcd_smem_raw);              // k      : row a of C
-    T *red = Ca + round_up(k, 32);                        // IG*CW  : cross-group partial dots
-    T *vown = red + BCD_THREADS;                              // ncp    : candidate / new atom slice
-    T *scratch = vown + ncp;                                  // 40
-    double *dscratch = reinterpret_cast<double *>(scratch + 40);   // 40 doubles (8-byte aligned below)
+    // ---- shared memory carve-up (all offsets multiples of 32 elements) ----
+    T *Ca = reinterpret_cast<T *>(bcd_smem_raw);              // 3 * kp : ring of C rows
+    T *cnorm = Ca + 3 * kp;                                   // kp     : comp_norm_ staged
+    T *red = cnorm + kp;                                      // BCD_THREADS
+    T *vown = red + BCD_THREADS;                              // ncp : candidate / new atom slice
+    T *dotn = vown + ncp;                                     // ncp : C[a,:] . D for the atom being visited
+    T *brow = dotn + ncp;                                     // 2 * ncp : ring of B_sub rows
+    T *xch = brow + 2 * ncp;                                  // 2 * BCD_MAX_CLUSTER * BCD_NPART exchange slots
+    T *wred = xch + 2 * BCD_MAX_CLUSTER * BCD_NPART;          // 16 warps * 4
+    double *dscratch = reinterpret_cast<double *>(wred + 64); // 40 doubles
     T *Ds = reinterpret_cast<T *>(dscratch + 40);             // k * ncp (optional)
     __shared__ bool sh_inside;
     __shared__ T sh_l;
 
-    if (P.d_in_smem) {
+    const T *Dg = P.Dp + c0;                                  // my columns of the global panel
+    if (d_in_smem) {
         for (int e = tid; e < k * ncp; e += BCD_THREADS) {
             const int i = e / ncp, c = e % ncp;
-            Ds[e] = (c < nc) ? P.Dp[(int64_t)i * lds + c0 + c] : T(0);
+            Ds[e] = (c < nc) ? Dg[(int64_t)i * lds + c] : T(0);
         }
     }
+    for (int i = tid; i < k; i += BCD_THREADS) cnorm[i] = P.comp_norm[i];
+    // C rows of the first two atoms, B row of the first atom
+    {
+        const int a0 = P.order[0], a1 = P.order[k > 1 ? 1 : 0];
+        for (int i = tid; i < k; i += BCD_THREADS) {
+            Ca[i] = P.C[(int64_t)a0 * k + i];
+            Ca[kp + i] = P.C[(int64_t)a1 * k + i];
+        }
+        for (int c = tid; c < nc; c += BCD_THREADS) brow[c] = P.Bp[(int64_t)a0 * lds + c0 + c];
+    }
     __syncthreads();
+    bcd_row_product<T>(Ca, Ds, Dg, lds, d_in_smem, k, nc, ncp, CW, IG, -1, red, dotn);
 
+    cg::cluster_group cluster = cg::this_cluster();
+    if (use_cluster) {   // every peer is resident before anybody stores into its shared memory
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    }
     unsigned epoch = 0;
-    for (int oi = 0; oi < k; ++oi) {
-        const int a = P.order[oi];
-        const int par = oi & 1;
-        for (int i = tid; i < k; i += BCD_THREADS) Ca[i] = P.C[(int64_t)a * k + i];
-        __syncthreads();
-        const T caa = Ca[a];
-        T nb_local = T(0), sv2_local = T(0);
+    T na_carry = T(0);           // enet_norm partial of the previous atom held by this thread
+    T radius_prev = T(0);
+    int a_prev = -1;
 
-        // ---------------- phase A: candidate row on my columns ----------------
-        for (int cb = 0; cb < nc; cb += CW) {
-            const int c = cb + cl;                      // column within my slice
-            T acc = T(0);
-            if (ig < IG && c < nc) {
-                if (P.d_in_smem) {
-                    for (int i = ig; i < k; i += IG) acc = fma(Ca[i], Ds[i * ncp + c], acc);
-                } else {
-                    const T *col = P.Dp + c0 + c;
-                    for (int i = ig; i < k; i += IG) acc = fma(Ca[i], col[(int64_t)i * lds], acc);
-                }
-            }
-            if (ig < IG) red[ig * CW + cl] = acc;
-            __syncthreads();
-            if (ig == 0 && c < nc) {
-                T dot = T(0);
-                for (int gi = 0; gi < IG; ++gi) dot += red[gi * CW + cl];
-                const T dold = P.d_in_smem ? Ds[a * ncp + c] : P.Dp[(int64_t)a * lds + c0 + c];
-                const T grad = (P.Bp[(int64_t)a * lds + c0 + c] - dot) + caa * dold;
-                T v = (caa > T(1e-20)) ? grad / caa : dold;         // [ref: :681-683]
-                if (P.positive && v < T(0)) v = T(0);               // [ref: :684-685]
+    for (int oi = 0; oi <= k; ++oi) {
+        const bool live = oi < k;                  // oi == k: only flushes the last atom's norm
+        const int a = live ? P.order[oi] : 0;
+        const int an = (oi + 1 < k) ? P.order[oi + 1] : -1;
+        const int par = oi & 1;
+        const T *Ccur = Ca + (oi % 3) * kp;
+        const T *Cnext = Ca + ((oi + 1) % 3) * kp;
+        T *Cpre = Ca + ((oi + 2) % 3) * kp;
+        const T *bcur = brow + par * ncp;
+        T *bnext = brow + (par ^ 1) * ncp;
+        const T caa = live ? Ccur[a] : T(1);
+
+        // ---------------- S1: candidate row on my columns + partial sums ----------------
+        T nb_local = T(0), sv2_local = T(0);
+        if (live) {
+            for (int c = tid; c < nc; c += BCD_THREADS) {
+                const T dold = d_in_smem ? Ds[a * ncp + c] : Dg[(int64_t)a * lds + c];
+                const T grad = (bcur[c] - dotn[c]) + caa * dold;
+                T v = (caa > T(1e-20)) ? grad / caa : dold;          // [ref: :681-683]
+                if (P.positive && v < T(0)) v = T(0);                // [ref: :684-685]
                 vown[c] = v;
-                nb_local += enet_term(dold, P.l1_ratio);            // [ref: :676-678]
+                nb_local += enet_term(dold, P.l1_ratio);             // [ref: :676-678]
                 sv2_local = fma(v, v, sv2_local);
                 if (enet) P.vrow[(int64_t)par * s + c0 + c] = v;
             }
-            __syncthreads();
         }
-        nb_local = block_sum(nb_local, scratch);
-        sv2_local = block_sum(sv2_local, scratch);
-        if (tid == 0) {
-            T *dst = P.part + ((int64_t)par * nblk + g) * BCD_NPART;
-            dst[0] = nb_local;
-            dst[1] = sv2_local;
-        }
-
-        bcd_barrier(P.use_cluster != 0, P.bar, (unsigned)nblk, epoch);
-
-        // ---------------- phase B: global sums, projection, write-back ----------------
-        T nb = T(0), sv2 = T(0);
         {
-            const T *src = P.part + (int64_t)par * nblk * BCD_NPART;
-            for (int q = 0; q < nblk; ++q) {          // same order in every CTA
-                nb += __ldcg(src + q * BCD_NPART + 0);
-                sv2 += __ldcg(src + q * BCD_NPART + 1);
+            T r0 = warp_sum(nb_local), r1 = warp_sum(sv2_local), r2 = warp_sum(na_carry);
+            if (lane == 0) { wred[wid * 4 + 0] = r0; wred[wid * 4 + 1] = r1; wred[wid * 4 + 2] = r2; }
+        }
+        __syncthreads();
+        if (wid == 0) {
+            // fixed-order sum over the warps, then publish to every CTA (slot [par][g])
+            T t0 = T(0), t1 = T(0), t2 = T(0);
+            for (int w = 0; w < BCD_THREADS / 32; ++w) { t0 += wred[w * 4]; t1 += wred[w * 4 + 1]; t2 += wred[w * 4 + 2]; }
+            if (use_cluster) {
+                if (lane < nblk) {
+                    T *remote = cluster.map_shared_rank(xch, lane) + (par * BCD_MAX_CLUSTER + g) * BCD_NPART;
+                    remote[0] = t0; remote[1] = t1; remote[2] = t2;
+                }
+            } else if (lane == 0) {
+                T *dst = P.part + ((int64_t)par * nblk + g) * BCD_NPART;
+                dst[0] = t0; dst[1] = t1; dst[2] = t2;
             }
         }
-        const T radius = P.comp_norm[a] + nb;         // comp_norm_[k] += subset_norm
-        if (g == 0 && tid == 0) P.radius_log[a] = radius;
+        bcd_arrive(use_cluster, P.bar, epoch);
 
-        T na_local = T(0);
+        // ---------------- S2 (overlaps the barrier): prefetch + next atom's row product ----------------
+        if (oi + 2 < k) {
+            const int a2 = P.order[oi + 2];
+            for (int i = tid; i < k; i += BCD_THREADS) cp_async_elem(Cpre + i, P.C + (int64_t)a2 * k + i);
+        }
+        if (an >= 0)
+            for (int c = tid; c < nc; c += BCD_THREADS) cp_async_elem(bnext + c, P.Bp + (int64_t)an * lds + c0 + c);
+        cp_async_commit();
+        if (an >= 0)
+            bcd_row_product<T>(Cnext, Ds, Dg, lds, d_in_smem, k, nc, ncp, CW, IG, a, red, dotn);
+
+        bcd_wait(use_cluster, P.bar, (unsigned)nblk, epoch);
+
+        // ---------------- S3: global sums, projection, write-back, fix-up ----------------
+        T nb = T(0), sv2 = T(0), na_prev = T(0);
+        if (use_cluster) {
+            const T *src = xch + par * BCD_MAX_CLUSTER * BCD_NPART;
+            for (int q = 0; q < nblk; ++q) { nb += src[q * BCD_NPART]; sv2 += src[q * BCD_NPART + 1]; na_prev += src[q * BCD_NPART + 2]; }
+        } else {
+            const T *src = P.part + (int64_t)par * nblk * BCD_NPART;
+            for (int q = 0; q < nblk; ++q) {
+                nb += __ldcg(src + q * BCD_NPART); sv2 += __ldcg(src + q * BCD_NPART + 1); na_prev += __ldcg(src + q * BCD_NPART + 2);
+            }
+        }
+        if (a_prev >= 0 && g == 0 && tid == 0)
+            P.comp_norm[a_prev] = radius_prev - na_prev;              // comp_norm_[k] -= subset_norm  [ref: :690-692]
+        if (!live) break;
+        const T radius = cnorm[a] + nb;                               // comp_norm_[k] += subset_norm  [ref: :676-678]
+
+        T lthr = T(0), gamma = T(0), nrm = T(1);
+        int mode = 0;                                                 // 0: scale by 1/nrm, 1: zero, 2: shrink by lthr
         if (radius == T(0)) {                                         // [ref: enet.pyx:57-59]
-            for (int c = tid; c < nc; c += BCD_THREADS) vown[c] = T(0);
+            mode = 1;
         } else if (!enet) {                                           // [ref: enet.pyx:62-70]
-            const T nrm = (sv2 <= radius) ? T(1) : t_sqrt(sv2 / radius);
-            for (int c = tid; c < nc; c += BCD_THREADS) vown[c] = vown[c] / nrm;
+            nrm = (sv2 <= radius) ? T(1) : t_sqrt(sv2 / radius);
         } else {                                                      // [ref: enet.pyx:72-121]
-            const T gamma = T(2) / P.l1_ratio - T(2);
+            gamma = T(2) / P.l1_ratio - T(2);
             const T R = radius / P.l1_ratio;
             const T *vr = P.vrow + (int64_t)par * s;
             bool ins;
             const T l = enet_threshold_block<T>([&](int j) { return __ldcg(vr + j); }, s, R, gamma, &ins, dscratch);
             if (tid == 0) { sh_inside = ins; sh_l = l; }
             __syncthreads();
-            if (!sh_inside) {
-                const T lt = sh_l;
-                for (int c = tid; c < nc; c += BCD_THREADS) vown[c] = enet_shrink(vown[c], lt, gamma);
-            }
+            if (!sh_inside) { mode = 2; lthr = sh_l; }
         }
-        __syncthreads();
+        cp_async_wait_all();                                          // next C / B rows have landed (this thread's part)
+        const T can = (an >= 0) ? Cnext[a] : T(0);
+        na_carry = T(0);
         for (int c = tid; c < nc; c += BCD_THREADS) {
-            const T v = vown[c];
-            na_local += enet_term(v, P.l1_ratio);                     // [ref: :690-692]
-            if (P.d_in_smem) Ds[a * ncp + c] = v;
+            T v = vown[c];
+            if (mode == 1) v = T(0);
+            else if (mode == 2) v = enet_shrink(v, lthr, gamma);
+            else v = v / nrm;
+            na_carry += enet_term(v, P.l1_ratio);
+            if (d_in_smem) Ds[a * ncp + c] = v;
             P.Dp[(int64_t)a * lds + c0 + c] = v;                      // write-through
+            dotn[c] = fma(can, v, dotn[c]);                           // rank-1 fix-up of the next row product
         }
-        na_local = block_sum(na_local, scratch);
-        if (tid == 0) P.na_part[(int64_t)g * k + a] = na_local;
+        radius_prev = radius;
+        a_prev = a;
         __syncthreads();
-    }
-
-    // ---- comp_norm_[a] = radius_a - enet_norm(new atom): final fixed-order reduction ----
-    bcd_barrier(P.use_cluster != 0, P.bar, (unsigned)nblk, epoch);
-    if (g == 0) {
-        for (int a = tid; a < k; a += BCD_THREADS) {
-            T na = T(0);
-            for (int q = 0; q < nblk; ++q) na += __ldcg(P.na_part + (int64_t)q * k + a);
-            P.comp_norm[a] = __ldcg(P.radius_log + a) - na;
-        }
     }
 }
 

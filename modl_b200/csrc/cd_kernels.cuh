@@ -30,7 +30,7 @@ constexpr int CD_TILE = 32;
 constexpr int CD_TILE_ELEMS = CD_TILE * CD_TILE;
 
 __host__ __device__ inline int cd_tri(int I) { return I * (I + 1) / 2; }
-inline size_t cd_packed_elems(int tiles) { return (size_t)cd_tri(tiles) * CD_TILE_ELEMS; }
+__host__ __device__ inline size_t cd_packed_elems(int tiles) { return (size_t)cd_tri(tiles) * CD_TILE_ELEMS; }
 
 // Fill the packed lower-triangular tile image of G in shared memory (whole CTA).
 template <typename T>
@@ -47,6 +47,53 @@ __device__ void cd_load_packed_gram(T *sG, const T *__restrict__ G, int k, int t
         T v = T(0);
         if (gi < k && gj < k) v = G[(int64_t)gi * k + gj];
         sG[t * CD_TILE_ELEMS + a * CD_TILE + ((a + c) & 31)] = v;
+    }
+}
+
+// Same image written to GLOBAL memory once per Gram matrix (grid: one CTA per lower tile), so
+// that every CTA of the solver can pull it into shared memory with one TMA bulk copy per tile
+// instead of 36 K scalar loads each.
+template <typename T>
+__global__ void __launch_bounds__(256)
+cd_pack_gram_kernel(const T *__restrict__ G, int k, int tiles, T *__restrict__ packed)
+{
+    const int t = blockIdx.x;
+    int I = 0;
+    while (cd_tri(I + 1) <= t) ++I;
+    const int J = t - cd_tri(I);
+    for (int within = threadIdx.x; within < CD_TILE_ELEMS; within += blockDim.x) {
+        const int a = within / CD_TILE, c = within % CD_TILE;
+        const int gi = I * CD_TILE + a, gj = J * CD_TILE + c;
+        T v = T(0);
+        if (gi < k && gj < k) v = G[(int64_t)gi * k + gj];
+        packed[(int64_t)t * CD_TILE_ELEMS + a * CD_TILE + ((a + c) & 31)] = v;
+    }
+}
+
+// TMA (cp.async.bulk) copy of the packed image global -> shared, completion on an mbarrier.
+__device__ __forceinline__ void cd_bulk_load(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned chunk,
+                                             unsigned long long *mbar)
+{
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+        for (unsigned off = 0; off < bytes; off += chunk) {
+            const unsigned n = (bytes - off) < chunk ? (bytes - off) : chunk;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(dst + off), "l"((const char *)gmem_src + off), "r"(n), "r"(bar) : "memory");
+        }
+    }
+    // everybody waits for phase 0 of the barrier
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(bar) : "memory");
     }
 }
 
@@ -83,8 +130,20 @@ __device__ __forceinline__ int cd_solve_warp(const T *sG, const T *__restrict__ 
                                              T (&w)[TILES], const T (&q)[TILES], T ynorm2, T alpha,
                                              T beta, T tol, int max_iter, bool positive)
 {
-    T h[TILES], r[TILES];
+    T h[TILES], r[TILES], inv[TILES];
     unsigned zmask[TILES];
+    // 1 / (Q[c,c] + beta) for my own coordinates, once per sample.  The per-step division of
+    // the reference (:372-373) becomes multiply + one Newton correction (correctly rounded in
+    // all but pathological cases), which keeps the IEEE-division slow path -- triggered by the
+    // many zero numerators of a sparse code -- off the dependent chain.
+#pragma unroll
+    for (int J = 0; J < TILES; ++J) {
+        const int c = J * CD_TILE + lane;
+        T dg;
+        if (PACKED) dg = sG[(cd_tri(J) + J) * CD_TILE_ELEMS + lane * CD_TILE + ((2 * lane) & 31)];
+        else        dg = c < k ? Gs[(int64_t)c * k + c] : T(0);
+        inv[J] = T(1) / (dg + beta);
+    }
     // ---- H = Q w accumulated column by column (Q symmetric)  [ref: :340-347] ----
 #pragma unroll
     for (int J = 0; J < TILES; ++J) h[J] = T(0);
@@ -123,26 +182,21 @@ __device__ __forceinline__ int cd_solve_warp(const T *sG, const T *__restrict__ 
                 if (PACKED) cd_row_packed<T, TILES>(sG, J, l, lane, r);
                 else        cd_row_global<T, TILES>(Gs, k, c, lane, r);
                 const T w_old = __shfl_sync(kFullMask, w[J], l);
-                if (w_old != T(0)) {
+                // H -= w_old Q[c,:] -- branch-free: a zero coefficient leaves H bit-unchanged
 #pragma unroll
-                    for (int JJ = 0; JJ < TILES; ++JJ) h[JJ] = fma(-w_old, r[JJ], h[JJ]);
-                }
+                for (int JJ = 0; JJ < TILES; ++JJ) h[JJ] = fma(-w_old, r[JJ], h[JJ]);
                 // candidate for "my" coordinate of tile J; only lane l's value is consumed
                 const T tmp = q[J] - h[J];
-                T cand;
-                if (positive && tmp < T(0)) {
-                    cand = T(0);
-                } else {
-                    const T mag = t_abs(tmp) - alpha;
-                    const T m = mag > T(0) ? mag : T(0);
-                    cand = (tmp < T(0) ? -m : m) / (r[J] + beta);      // r[J] on lane l is Q[c,c]
-                }
+                const T mag = t_abs(tmp) - alpha;
+                T ms = mag > T(0) ? mag : T(0);
+                ms = (tmp < T(0)) ? (positive ? T(0) : -ms) : ms;
+                const T den = r[J] + beta;                             // r[J] on lane l is Q[c,c]
+                T cand = ms * inv[J];
+                cand = fma(fma(-cand, den, ms), inv[J], cand);         // Newton step: ms / den
                 const T w_new = __shfl_sync(kFullMask, cand, l);
-                if (lane == l) w[J] = w_new;
-                if (w_new != T(0)) {
+                w[J] = (lane == l) ? w_new : w[J];
 #pragma unroll
-                    for (int JJ = 0; JJ < TILES; ++JJ) h[JJ] = fma(w_new, r[JJ], h[JJ]);
-                }
+                for (int JJ = 0; JJ < TILES; ++JJ) h[JJ] = fma(w_new, r[JJ], h[JJ]);
                 const T d = t_abs(w_new - w_old);
                 if (d > d_w_max) d_w_max = d;
                 const T aw = t_abs(w_new);
@@ -196,11 +250,12 @@ __global__ void cd_regression_kernel(const T *__restrict__ G, int64_t g_stride, 
                                      int b, int k, T alpha, T beta, T tol, int max_iter, int positive,
                                      int32_t *__restrict__ sweeps_out)
 {
-    extern __shared__ __align__(16) unsigned char cd_smem_raw[];
+    extern __shared__ __align__(128) unsigned char cd_smem_raw[];
     T *sG = reinterpret_cast<T *>(cd_smem_raw);
     if (PACKED) {
-        cd_load_packed_gram<T>(sG, G, k, TILES);
-        __syncthreads();
+        // G points at the tile-packed image (cd_pack_gram_kernel); one TMA bulk copy per tile
+        __shared__ __align__(8) unsigned long long mbar;
+        cd_bulk_load(sG, G, (unsigned)(cd_packed_elems(TILES) * sizeof(T)), (unsigned)(CD_TILE_ELEMS * sizeof(T)), &mbar);
     }
     const int lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;

@@ -64,6 +64,7 @@ enum WsSlot {
     WS_BCD_SYNC,     // barrier counter + partial sums + v rows
     WS_CHOL,         // k x k factor (x b for per-sample Grams)
     WS_GROWS,        // gathered per-sample Gram matrices
+    WS_GPACK,        // tile-packed lower triangle of the shared Gram
     WS_MISC,         // small scalars
     WS_INFO,         // int status flags
     WS_COUNT
