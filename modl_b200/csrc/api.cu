@@ -303,7 +303,7 @@ static int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C
     auto kern = bcd_update_kernel<T>;
     const size_t budget = (size_t)ctx->max_smem_optin - 1024;
     auto base_smem = [&](int64_t ncp) {
-        return (size_t)(4 * round_up(k, 32) + BCD_THREADS + 4 * ncp + 2 * BCD_MAX_CLUSTER * BCD_NPART + 64) * sizeof(T) +
+        return (size_t)(4 * round_up(k, 32) + bcd_red_elems(ncp) + 4 * ncp + 2 * BCD_MAX_CLUSTER * BCD_NPART + 64) * sizeof(T) +
                40 * sizeof(double);
     };
     BcdParams<T> P;
@@ -319,7 +319,7 @@ static int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C
             if (cs > ctx->opt_bcd_cluster) continue;
             const int64_t c = ceil_div(s, cs), ncp = round_up(c, 32);
             const size_t need = base_smem(ncp) + (size_t)k * ncp * sizeof(T);
-            if (need > budget) continue;
+            if (need > budget || ncp > 2 * BCD_THREADS) continue;
             if (cs > 8) {
                 if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
                     cudaGetLastError();
@@ -352,7 +352,7 @@ static int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C
         cols = ceil_div(s, want);
         const int64_t ncp = round_up(cols, 32);
         size_t need = base_smem(ncp) + (size_t)k * ncp * sizeof(T);
-        d_in_smem = need <= budget;
+        d_in_smem = need <= budget && ncp <= 2 * BCD_THREADS;
         if (!d_in_smem) need = base_smem(ncp);
         MODL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
         int per_sm = 0;

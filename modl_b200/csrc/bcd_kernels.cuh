@@ -40,9 +40,18 @@ namespace modl {
 
 namespace cg = cooperative_groups;
 
-constexpr int BCD_THREADS = 512;
+constexpr int BCD_THREADS = 256;
 constexpr int BCD_NPART = 4;     // partial sums exchanged per atom and CTA (3 used)
 constexpr int BCD_MAX_CLUSTER = 16;
+
+// elements of the cross-row-block reduction scratch for a slice of `ncp` (padded) columns
+__host__ __device__ inline int64_t bcd_red_elems(int64_t ncp)
+{
+    const int64_t np = ncp / 2 > 0 ? ncp / 2 : 1;
+    const int64_t ig = BCD_THREADS / np > 0 ? BCD_THREADS / np : 1;
+    const int64_t a = ig * ncp;
+    return round_up(a > BCD_THREADS ? a : BCD_THREADS, 32);
+}
 
 template <typename T>
 struct BcdParams {
@@ -105,44 +114,73 @@ __device__ __forceinline__ void bcd_wait(bool use_cluster, unsigned *bar, unsign
     }
 }
 
-// dotn[c] = sum_{i != skip} crow[i] * D[i][c] for the CTA's columns (all threads cooperate).
+// dotn[c] = sum_i crow[i] * D[i][c] over ALL rows, for the CTA's columns (all threads
+// cooperate).  Shared-memory path: a thread owns a PAIR of adjacent columns and a contiguous
+// block of rows, so the C row is read as 128-bit and the D slice as 64-bit shared loads
+// (~1.6 instructions per FMA); partial sums of the row blocks are combined in a fixed order.
+template <typename T> struct alignas(2 * sizeof(T)) Pair { T x, y; };
+template <typename T> struct alignas(16) Quad { T x, y, z, w; };
+
 template <typename T>
 __device__ __forceinline__ void bcd_row_product(const T *crow, const T *Ds, const T *Dg, int64_t lds, bool d_in_smem,
-                                                int k, int nc, int ncp, int CW, int IG, int skip, T *red, T *dotn)
+                                                int k, int nc, int ncp, int CW, T *red, T *dotn)
 {
     const int tid = threadIdx.x;
-    const int cl = tid % CW, ig = tid / CW;
-    for (int cb = 0; cb < nc; cb += CW) {
-        const int c = cb + cl;
+    if (d_in_smem) {
+        const int NP = ncp >> 1;                       // column pairs
+        const int IG = BCD_THREADS / NP;               // row blocks (>= 1 because ncp <= 2 * BCD_THREADS)
+        const int RB = (((k + IG - 1) / IG) + 3) & ~3; // rows per block, multiple of 4
+        const int pr = tid % NP, ig = tid / NP;
         T a0 = T(0), a1 = T(0);
-        if (ig < IG && c < nc) {
-            if (d_in_smem) {
-                int i = ig;
-#pragma unroll 4
-                for (; i + IG < k; i += 2 * IG) {
-                    const T x0 = (i != skip) ? crow[i] : T(0);
-                    const T x1 = (i + IG != skip) ? crow[i + IG] : T(0);
-                    a0 = fma(x0, Ds[i * ncp + c], a0);
-                    a1 = fma(x1, Ds[(i + IG) * ncp + c], a1);
-                }
-                if (i < k && i != skip) a0 = fma(crow[i], Ds[i * ncp + c], a0);
-            } else {
-                const T *col = Dg + c;
-#pragma unroll 4
-                for (int i = ig; i < k; i += IG) {
-                    const T x0 = (i != skip) ? crow[i] : T(0);
-                    a0 = fma(x0, col[(int64_t)i * lds], a0);
-                }
+        if (ig < IG) {
+            const int r0 = ig * RB, r1 = min(k, r0 + RB);
+            const Pair<T> *dcol = reinterpret_cast<const Pair<T> *>(Ds) + pr;      // Ds[i][2*pr .. 2*pr+1]
+            const int rs = ncp >> 1;                                              // row stride in pairs
+            int i = r0;
+            for (; i + 4 <= r1; i += 4) {
+                const Quad<T> cq = *reinterpret_cast<const Quad<T> *>(crow + i);
+                const T c0 = cq.x, c1 = cq.y, c2 = cq.z, c3 = cq.w;
+                const Pair<T> d0 = dcol[(i + 0) * rs], d1 = dcol[(i + 1) * rs], d2 = dcol[(i + 2) * rs], d3 = dcol[(i + 3) * rs];
+                a0 = fma(c0, d0.x, a0); a1 = fma(c0, d0.y, a1);
+                a0 = fma(c1, d1.x, a0); a1 = fma(c1, d1.y, a1);
+                a0 = fma(c2, d2.x, a0); a1 = fma(c2, d2.y, a1);
+                a0 = fma(c3, d3.x, a0); a1 = fma(c3, d3.y, a1);
             }
+            for (; i < r1; ++i) {
+                const T c0 = crow[i];
+                const Pair<T> d0 = dcol[i * rs];
+                a0 = fma(c0, d0.x, a0); a1 = fma(c0, d0.y, a1);
+            }
+            red[ig * ncp + 2 * pr] = a0;
+            red[ig * ncp + 2 * pr + 1] = a1;
         }
-        if (ig < IG) red[ig * CW + cl] = a0 + a1;
         __syncthreads();
-        if (ig == 0 && c < nc) {
+        for (int c = tid; c < nc; c += BCD_THREADS) {
             T dot = T(0);
-            for (int gi = 0; gi < IG; ++gi) dot += red[gi * CW + cl];
+            for (int gi = 0; gi < IG; ++gi) dot += red[gi * ncp + c];
             dotn[c] = dot;
         }
         __syncthreads();
+    } else {
+        const int IG = BCD_THREADS / CW;
+        const int cl = tid % CW, ig = tid / CW;
+        for (int cb = 0; cb < nc; cb += CW) {
+            const int c = cb + cl;
+            T a0 = T(0);
+            if (ig < IG && c < nc) {
+                const T *col = Dg + c;
+#pragma unroll 4
+                for (int i = ig; i < k; i += IG) a0 = fma(crow[i], col[(int64_t)i * lds], a0);
+            }
+            if (ig < IG) red[ig * CW + cl] = a0;
+            __syncthreads();
+            if (ig == 0 && c < nc) {
+                T dot = T(0);
+                for (int gi = 0; gi < IG; ++gi) dot += red[gi * CW + cl];
+                dotn[c] = dot;
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -159,7 +197,7 @@ bcd_update_kernel(BcdParams<T> P)
     const int ncp = (int)round_up(P.cols_per_cta, 32);
     const int kp = (int)round_up(k, 32);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int CW = P.chunk, IG = BCD_THREADS / CW;
+    const int CW = P.chunk;
     const bool enet = P.l1_ratio != T(0);
     const bool use_cluster = P.use_cluster != 0;
     const bool d_in_smem = P.d_in_smem != 0;
@@ -167,8 +205,8 @@ bcd_update_kernel(BcdParams<T> P)
     // ---- shared memory carve-up (all offsets multiples of 32 elements) ----
     T *Ca = reinterpret_cast<T *>(bcd_smem_raw);              // 3 * kp : ring of C rows
     T *cnorm = Ca + 3 * kp;                                   // kp     : comp_norm_ staged
-    T *red = cnorm + kp;                                      // BCD_THREADS
-    T *vown = red + BCD_THREADS;                              // ncp : candidate / new atom slice
+    T *red = cnorm + kp;                                      // max(BCD_THREADS, row blocks * ncp)
+    T *vown = red + bcd_red_elems(ncp);                       // ncp : candidate / new atom slice
     T *dotn = vown + ncp;                                     // ncp : C[a,:] . D for the atom being visited
     T *brow = dotn + ncp;                                     // 2 * ncp : ring of B_sub rows
     T *xch = brow + 2 * ncp;                                  // 2 * BCD_MAX_CLUSTER * BCD_NPART exchange slots
@@ -196,7 +234,7 @@ bcd_update_kernel(BcdParams<T> P)
         for (int c = tid; c < nc; c += BCD_THREADS) brow[c] = P.Bp[(int64_t)a0 * lds + c0 + c];
     }
     __syncthreads();
-    bcd_row_product<T>(Ca, Ds, Dg, lds, d_in_smem, k, nc, ncp, CW, IG, -1, red, dotn);
+    bcd_row_product<T>(Ca, Ds, Dg, lds, d_in_smem, k, nc, ncp, CW, red, dotn);
 
     cg::cluster_group cluster = cg::this_cluster();
     if (use_cluster) {   // every peer is resident before anybody stores into its shared memory
@@ -240,9 +278,11 @@ bcd_update_kernel(BcdParams<T> P)
         }
         __syncthreads();
         if (wid == 0) {
-            // fixed-order sum over the warps, then publish to every CTA (slot [par][g])
-            T t0 = T(0), t1 = T(0), t2 = T(0);
-            for (int w = 0; w < BCD_THREADS / 32; ++w) { t0 += wred[w * 4]; t1 += wred[w * 4 + 1]; t2 += wred[w * 4 + 2]; }
+            // fixed tree over the warps, then publish to every CTA (slot [par][g])
+            constexpr int NW = BCD_THREADS / 32;
+            T t0 = lane < NW ? wred[lane * 4] : T(0), t1 = lane < NW ? wred[lane * 4 + 1] : T(0),
+              t2 = lane < NW ? wred[lane * 4 + 2] : T(0);
+            t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
             if (use_cluster) {
                 if (lane < nblk) {
                     T *remote = cluster.map_shared_rank(xch, lane) + (par * BCD_MAX_CLUSTER + g) * BCD_NPART;
@@ -264,23 +304,25 @@ bcd_update_kernel(BcdParams<T> P)
             for (int c = tid; c < nc; c += BCD_THREADS) cp_async_elem(bnext + c, P.Bp + (int64_t)an * lds + c0 + c);
         cp_async_commit();
         if (an >= 0)
-            bcd_row_product<T>(Cnext, Ds, Dg, lds, d_in_smem, k, nc, ncp, CW, IG, a, red, dotn);
+            bcd_row_product<T>(Cnext, Ds, Dg, lds, d_in_smem, k, nc, ncp, CW, red, dotn);
 
         bcd_wait(use_cluster, P.bar, (unsigned)nblk, epoch);
 
         // ---------------- S3: global sums, projection, write-back, fix-up ----------------
         T nb = T(0), sv2 = T(0), na_prev = T(0);
         if (use_cluster) {
-            const T *src = xch + par * BCD_MAX_CLUSTER * BCD_NPART;
-            for (int q = 0; q < nblk; ++q) { nb += src[q * BCD_NPART]; sv2 += src[q * BCD_NPART + 1]; na_prev += src[q * BCD_NPART + 2]; }
+            // every warp reduces the <= 16 CTA partials with the same shuffle tree (bit-identical everywhere)
+            const T *src = xch + (par * BCD_MAX_CLUSTER + lane) * BCD_NPART;
+            const bool on = lane < nblk;
+            nb = warp_sum(on ? src[0] : T(0)); sv2 = warp_sum(on ? src[1] : T(0)); na_prev = warp_sum(on ? src[2] : T(0));
         } else {
             const T *src = P.part + (int64_t)par * nblk * BCD_NPART;
             for (int q = 0; q < nblk; ++q) {
                 nb += __ldcg(src + q * BCD_NPART); sv2 += __ldcg(src + q * BCD_NPART + 1); na_prev += __ldcg(src + q * BCD_NPART + 2);
             }
         }
-        if (a_prev >= 0 && g == 0 && tid == 0)
-            P.comp_norm[a_prev] = radius_prev - na_prev;              // comp_norm_[k] -= subset_norm  [ref: :690-692]
+        if (a_prev >= 0 && tid == 0)
+            cnorm[a_prev] = radius_prev - na_prev;                    // comp_norm_[k] -= subset_norm  [ref: :690-692]
         if (!live) break;
         const T radius = cnorm[a] + nb;                               // comp_norm_[k] += subset_norm  [ref: :676-678]
 
@@ -309,14 +351,31 @@ bcd_update_kernel(BcdParams<T> P)
             else if (mode == 2) v = enet_shrink(v, lthr, gamma);
             else v = v / nrm;
             na_carry += enet_term(v, P.l1_ratio);
-            if (d_in_smem) Ds[a * ncp + c] = v;
-            P.Dp[(int64_t)a * lds + c0 + c] = v;                      // write-through
-            dotn[c] = fma(can, v, dotn[c]);                           // rank-1 fix-up of the next row product
+            T dold;
+            if (d_in_smem) {
+                dold = Ds[a * ncp + c];
+                Ds[a * ncp + c] = v;                                  // global panel is refreshed once, at the end
+            } else {
+                dold = Dg[(int64_t)a * lds + c];
+                P.Dp[(int64_t)a * lds + c0 + c] = v;
+            }
+            // the next row product was taken over the OLD row a: rank-1 correction with the change
+            dotn[c] = fma(can, v - dold, dotn[c]);
         }
         radius_prev = radius;
         a_prev = a;
         __syncthreads();
     }
+    // ---- write-back ----
+    __syncthreads();
+    if (d_in_smem) {
+        for (int e = tid; e < k * ncp; e += BCD_THREADS) {
+            const int i = e / ncp, c = e % ncp;
+            if (c < nc) P.Dp[(int64_t)i * lds + c0 + c] = Ds[e];
+        }
+    }
+    if (g == 0)
+        for (int i = tid; i < k; i += BCD_THREADS) P.comp_norm[i] = cnorm[i];
 }
 
 }  // namespace modl

@@ -97,17 +97,31 @@ __device__ __forceinline__ void cd_bulk_load(void *smem_dst, const void *gmem_sr
     }
 }
 
+// explicit shared-window loads (32-bit address computed once per warp; the per-tile offsets fold
+// into the instruction immediates)
+__device__ __forceinline__ float lds_real(unsigned addr, float) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_real(unsigned addr, double) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
 // Row `c = 32*Jc + l` of the symmetric matrix from the packed image; lane gets columns 32*JJ+lane.
+// sbase: shared address of the image; swz = (l + lane) & 31.
 template <typename T, int TILES>
-__device__ __forceinline__ void cd_row_packed(const T *sG, int Jc, int l, int lane, T (&r)[TILES])
+__device__ __forceinline__ void cd_row_packed(unsigned sbase, int Jc, int l, int lane, T (&r)[TILES])
 {
+    const unsigned swz = (unsigned)((l + lane) & 31);
+    const unsigned rowoff = sbase + (unsigned)sizeof(T) * ((unsigned)l * CD_TILE + swz);      // tile row l
+    const unsigned coloff = sbase + (unsigned)sizeof(T) * ((unsigned)lane * CD_TILE + swz);   // tile column l
 #pragma unroll
     for (int JJ = 0; JJ < TILES; ++JJ) {
-        if (JJ <= Jc) {
-            r[JJ] = sG[(cd_tri(Jc) + JJ) * CD_TILE_ELEMS + l * CD_TILE + ((l + lane) & 31)];
-        } else {
-            r[JJ] = sG[(cd_tri(JJ) + Jc) * CD_TILE_ELEMS + lane * CD_TILE + ((lane + l) & 31)];
-        }
+        if (JJ <= Jc) r[JJ] = lds_real(rowoff + (unsigned)sizeof(T) * (unsigned)((cd_tri(Jc) + JJ) * CD_TILE_ELEMS), T(0));
+        else          r[JJ] = lds_real(coloff + (unsigned)sizeof(T) * (unsigned)((cd_tri(JJ) + Jc) * CD_TILE_ELEMS), T(0));
     }
 }
 
@@ -122,16 +136,35 @@ __device__ __forceinline__ void cd_row_global(const T *__restrict__ Gs, int k, i
     }
 }
 
-template <typename T> struct CdWide { typedef double type; };
+// h += c * r over the register tiles.  float: packed FFMA2 (fma.rn.f32x2, new on sm_100) halves
+// the instruction count of the two rank-1 updates that dominate a coordinate step.
+template <int TILES>
+__device__ __forceinline__ void cd_axpy_tiles(float (&h)[TILES], const float (&r)[TILES], float c)
+{
+    const float2 cc = make_float2(c, c);
+#pragma unroll
+    for (int m = 0; m + 1 < TILES; m += 2) {
+        const float2 hv = __ffma2_rn(cc, make_float2(r[m], r[m + 1]), make_float2(h[m], h[m + 1]));
+        h[m] = hv.x;
+        h[m + 1] = hv.y;
+    }
+    if (TILES & 1) h[TILES - 1] = fmaf(c, r[TILES - 1], h[TILES - 1]);
+}
+template <int TILES>
+__device__ __forceinline__ void cd_axpy_tiles(double (&h)[TILES], const double (&r)[TILES], double c)
+{
+#pragma unroll
+    for (int m = 0; m < TILES; ++m) h[m] = fma(c, r[m], h[m]);
+}
 
 // One coordinate-descent solve for the sample owned by this warp.
 template <typename T, int TILES, bool PACKED>
-__device__ __forceinline__ int cd_solve_warp(const T *sG, const T *__restrict__ Gs, int k, int lane,
+__device__ __forceinline__ int cd_solve_warp(unsigned sbase, const T *__restrict__ Gs, int k, int lane,
                                              T (&w)[TILES], const T (&q)[TILES], T ynorm2, T alpha,
                                              T beta, T tol, int max_iter, bool positive)
 {
     T h[TILES], r[TILES], inv[TILES];
-    unsigned zmask[TILES];
+    unsigned dead = 0;      // bit J: my coordinate 32 J + lane has a zero diagonal (or is padding)
     // 1 / (Q[c,c] + beta) for my own coordinates, once per sample.  The per-step division of
     // the reference (:372-373) becomes multiply + one Newton correction (correctly rounded in
     // all but pathological cases), which keeps the IEEE-division slow path -- triggered by the
@@ -140,30 +173,24 @@ __device__ __forceinline__ int cd_solve_warp(const T *sG, const T *__restrict__ 
     for (int J = 0; J < TILES; ++J) {
         const int c = J * CD_TILE + lane;
         T dg;
-        if (PACKED) dg = sG[(cd_tri(J) + J) * CD_TILE_ELEMS + lane * CD_TILE + ((2 * lane) & 31)];
+        if (PACKED) dg = lds_real(sbase + (unsigned)sizeof(T) * (unsigned)((cd_tri(J) + J) * CD_TILE_ELEMS + lane * CD_TILE + ((2 * lane) & 31)), T(0));
         else        dg = c < k ? Gs[(int64_t)c * k + c] : T(0);
+        if (dg == T(0) || c >= k) dead |= (1u << J);
         inv[J] = T(1) / (dg + beta);
+        h[J] = T(0);
     }
     // ---- H = Q w accumulated column by column (Q symmetric)  [ref: :340-347] ----
 #pragma unroll
-    for (int J = 0; J < TILES; ++J) h[J] = T(0);
-#pragma unroll
     for (int J = 0; J < TILES; ++J) {
-        unsigned zm = 0;
-        for (int l = 0; l < CD_TILE; ++l) {
-            const int c = J * CD_TILE + l;
-            if (c >= k) { zm |= (0xffffffffu << l); break; }
+        const int lmax = min(CD_TILE, k - J * CD_TILE);
+        for (int l = 0; l < lmax; ++l) {
             const T wc = __shfl_sync(kFullMask, w[J], l);
-            if (PACKED) cd_row_packed<T, TILES>(sG, J, l, lane, r);
-            else        cd_row_global<T, TILES>(Gs, k, c, lane, r);
-            const T diag = __shfl_sync(kFullMask, r[J], l);
-            if (diag == T(0)) zm |= (1u << l);
             if (wc != T(0)) {
-#pragma unroll
-                for (int JJ = 0; JJ < TILES; ++JJ) h[JJ] = fma(wc, r[JJ], h[JJ]);
+                if (PACKED) cd_row_packed<T, TILES>(sbase, J, l, lane, r);
+                else        cd_row_global<T, TILES>(Gs, k, J * CD_TILE + l, lane, r);
+                cd_axpy_tiles<TILES>(h, r, wc);
             }
         }
-        zmask[J] = zm;
     }
 
     const T d_w_tol = tol;
@@ -171,20 +198,20 @@ __device__ __forceinline__ int cd_solve_warp(const T *sG, const T *__restrict__ 
     int sweeps = 0;
     for (int it = 0; it < max_iter; ++it) {
         sweeps = it + 1;
-        T w_max = T(0), d_w_max = T(0);
+        T w0[TILES];
+#pragma unroll
+        for (int J = 0; J < TILES; ++J) w0[J] = w[J];
 #pragma unroll
         for (int J = 0; J < TILES; ++J) {
-            if (zmask[J] == 0xffffffffu) continue;        // tile entirely padding / zero diagonal
+            const int lmax = min(CD_TILE, k - J * CD_TILE);
+            const bool my_dead = (dead >> J) & 1u;
 #pragma unroll 2
-            for (int l = 0; l < CD_TILE; ++l) {
-                if ((zmask[J] >> l) & 1u) continue;       // Q[c,c] == 0 -> skip  [ref: :357-358]
-                const int c = J * CD_TILE + l;
-                if (PACKED) cd_row_packed<T, TILES>(sG, J, l, lane, r);
-                else        cd_row_global<T, TILES>(Gs, k, c, lane, r);
+            for (int l = 0; l < lmax; ++l) {
+                if (PACKED) cd_row_packed<T, TILES>(sbase, J, l, lane, r);
+                else        cd_row_global<T, TILES>(Gs, k, J * CD_TILE + l, lane, r);
                 const T w_old = __shfl_sync(kFullMask, w[J], l);
                 // H -= w_old Q[c,:] -- branch-free: a zero coefficient leaves H bit-unchanged
-#pragma unroll
-                for (int JJ = 0; JJ < TILES; ++JJ) h[JJ] = fma(-w_old, r[JJ], h[JJ]);
+                cd_axpy_tiles<TILES>(h, r, -w_old);
                 // candidate for "my" coordinate of tile J; only lane l's value is consumed
                 const T tmp = q[J] - h[J];
                 const T mag = t_abs(tmp) - alpha;
@@ -193,16 +220,23 @@ __device__ __forceinline__ int cd_solve_warp(const T *sG, const T *__restrict__ 
                 const T den = r[J] + beta;                             // r[J] on lane l is Q[c,c]
                 T cand = ms * inv[J];
                 cand = fma(fma(-cand, den, ms), inv[J], cand);         // Newton step: ms / den
+                cand = my_dead ? w[J] : cand;                          // Q[c,c] == 0: coordinate skipped [ref: :357-358]
                 const T w_new = __shfl_sync(kFullMask, cand, l);
                 w[J] = (lane == l) ? w_new : w[J];
-#pragma unroll
-                for (int JJ = 0; JJ < TILES; ++JJ) h[JJ] = fma(w_new, r[JJ], h[JJ]);
-                const T d = t_abs(w_new - w_old);
-                if (d > d_w_max) d_w_max = d;
-                const T aw = t_abs(w_new);
-                if (aw > w_max) w_max = aw;
+                cd_axpy_tiles<TILES>(h, r, w_new);
             }
         }
+        // max |w| and max |delta w| of this sweep over the visited coordinates [ref: :379-386]
+        T w_max = T(0), d_w_max = T(0);
+#pragma unroll
+        for (int J = 0; J < TILES; ++J) {
+            const T aw = ((dead >> J) & 1u) ? T(0) : t_abs(w[J]);
+            const T dw = t_abs(w[J] - w0[J]);
+            w_max = aw > w_max ? aw : w_max;
+            d_w_max = dw > d_w_max ? dw : d_w_max;
+        }
+        w_max = warp_max(w_max);
+        d_w_max = warp_max(d_w_max);
         if (w_max == T(0) || d_w_max / w_max < d_w_tol || it == max_iter - 1) {
             // ---- duality gap  [ref: :388-427] ----
             T qw = T(0), wh = T(0), w2 = T(0), l1 = T(0);
@@ -271,8 +305,8 @@ __global__ void cd_regression_kernel(const T *__restrict__ G, int64_t g_stride, 
             q[J] = c < k ? qrow[c] : T(0);
         }
         const T *Gs = G + (int64_t)ii * g_stride;
-        const int sw = cd_solve_warp<T, TILES, PACKED>(sG, Gs, k, lane, w, q, xnorm2[ii], alpha, beta, tol,
-                                                       max_iter, positive != 0);
+        const int sw = cd_solve_warp<T, TILES, PACKED>((unsigned)__cvta_generic_to_shared(sG), Gs, k, lane, w, q,
+                                                       xnorm2[ii], alpha, beta, tol, max_iter, positive != 0);
 #pragma unroll
         for (int J = 0; J < TILES; ++J) {
             const int c = J * CD_TILE + lane;
