@@ -9,6 +9,7 @@
 
 #include "basic_kernels.cuh"
 #include "bcd_kernels.cuh"
+#include "bcd_pilot.cuh"
 #include "cd_kernels.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -93,6 +94,8 @@ int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "bcd_cluster")) ctx->opt_bcd_cluster = value;
     else if (!strcmp(name, "cd_warps")) ctx->opt_cd_warps = value;
     else if (!strcmp(name, "force_global_gram")) ctx->opt_force_global_gram = value;
+    else if (!strcmp(name, "bcd_timing")) ctx->opt_bcd_timing = value;
+    else if (!strcmp(name, "bcd_pilot")) ctx->opt_bcd_pilot = value;
     else { set_error("unknown option %s", name); return MODL_EINVAL; }
     return MODL_OK;
 }
@@ -120,6 +123,34 @@ int modl_ctx_profile_read(modl_ctx *ctx, double *h_ms, int64_t *h_steps)
     return MODL_OK;
 }
 
+// debug: mean clock cycles between the 8 stamps of the last dictionary-update launch (7 gaps)
+int modl_debug_bcd_timing(modl_ctx *ctx, double *h_gaps7)
+{
+    MODL_REQUIRE(ctx && h_gaps7 && ctx->bcd_timing_k > 0 && ctx->slot_ptr[WS_MISC], "no timing recorded");
+    const int k = ctx->bcd_timing_k;
+    std::vector<long long> t((size_t)8 * k);
+    MODL_CUDA_TRY(cudaDeviceSynchronize());
+    MODL_CUDA_TRY(cudaMemcpy(t.data(), ctx->slot_ptr[WS_MISC], sizeof(long long) * t.size(), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < 7; ++j) {
+        double acc = 0;
+        for (int i = 1; i < k; ++i) acc += (double)(t[(size_t)i * 8 + j + 1] - t[(size_t)i * 8 + j]);
+        h_gaps7[j] = acc / (k - 1);
+    }
+    if (getenv("MODL_BCD_TIMING_VERBOSE")) {
+        std::vector<long long> x(16 + 2 * ((size_t)k / 8 + 1));
+        cudaMemcpy(x.data(), (long long *)ctx->slot_ptr[WS_MISC] + 8 * k, sizeof(long long) * x.size(), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "bcd pilot: prologue %lld, loop %lld, final sync %lld, write-back %lld cycles; first atom at +%lld\n",
+                x[1] - x[0], x[2] - x[1], x[3] - x[2], x[4] - x[3], t[0] - x[0]);
+        double wsync = 0, blk = 0;
+        int nb = k / 8;
+        for (int b = 0; b < nb; ++b) wsync += (double)(x[16 + 2 * b + 1] - x[16 + 2 * b]);
+        for (int b = 1; b < nb; ++b) blk += (double)(x[16 + 2 * b] - x[16 + 2 * (b - 1)]);
+        fprintf(stderr, "bcd pilot: mean wait for workers %.0f, mean block period %.0f cycles; atom 8->9 gap %lld, atom 7 end -> block1 start %lld\n",
+                wsync / nb, blk / (nb - 1), t[9 * 8] - t[8 * 8 + 7], x[16 + 2] - t[7 * 8 + 7]);
+    }
+    return MODL_OK;
+}
+
 // Synchronises `stream` and reports (then clears) the sticky numerical status:
 // MODL_ENOTSPD if a Cholesky pivot was non-positive since the last check.
 int modl_ctx_check_info(modl_ctx *ctx, void *stream)
@@ -140,6 +171,9 @@ int modl_ctx_check_info(modl_ctx *ctx, void *stream)
 }  // extern "C"
 
 namespace modl {
+
+// leading dimension of the gathered subset panels: padded so that rows start 16-byte aligned
+static inline int64_t panel_ld(int64_t s) { return s > 0 ? round_up(s, 4) : 4; }
 
 static inline int grid_for(modl_ctx *ctx, int64_t work, int per_sm = 8)
 {
@@ -295,6 +329,24 @@ static int regression(modl_ctx *ctx, const T *G, int64_t g_stride, T *Dx, const 
 // ---------------------------------------------------------------------------------------
 // dictionary update
 // ---------------------------------------------------------------------------------------
+template <typename T, bool ENET>
+static const void *pilot_kernel_for_e(int ncl)
+{
+    switch (ncl) {
+        case 1: return (const void *)bcd_pilot_kernel<T, 1, ENET>;
+        case 2: return (const void *)bcd_pilot_kernel<T, 2, ENET>;
+        case 3: return (const void *)bcd_pilot_kernel<T, 3, ENET>;
+        case 4: return (const void *)bcd_pilot_kernel<T, 4, ENET>;
+        case 5: return (const void *)bcd_pilot_kernel<T, 5, ENET>;
+        default: return (const void *)bcd_pilot_kernel<T, 6, ENET>;
+    }
+}
+template <typename T>
+static const void *pilot_kernel_for(int ncl, bool enet)
+{
+    return enet ? pilot_kernel_for_e<T, true>(ncl) : pilot_kernel_for_e<T, false>(ncl);
+}
+
 template <typename T>
 static int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *comp_norm,
                       const int32_t *d_order, int64_t k, int64_t s, T l1_ratio, int positive, cudaStream_t st)
@@ -310,38 +362,47 @@ static int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C
     P.Dp = Dp; P.Bp = Bp; P.C = C; P.comp_norm = comp_norm; P.order = d_order;
     P.k = (int)k; P.s = (int)s; P.lds = (int)lds; P.l1_ratio = l1_ratio; P.positive = positive;
 
-    int nblk = 0, use_cluster = 0, d_in_smem = 0;
+    int nblk = 0, use_cluster = 0, d_in_smem = 0, use_pilot = 0;
     int64_t cols = 0;
     size_t smem = 0;
     // 1) a single thread-block cluster with the panel resident in shared memory
     if (ctx->cluster_ok && ctx->opt_bcd_cluster >= 2) {
         for (int cs = 16; cs >= 2 && !nblk; cs >>= 1) {
             if (cs > ctx->opt_bcd_cluster) continue;
-            const int64_t c = ceil_div(s, cs), ncp = round_up(c, 32);
-            const size_t need = base_smem(ncp) + (size_t)k * ncp * sizeof(T);
-            if (need > budget || ncp > 2 * BCD_THREADS) continue;
-            if (cs > 8) {
-                if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            const int64_t c = round_up(ceil_div(s, cs), 4), ncp = round_up(c, 32);
+            for (int pilot = ctx->opt_bcd_pilot ? 1 : 0; pilot >= 0 && !nblk; --pilot) {
+                size_t need;
+                if (pilot) {
+                    if (ncp > 192) continue;
+                    need = bcd_pilot_smem_bytes<T>(k, ncp);
+                } else {
+                    need = base_smem(ncp) + (size_t)k * ncp * sizeof(T);
+                    if (ncp > 2 * BCD_THREADS) continue;
+                }
+                if (need > budget) continue;
+                const void *fn = pilot ? pilot_kernel_for<T>((int)(ncp / 32), l1_ratio != T(0)) : (const void *)kern;
+                if (cs > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
                     cudaGetLastError();
                     continue;
                 }
+                if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess) {
+                    cudaGetLastError();
+                    continue;
+                }
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(cs); cfg.blockDim = dim3(pilot ? BP_THREADS : BCD_THREADS);
+                cfg.dynamicSmemBytes = need; cfg.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                int nclusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters < 1) {
+                    cudaGetLastError();
+                    continue;
+                }
+                nblk = cs; use_cluster = 1; d_in_smem = 1; cols = c; smem = need; use_pilot = pilot;
             }
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess) {
-                cudaGetLastError();
-                continue;
-            }
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(cs); cfg.blockDim = dim3(BCD_THREADS); cfg.dynamicSmemBytes = need; cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
-                cudaGetLastError();
-                continue;
-            }
-            nblk = cs; use_cluster = 1; d_in_smem = 1; cols = c; smem = need;
         }
     }
     // 2) cooperative launch over the SMs with a global barrier
@@ -368,17 +429,24 @@ static int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C
     P.cols_per_cta = (int)cols; P.chunk = (int)cw; P.d_in_smem = d_in_smem; P.use_cluster = use_cluster;
 
     // exchange workspace: [barrier 256 B][part 2*nblk*4][vrow 2*s]
-    const size_t n_t = (size_t)(2 * nblk * BCD_NPART) + 2 * (size_t)s;
+    const size_t n_t = (size_t)(2 * nblk * BCD_NPART) + (size_t)nblk * k + 2 * (size_t)s;
     unsigned char *base = nullptr;
     MODL_TRY(ws<unsigned char>(ctx, WS_BCD_SYNC, 256 + n_t * sizeof(T), &base));
     P.bar = reinterpret_cast<unsigned *>(base);
     T *tb = reinterpret_cast<T *>(base + 256);
-    P.part = tb; tb += 2 * nblk * BCD_NPART;
+    P.part = tb; tb += 2 * nblk * BCD_NPART + (size_t)nblk * k;
     P.vrow = tb;
     MODL_CUDA_TRY(cudaMemsetAsync(P.bar, 0, 256, st));
+    P.timing = nullptr;
+    if (ctx->opt_bcd_timing) {
+        long long *tbuf = nullptr;
+        MODL_TRY(ws<long long>(ctx, WS_MISC, (size_t)(8 * k + 16 + 2 * ceil_div(k, 8) + 8), &tbuf));
+        P.timing = tbuf;
+        ctx->bcd_timing_k = (int)k;
+    }
 
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(BCD_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(use_pilot ? BP_THREADS : BCD_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     if (use_cluster) {
         at[0].id = cudaLaunchAttributeClusterDimension;
@@ -388,7 +456,12 @@ static int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C
         at[0].val.cooperative = 1;
     }
     cfg.attrs = at; cfg.numAttrs = 1;
-    MODL_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P));
+    if (use_pilot) {
+        void *args[] = {&P};
+        MODL_CUDA_TRY(cudaLaunchKernelExC(&cfg, pilot_kernel_for<T>((int)(round_up(cols, 32) / 32), l1_ratio != T(0)), args));
+    } else {
+        MODL_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P));
+    }
     MODL_LAUNCH_CHECK(ctx);
     return MODL_OK;
 }
@@ -417,7 +490,7 @@ static int update_dict_impl(modl_ctx *ctx, T *components, int64_t ldd, const T *
 {
     MODL_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (variational) or 1 (sgd)");
     if (k <= 0) return MODL_OK;
-    const int64_t lds = s > 0 ? s : 1;
+    const int64_t lds = panel_ld(s);
     T *Bp = nullptr;
     prof_mark(ctx, st, MODL_PROF_DICT_PREP);
     MODL_TRY(ws<T>(ctx, WS_PANEL_B, (size_t)(k * lds), &Bp));
@@ -515,7 +588,7 @@ static int gram_dx_impl(modl_ctx *ctx, const T *D, int64_t ldd, const T *X, int6
         return MODL_OK;
     }
     MODL_REQUIRE(s >= 0 && s <= p, "subset length");
-    const int64_t lds = s > 0 ? s : 1;
+    const int64_t lds = panel_ld(s);
     T *panel = nullptr;
     MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)((k + b) * lds), &panel));
     T *Dsub = panel, *Xsub = panel + k * lds;
@@ -582,7 +655,7 @@ static int update_dict_entry(modl_ctx *ctx, T *components, int64_t ldd, const T 
     MODL_REQUIRE(ctx && components && B && C && comp_norm && subset && h_order, "update_dict arguments");
     MODL_REQUIRE(s >= 0 && s <= p, "subset length");
     T *panel = nullptr;
-    MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)(k * (s > 0 ? s : 1)), &panel));
+    MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)(k * panel_ld(s)), &panel));
     return update_dict_impl<T>(ctx, components, ldd, B, ldb, C, comp_norm, G_full, subset, s, h_order, k, p, comp_l1_ratio,
                                comp_pos, mode, w, step_size, panel, false, (cudaStream_t)stream);
 }
@@ -695,7 +768,7 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     // ---- _update_dict [ref: :650-715] ----
     T *Dpanel = panel_keep;
     bool ready = panel_keep != nullptr;
-    if (!ready) MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)(k * (s > 0 ? s : 1)), &Dpanel));
+    if (!ready) MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)(k * panel_ld(s)), &Dpanel));
     MODL_TRY(update_dict_impl<T>(ctx, D, p, static_cast<const T *>(q->B), p, static_cast<const T *>(q->C),
                                  static_cast<T *>(q->comp_norm), q->G_agg == MODL_AGG_FULL ? static_cast<T *>(q->G_full) : (T *)nullptr,
                                  d_subset, s, q->h_order, k, p, (T)q->comp_l1_ratio, q->comp_pos, q->optimizer_sgd ? 1 : 0, q->w,

@@ -70,6 +70,7 @@ struct BcdParams {
     unsigned *bar;       // global barrier counter (zero on entry)
     T *part;             // [2][nblk][BCD_NPART]       (global exchange, use_cluster == 0)
     T *vrow;             // [2][s]   candidate rows (elastic-net ball only)
+    long long *timing;   // debug: [k][8] clock64 stamps of CTA 0 (NULL = off)
 };
 
 template <typename T>
@@ -80,6 +81,44 @@ __device__ __forceinline__ void cp_async_elem(T *smem_dst, const T *gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// ---- cluster exchange: st.async pushes 16 (float) / 32 (double) bytes into a peer's slot and
+// completes that many bytes on the PEER's mbarrier: one-way latency, no fences, no barrier ----
+__device__ __forceinline__ unsigned mapa_u32(unsigned local_smem_addr, unsigned cta_rank)
+{
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_triplet(unsigned remote_slot, unsigned remote_mbar, float a, float b, float c)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n"
+                 ::"r"(remote_slot), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(0u),
+                   "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_triplet(unsigned remote_slot, unsigned remote_mbar, double a, double b, double c)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];\n"
+                 ::"r"(remote_slot), "l"(__double_as_longlong(a)), "l"(__double_as_longlong(b)), "r"(remote_mbar) : "memory");
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];\n"
+                 ::"r"(remote_slot + 16u), "l"(__double_as_longlong(c)), "l"(0ll), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
 
 __device__ __forceinline__ void bcd_arrive(bool use_cluster, unsigned *bar, unsigned &epoch)
 {
@@ -119,6 +158,15 @@ __device__ __forceinline__ void bcd_wait(bool use_cluster, unsigned *bar, unsign
 // block of rows, so the C row is read as 128-bit and the D slice as 64-bit shared loads
 // (~1.6 instructions per FMA); partial sums of the row blocks are combined in a fixed order.
 template <typename T> struct alignas(2 * sizeof(T)) Pair { T x, y; };
+__device__ __forceinline__ void pair_fma(float c, const Pair<float> &d, Pair<float> &acc)
+{
+    const float2 r = __ffma2_rn(make_float2(c, c), make_float2(d.x, d.y), make_float2(acc.x, acc.y));
+    acc.x = r.x; acc.y = r.y;
+}
+__device__ __forceinline__ void pair_fma(double c, const Pair<double> &d, Pair<double> &acc)
+{
+    acc.x = fma(c, d.x, acc.x); acc.y = fma(c, d.y, acc.y);
+}
 template <typename T> struct alignas(16) Quad { T x, y, z, w; };
 
 template <typename T>
@@ -131,28 +179,24 @@ __device__ __forceinline__ void bcd_row_product(const T *crow, const T *Ds, cons
         const int IG = BCD_THREADS / NP;               // row blocks (>= 1 because ncp <= 2 * BCD_THREADS)
         const int RB = (((k + IG - 1) / IG) + 3) & ~3; // rows per block, multiple of 4
         const int pr = tid % NP, ig = tid / NP;
-        T a0 = T(0), a1 = T(0);
         if (ig < IG) {
             const int r0 = ig * RB, r1 = min(k, r0 + RB);
             const Pair<T> *dcol = reinterpret_cast<const Pair<T> *>(Ds) + pr;      // Ds[i][2*pr .. 2*pr+1]
             const int rs = ncp >> 1;                                              // row stride in pairs
+            Pair<T> accA = {T(0), T(0)}, accB = {T(0), T(0)};                      // two independent FMA chains
             int i = r0;
+#pragma unroll 2
             for (; i + 4 <= r1; i += 4) {
                 const Quad<T> cq = *reinterpret_cast<const Quad<T> *>(crow + i);
-                const T c0 = cq.x, c1 = cq.y, c2 = cq.z, c3 = cq.w;
                 const Pair<T> d0 = dcol[(i + 0) * rs], d1 = dcol[(i + 1) * rs], d2 = dcol[(i + 2) * rs], d3 = dcol[(i + 3) * rs];
-                a0 = fma(c0, d0.x, a0); a1 = fma(c0, d0.y, a1);
-                a0 = fma(c1, d1.x, a0); a1 = fma(c1, d1.y, a1);
-                a0 = fma(c2, d2.x, a0); a1 = fma(c2, d2.y, a1);
-                a0 = fma(c3, d3.x, a0); a1 = fma(c3, d3.y, a1);
+                pair_fma(cq.x, d0, accA);
+                pair_fma(cq.y, d1, accB);
+                pair_fma(cq.z, d2, accA);
+                pair_fma(cq.w, d3, accB);
             }
-            for (; i < r1; ++i) {
-                const T c0 = crow[i];
-                const Pair<T> d0 = dcol[i * rs];
-                a0 = fma(c0, d0.x, a0); a1 = fma(c0, d0.y, a1);
-            }
-            red[ig * ncp + 2 * pr] = a0;
-            red[ig * ncp + 2 * pr + 1] = a1;
+            for (; i < r1; ++i) pair_fma(crow[i], dcol[i * rs], accA);
+            red[ig * ncp + 2 * pr] = accA.x + accB.x;
+            red[ig * ncp + 2 * pr + 1] = accA.y + accB.y;
         }
         __syncthreads();
         for (int c = tid; c < nc; c += BCD_THREADS) {
@@ -215,6 +259,15 @@ bcd_update_kernel(BcdParams<T> P)
     T *Ds = reinterpret_cast<T *>(dscratch + 40);             // k * ncp (optional)
     __shared__ bool sh_inside;
     __shared__ T sh_l;
+    __shared__ __align__(8) unsigned long long xbar[2];      // one mbarrier per atom parity (cluster exchange)
+    const unsigned xbar_addr = (unsigned)__cvta_generic_to_shared(xbar);
+    const unsigned xch_addr = (unsigned)__cvta_generic_to_shared(xch);
+    constexpr unsigned kSlotBytes = BCD_NPART * sizeof(T);
+    if (use_cluster && tid == 0) {
+        mbar_init(xbar_addr, 1);
+        mbar_init(xbar_addr + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
 
     const T *Dg = P.Dp + c0;                                  // my columns of the global panel
     if (d_in_smem) {
@@ -258,6 +311,8 @@ bcd_update_kernel(BcdParams<T> P)
         T *bnext = brow + (par ^ 1) * ncp;
         const T caa = live ? Ccur[a] : T(1);
 
+#define BCD_STAMP(slot) do { if (P.timing && g == 0 && tid == 0 && live) P.timing[(int64_t)oi * 8 + (slot)] = clock64(); } while (0)
+        BCD_STAMP(0);
         // ---------------- S1: candidate row on my columns + partial sums ----------------
         T nb_local = T(0), sv2_local = T(0);
         if (live) {
@@ -278,22 +333,25 @@ bcd_update_kernel(BcdParams<T> P)
         }
         __syncthreads();
         if (wid == 0) {
-            // fixed tree over the warps, then publish to every CTA (slot [par][g])
+            // fixed-order sum over the warps (every lane the same), then publish to every CTA (slot [par][g])
             constexpr int NW = BCD_THREADS / 32;
-            T t0 = lane < NW ? wred[lane * 4] : T(0), t1 = lane < NW ? wred[lane * 4 + 1] : T(0),
-              t2 = lane < NW ? wred[lane * 4 + 2] : T(0);
-            t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
+            T t0 = T(0), t1 = T(0), t2 = T(0);
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { t0 += wred[w * 4]; t1 += wred[w * 4 + 1]; t2 += wred[w * 4 + 2]; }
             if (use_cluster) {
-                if (lane < nblk) {
-                    T *remote = cluster.map_shared_rank(xch, lane) + (par * BCD_MAX_CLUSTER + g) * BCD_NPART;
-                    remote[0] = t0; remote[1] = t1; remote[2] = t2;
-                }
+                if (enet) __threadfence();      // my slice of the candidate row (global) before the signal
+                if (lane == 0) mbar_expect_tx(xbar_addr + 8 * par, (unsigned)nblk * kSlotBytes);   // what I will receive
+                if (lane < nblk)
+                    st_async_triplet(mapa_u32(xch_addr + (unsigned)(par * BCD_MAX_CLUSTER + g) * kSlotBytes, (unsigned)lane),
+                                     mapa_u32(xbar_addr + 8 * par, (unsigned)lane), t0, t1, t2);
             } else if (lane == 0) {
                 T *dst = P.part + ((int64_t)par * nblk + g) * BCD_NPART;
                 dst[0] = t0; dst[1] = t1; dst[2] = t2;
             }
         }
-        bcd_arrive(use_cluster, P.bar, epoch);
+        BCD_STAMP(1);
+        if (!use_cluster) bcd_arrive(false, P.bar, epoch);
+        BCD_STAMP(2);
 
         // ---------------- S2 (overlaps the barrier): prefetch + next atom's row product ----------------
         if (oi + 2 < k) {
@@ -306,7 +364,14 @@ bcd_update_kernel(BcdParams<T> P)
         if (an >= 0)
             bcd_row_product<T>(Cnext, Ds, Dg, lds, d_in_smem, k, nc, ncp, CW, red, dotn);
 
-        bcd_wait(use_cluster, P.bar, (unsigned)nblk, epoch);
+        BCD_STAMP(3);
+        if (use_cluster) {
+            mbar_wait(xbar_addr + 8 * par, (unsigned)((oi >> 1) & 1));
+            if (enet) __threadfence();
+        } else {
+            bcd_wait(false, P.bar, (unsigned)nblk, epoch);
+        }
+        BCD_STAMP(4);
 
         // ---------------- S3: global sums, projection, write-back, fix-up ----------------
         T nb = T(0), sv2 = T(0), na_prev = T(0);
@@ -316,10 +381,13 @@ bcd_update_kernel(BcdParams<T> P)
             const bool on = lane < nblk;
             nb = warp_sum(on ? src[0] : T(0)); sv2 = warp_sum(on ? src[1] : T(0)); na_prev = warp_sum(on ? src[2] : T(0));
         } else {
+            // lanes stride over the CTA partials, then the same shuffle tree in every warp of every CTA
             const T *src = P.part + (int64_t)par * nblk * BCD_NPART;
-            for (int q = 0; q < nblk; ++q) {
-                nb += __ldcg(src + q * BCD_NPART); sv2 += __ldcg(src + q * BCD_NPART + 1); na_prev += __ldcg(src + q * BCD_NPART + 2);
+            T p0 = T(0), p1 = T(0), p2 = T(0);
+            for (int q = lane; q < nblk; q += 32) {
+                p0 += __ldcg(src + q * BCD_NPART); p1 += __ldcg(src + q * BCD_NPART + 1); p2 += __ldcg(src + q * BCD_NPART + 2);
             }
+            nb = warp_sum(p0); sv2 = warp_sum(p1); na_prev = warp_sum(p2);
         }
         if (a_prev >= 0 && tid == 0)
             cnorm[a_prev] = radius_prev - na_prev;                    // comp_norm_[k] -= subset_norm  [ref: :690-692]
@@ -342,7 +410,9 @@ bcd_update_kernel(BcdParams<T> P)
             __syncthreads();
             if (!sh_inside) { mode = 2; lthr = sh_l; }
         }
+        BCD_STAMP(5);
         cp_async_wait_all();                                          // next C / B rows have landed (this thread's part)
+        BCD_STAMP(6);
         const T can = (an >= 0) ? Cnext[a] : T(0);
         na_carry = T(0);
         for (int c = tid; c < nc; c += BCD_THREADS) {
@@ -365,9 +435,15 @@ bcd_update_kernel(BcdParams<T> P)
         radius_prev = radius;
         a_prev = a;
         __syncthreads();
+        BCD_STAMP(7);
     }
+#undef BCD_STAMP
     // ---- write-back ----
     __syncthreads();
+    if (use_cluster) {   // nobody leaves while a peer could still address its shared memory
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    }
     if (d_in_smem) {
         for (int e = tid; e < k * ncp; e += BCD_THREADS) {
             const int i = e / ncp, c = e % ncp;

@@ -1,0 +1,436 @@
+// bcd_pilot.cuh -- latency-optimised dictionary update for panels that fit the shared memory of
+// ONE thread-block cluster (the common case: k * s * sizeof(T) <= ~2.5 MB, e.g. BASELINE
+// config 2: 256 x 1250 floats).  Same mathematics and same fixed-order reductions as
+// bcd_update_kernel (bcd_kernels.cuh) [ref: modl/decomposition/dict_fact.py:675-694]; what
+// changes is how the k-step dependent chain is scheduled on the SM:
+//
+//   * warp specialisation.  Warp 0 of every CTA (the "pilot") owns the critical path of an atom
+//     step -- candidate row on the CTA's columns, three partial sums, all-to-all exchange,
+//     projection -- entirely with warp-level primitives: no __syncthreads on the chain.
+//   * blocked look-ahead.  The row products C[a,:] . D_sub that every atom needs are produced by
+//     the other 7 warps ("workers") for M = 8 atoms at a time as an 8 x k x cols register-tiled
+//     product (D slice read from shared memory once per 8 atoms instead of once per atom, FFMA2),
+//     one block AHEAD of the pilot and against the dictionary as it was one block ago; the pilot
+//     repairs the staleness with rank-1 corrections  sum_j' C[a, a_j'] (d_new - d_old)_j'  over the
+//     <= 8 + 8 atoms updated since (exact algebra, a handful of FMAs per column).
+//   * the exchange is st.async + mbarrier over distributed shared memory (one-way latency).
+//
+// Roles synchronise once per block of 8 atoms with named barriers; new atom rows are staged and
+// committed to the shared D slice at block boundaries so the workers always read a consistent
+// snapshot.
+#pragma once
+#include "bcd_kernels.cuh"
+
+namespace modl {
+
+constexpr int BP_M = 8;                       // atoms per look-ahead block
+constexpr int BP_THREADS = 256;               // warp 0 = pilot, warps 1..7 = workers
+constexpr int BP_WORKERS = BP_THREADS - 32;
+enum { BP_BAR_PRODUCT = 1, BP_BAR_SNAPSHOT = 2, BP_BAR_WORKERS = 3 };
+
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+
+// shared-memory footprint (elements of T, then bytes) -- must match the carve-up in the kernel
+template <typename T>
+__host__ __device__ inline size_t bcd_pilot_smem_bytes(int64_t k, int64_t ncp)
+{
+    const int64_t kp = round_up(k, 32);
+    const int64_t np = ncp / 2;
+    const int64_t igw = BP_WORKERS / np > 0 ? BP_WORKERS / np : 1;
+    const int64_t elems = 2 * kp * BP_M          // Cblk
+                          + 2 * BP_M * ncp       // Rbuf
+                          + 2 * BP_M * ncp       // brows
+                          + 4 * BP_M * ncp       // vnew, delta (two blocks each)
+                          + 2 * kp               // cnorm, rad
+                          + 2 * BCD_MAX_CLUSTER * BCD_NPART   // xch
+                          + igw * BP_M * ncp     // red
+                          + 2 * 224;             // per-block tables (two coefficient tables, diagonals, atom ids), x2
+    return (size_t)elems * sizeof(T) + 40 * sizeof(double) + (size_t)k * ncp * sizeof(T);
+}
+
+// warp-level version of enet_threshold_block (basic_kernels.cuh): same monotone active-set fixed point.
+template <typename T, typename Load>
+__device__ T enet_threshold_warp(Load load, int n, T radius_over_l1, T gamma, bool *inside)
+{
+    const int lane = threadIdx.x & 31;
+    double s1 = 0, s2 = 0, cnt = 0;
+    for (int j = lane; j < n; j += 32) {
+        const double a = fabs((double)load(j));
+        s1 += a; s2 += a * a; cnt += 1;
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2); cnt = warp_sum(cnt);
+    const double g = (double)gamma, R = (double)radius_over_l1;
+    const double norm = s1 + 0.5 * g * s2;
+    if ((T)norm <= radius_over_l1) { *inside = true; return T(0); }
+    *inside = false;
+    double l = 0;
+    for (int it = 0; it < 64; ++it) {
+        const double sa = s1 + 0.5 * g * s2;
+        double lnew;
+        if (g != 0) {
+            const double qa = g * g * R + 0.5 * g * cnt, qd = 2 * R * g + cnt, qc = R - sa;
+            lnew = (-qd + sqrt(qd * qd - 4 * qa * qc)) / (2 * qa);
+        } else {
+            lnew = (sa - R) / cnt;
+        }
+        double n1 = 0, n2 = 0, nc = 0;
+        for (int j = lane; j < n; j += 32) {
+            const double a = fabs((double)load(j));
+            if (a > lnew) { n1 += a; n2 += a * a; nc += 1; }
+        }
+        n1 = warp_sum(n1); n2 = warp_sum(n2); nc = warp_sum(nc);
+        l = lnew;
+        if (nc == cnt || nc == 0) break;
+        s1 = n1; s2 = n2; cnt = nc;
+    }
+    return (T)l;
+}
+
+template <typename T, int NCL, bool ENET>
+__global__ void __launch_bounds__(BP_THREADS, 1)
+bcd_pilot_kernel(BcdParams<T> P)
+{
+    extern __shared__ __align__(16) unsigned char bp_smem_raw[];
+    const int k = P.k, s = P.s, lds = P.lds;
+    const int nblk = gridDim.x, g = blockIdx.x;
+    const int c0 = min(s, g * P.cols_per_cta);
+    const int c1 = min(s, c0 + P.cols_per_cta);
+    const int nc = c1 - c0;
+    const int ncp = (int)round_up(P.cols_per_cta, 32);
+    const int kp = (int)round_up(k, 32);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr bool enet = ENET;
+    const int nbk = (k + BP_M - 1) / BP_M;
+    const int NP = ncp >> 1;
+    const int IGW = max(1, BP_WORKERS / NP);
+    constexpr int TAB = 224;                                  // per-block table: cfm 64 | cfp 64 | rcv 8 | cav 8 | ordc 16 ints
+
+    // ---- shared memory carve-up (see bcd_pilot_smem_bytes) ----
+    T *Cblk = reinterpret_cast<T *>(bp_smem_raw);            // [2][kp][M] : C[A[j], i] at [i*M + j]
+    T *Rbuf = Cblk + 2 * kp * BP_M;                           // [2][M][ncp] look-ahead products
+    T *brows = Rbuf + 2 * BP_M * ncp;                         // [2][M][ncp] B_sub rows
+    T *vnew = brows + 2 * BP_M * ncp;                         // [2][M][ncp] staged new rows, by block parity
+    T *delta = vnew + 2 * BP_M * ncp;                         // [2][M][ncp] new - old, by block parity
+    T *cnorm = delta + 2 * BP_M * ncp;                        // [kp] comp_norm_ on entry
+    T *rad = cnorm + kp;                                      // [kp] radius used for every atom
+    T *xch = rad + kp;                                        // [2][16][4] exchange slots
+    T *red = xch + 2 * BCD_MAX_CLUSTER * BCD_NPART;           // [IGW][M][ncp]
+    T *tabs = red + (size_t)IGW * BP_M * ncp;                 // [2][TAB]
+    double *dscratch = reinterpret_cast<double *>(tabs + 2 * TAB);
+    T *Ds = reinterpret_cast<T *>(dscratch + 40);             // [k][ncp]
+    __shared__ __align__(8) unsigned long long xbar[2];
+    const unsigned xbar_addr = (unsigned)__cvta_generic_to_shared(xbar);
+    const unsigned xch_addr = (unsigned)__cvta_generic_to_shared(xch);
+    constexpr unsigned kSlotBytes = BCD_NPART * sizeof(T);
+
+    long long *xstamp = (P.timing && g == 0 && tid == 0) ? P.timing + (int64_t)8 * k : nullptr;   // debug
+    if (xstamp) xstamp[0] = clock64();
+    const T *Dg = P.Dp + c0;
+    constexpr int VE = 16 / (int)sizeof(T);                   // elements per 128-bit access
+    const bool vec_ok = (lds % VE == 0) && (c0 % VE == 0) && ((reinterpret_cast<uintptr_t>(P.Dp) & 15) == 0);
+    if (vec_ok) {
+        const int nv = ncp / VE;
+#pragma unroll 4
+        for (int e = tid; e < k * nv; e += BP_THREADS) {
+            const int i = e / nv, cv = (e % nv) * VE;
+            alignas(16) T tmp[VE];
+#pragma unroll
+            for (int u = 0; u < VE; ++u) tmp[u] = T(0);
+            if (cv < nc) *reinterpret_cast<uint4 *>(tmp) = *reinterpret_cast<const uint4 *>(Dg + (int64_t)i * lds + cv);
+#pragma unroll
+            for (int u = 0; u < VE; ++u) Ds[i * ncp + cv + u] = (cv + u < nc) ? tmp[u] : T(0);
+        }
+    } else {
+        for (int e = tid; e < k * ncp; e += BP_THREADS) {
+            const int i = e / ncp, c = e % ncp;
+            Ds[e] = (c < nc) ? Dg[(int64_t)i * lds + c] : T(0);
+        }
+    }
+    for (int i = tid; i < k; i += BP_THREADS) cnorm[i] = P.comp_norm[i];
+    for (int e = tid; e < 4 * BP_M * ncp; e += BP_THREADS) vnew[e] = T(0);       // vnew and delta (contiguous)
+    for (int e = tid; e < 2 * BCD_MAX_CLUSTER * BCD_NPART; e += BP_THREADS) xch[e] = T(0);
+    if (tid == 0) {
+        mbar_init(xbar_addr, 1);
+        mbar_init(xbar_addr + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    // every peer is resident and its mbarriers initialised before anybody sends
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    if (xstamp) xstamp[1] = clock64();
+
+    if (wid != 0) {
+        // =========================== workers: everything off the critical path ===========================
+        const int wt = tid - 32;
+        const int pr = wt % NP, ig = wt / NP;
+        const int RB = (((k + IGW - 1) / IGW) + 3) & ~3;
+        for (int b = 0; b < nbk; ++b) {
+            if (b > 0) named_sync(BP_BAR_SNAPSHOT, BP_THREADS);     // pilot is done with block b-2 and its buffers
+            const int nb = b & 1;
+            const int mb = min(BP_M, k - b * BP_M);
+            T *Cb = Cblk + nb * kp * BP_M;
+            T *Rb = Rbuf + nb * BP_M * ncp;
+            T *Bb = brows + nb * BP_M * ncp;
+            T *tab = tabs + nb * TAB;
+            // coefficients (transposed) and B_sub rows of the block's atoms: all copies in flight at once
+            for (int e = wt; e < k * BP_M; e += BP_WORKERS) {
+                const int j = e / k, i = e % k;
+                if (j < mb) cp_async_elem(Cb + i * BP_M + j, P.C + (int64_t)P.order[b * BP_M + j] * k + i);
+                else Cb[i * BP_M + j] = T(0);
+            }
+            for (int e = wt; e < BP_M * ncp; e += BP_WORKERS) {
+                const int j = e / ncp, c = e % ncp;
+                if (j < mb && c < nc) cp_async_elem(Bb + e, P.Bp + (int64_t)P.order[b * BP_M + j] * lds + c0 + c);
+                else Bb[e] = T(0);
+            }
+            cp_async_commit();
+            // commit the rows staged two blocks ago: the shared slice becomes the dictionary at the start of block b-1
+            if (b >= 2) {
+                const T *vs = vnew + nb * BP_M * ncp;
+                for (int e = wt; e < BP_M * ncp; e += BP_WORKERS) {
+                    const int jp = e / ncp, c = e % ncp;
+                    Ds[P.order[(b - 2) * BP_M + jp] * ncp + c] = vs[e];
+                }
+            }
+            cp_async_wait_all();
+            named_sync(BP_BAR_WORKERS, BP_WORKERS);
+            // small tables for the pilot: repair coefficients, diagonals, atom ids
+            if (wt < BP_M * BP_M) {
+                const int j = wt / BP_M, jp = wt % BP_M;
+                tab[wt] = (jp < j && j < mb) ? Cb[P.order[b * BP_M + jp] * BP_M + j] : T(0);                   // cfm
+                tab[64 + wt] = (b > 0 && j < mb) ? Cb[P.order[(b - 1) * BP_M + jp] * BP_M + j] : T(0);         // cfp
+            } else if (wt < BP_M * BP_M + BP_M) {
+                const int j = wt - BP_M * BP_M;
+                const T d = (j < mb) ? Cb[P.order[b * BP_M + j] * BP_M + j] : T(1);
+                tab[136 + j] = d;                                                                             // cav
+                tab[128 + j] = T(1) / d;                                                                      // rcv
+            } else if (wt < BP_M * BP_M + 2 * BP_M) {
+                const int j = wt - BP_M * BP_M - BP_M;
+                reinterpret_cast<int *>(tab + 144)[j] = (j < mb) ? P.order[b * BP_M + j] : 0;                 // ordc
+            }
+            if (ig < IGW) {
+                const int r0 = ig * RB, r1 = min(k, r0 + RB);
+                const Pair<T> *dcol = reinterpret_cast<const Pair<T> *>(Ds) + pr;
+                const int rs = ncp >> 1;
+                Pair<T> acc[BP_M];
+#pragma unroll
+                for (int j = 0; j < BP_M; ++j) acc[j].x = acc[j].y = T(0);
+#pragma unroll 2
+                for (int i = r0; i < r1; ++i) {
+                    const Pair<T> d = dcol[i * rs];
+                    const Quad<T> q0 = *reinterpret_cast<const Quad<T> *>(Cb + i * BP_M);
+                    const Quad<T> q1 = *reinterpret_cast<const Quad<T> *>(Cb + i * BP_M + 4);
+                    pair_fma(q0.x, d, acc[0]); pair_fma(q0.y, d, acc[1]); pair_fma(q0.z, d, acc[2]); pair_fma(q0.w, d, acc[3]);
+                    pair_fma(q1.x, d, acc[4]); pair_fma(q1.y, d, acc[5]); pair_fma(q1.z, d, acc[6]); pair_fma(q1.w, d, acc[7]);
+                }
+#pragma unroll
+                for (int j = 0; j < BP_M; ++j) {
+                    red[((size_t)ig * BP_M + j) * ncp + 2 * pr] = acc[j].x;
+                    red[((size_t)ig * BP_M + j) * ncp + 2 * pr + 1] = acc[j].y;
+                }
+            }
+            named_sync(BP_BAR_WORKERS, BP_WORKERS);
+            for (int e = wt; e < BP_M * ncp; e += BP_WORKERS) {
+                T sum = T(0);
+                for (int gi = 0; gi < IGW; ++gi) sum += red[(size_t)gi * BP_M * ncp + e];   // fixed order
+                Rb[e] = sum;
+            }
+            __threadfence_block();
+            named_arrive(BP_BAR_PRODUCT, BP_THREADS);
+        }
+    } else {
+        // =========================== pilot: the dependent chain ===========================
+        // Lane l owns columns l + 32 m, m < NCL, of the CTA's slice; padded columns carry zeros
+        // through every formula, so the column loops are branch-free and fully unrolled.
+        unsigned xi = 0;                                   // exchange counter
+        long long *tstamp = nullptr;
+#define BP_STAMP(slot) do { if (tstamp && lane == 0) tstamp[(slot)] = clock64(); } while (0)
+        // peer addresses of my slot and of the peer's mbarrier, per parity
+        unsigned rslot[2], rbar[2];
+#pragma unroll
+        for (unsigned par = 0; par < 2; ++par) {
+            const unsigned peer = (unsigned)(lane < nblk ? lane : 0);
+            rslot[par] = mapa_u32(xch_addr + (par * BCD_MAX_CLUSTER + (unsigned)g) * kSlotBytes, peer);
+            rbar[par] = mapa_u32(xbar_addr + 8 * par, peer);
+        }
+        auto exchange = [&](T p0, T p1, T &o0, T &o1) {
+            const unsigned par = xi & 1u;
+            p0 = warp_sum(p0); p1 = warp_sum(p1);
+            BP_STAMP(2);
+            if (enet) __threadfence();
+            if (lane == 0) mbar_expect_tx(xbar_addr + 8 * par, (unsigned)nblk * kSlotBytes);
+            if (lane < nblk) st_async_triplet(rslot[par], rbar[par], p0, p1, T(0));
+            BP_STAMP(3);
+            mbar_wait(xbar_addr + 8 * par, (xi >> 1) & 1u);
+            BP_STAMP(4);
+            if (enet) __threadfence();
+            // slots of absent peers stay zero; both half-warps read the same 16 slots, so a 4-round
+            // butterfly leaves the full sum in every lane (same tree in every CTA -> bit-identical)
+            const T *src = xch + (par * BCD_MAX_CLUSTER + (lane & 15)) * BCD_NPART;
+            T q0 = src[0], q1 = src[1];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                q0 += __shfl_xor_sync(kFullMask, q0, o);
+                q1 += __shfl_xor_sync(kFullMask, q1, o);
+            }
+            o0 = q0; o1 = q1;
+            xi += 1;
+        };
+
+        for (int b = 0; b < nbk; ++b) {
+            const int cur = b & 1;
+            const int mb = min(BP_M, k - b * BP_M);
+            const T *Rb = Rbuf + cur * BP_M * ncp;
+            const T *Bb = brows + cur * BP_M * ncp;
+            const T *tab = tabs + cur * TAB;
+            const T *cfm = tab, *cfp = tab + 64, *rcv = tab + 128, *cav = tab + 136;
+            const int *ordc = reinterpret_cast<const int *>(tab + 144);
+            T *vcur = vnew + cur * BP_M * ncp;
+            T *dcur = delta + cur * BP_M * ncp;
+            const T *dprev = delta + (cur ^ 1) * BP_M * ncp;
+            if (xstamp) xstamp[16 + 2 * b] = clock64();
+            named_sync(BP_BAR_PRODUCT, BP_THREADS);               // look-ahead product, B rows and tables of block b are ready
+            if (xstamp) xstamp[16 + 2 * b + 1] = clock64();
+            if (b + 1 < nbk) named_arrive(BP_BAR_SNAPSHOT, BP_THREADS);   // workers may recycle the buffers of block b-1
+
+            for (int j = 0; j < mb; ++j) {
+                tstamp = (P.timing && g == 0) ? P.timing + (int64_t)(b * BP_M + j) * 8 : nullptr;
+                BP_STAMP(0);
+                const int a = ordc[j];
+                const T caa = cav[j];
+                const bool upd = caa > T(1e-20);                    // [ref: :681-683]
+                const T rcaa = rcv[j];
+                const unsigned par = xi & 1u;
+                T cf[BP_M], cp[BP_M];                               // C[a, .] against this block's / the previous block's atoms
+                {
+                    const Quad<T> q0 = *reinterpret_cast<const Quad<T> *>(cfm + j * BP_M);
+                    const Quad<T> q1 = *reinterpret_cast<const Quad<T> *>(cfm + j * BP_M + 4);
+                    const Quad<T> p0 = *reinterpret_cast<const Quad<T> *>(cfp + j * BP_M);
+                    const Quad<T> p1 = *reinterpret_cast<const Quad<T> *>(cfp + j * BP_M + 4);
+                    cf[0] = q0.x; cf[1] = q0.y; cf[2] = q0.z; cf[3] = q0.w;
+                    cf[4] = q1.x; cf[5] = q1.y; cf[6] = q1.z; cf[7] = q1.w;
+                    cp[0] = p0.x; cp[1] = p0.y; cp[2] = p0.z; cp[3] = p0.w;
+                    cp[4] = p1.x; cp[5] = p1.y; cp[6] = p1.z; cp[7] = p1.w;
+                }
+                // ---- candidate row on my columns [ref: :676-685] ----
+                T nb_l = T(0), sv2_l = T(0);
+                T v[NCL], dold[NCL];
+#pragma unroll
+                for (int m = 0; m < NCL; ++m) {
+                    const int c = lane + 32 * m;
+                    // look-ahead product + repairs for the <= 8 + 7 atoms updated since its snapshot
+                    T dot = Rb[j * ncp + c], dot2 = T(0);
+#pragma unroll
+                    for (int jp = 0; jp < BP_M; ++jp) dot = fma(cp[jp], dprev[jp * ncp + c], dot);
+#pragma unroll
+                    for (int jp = 0; jp < BP_M - 1; ++jp) dot2 = fma(cf[jp], dcur[jp * ncp + c], dot2);
+                    dot += dot2;
+                    dold[m] = Ds[a * ncp + c];
+                    const T grad = (Bb[j * ncp + c] - dot) + caa * dold[m];
+                    T q = grad * rcaa;
+                    q = fma(fma(-q, caa, grad), rcaa, q);           // grad / caa, Newton-corrected
+                    q = upd ? q : dold[m];
+                    if (P.positive && q < T(0)) q = T(0);           // [ref: :684-685]
+                    v[m] = q;
+                    nb_l += enet_term(dold[m], P.l1_ratio);
+                    sv2_l = fma(q, q, sv2_l);
+                    if (enet && c < nc) P.vrow[(int64_t)par * s + c0 + c] = q;
+                }
+                T nb, sv2;
+                BP_STAMP(1);
+                exchange(nb_l, sv2_l, nb, sv2);
+                BP_STAMP(5);
+                const T radius = cnorm[a] + nb;                      // comp_norm_[k] += subset_norm  [ref: :676-678]
+                if (lane == 0) rad[a] = radius;
+                // projection of the candidate on the ball of "radius" [ref: enet.pyx:38-122].  The L2 case is a
+                // pure rescale v / nrm (Newton-corrected reciprocal multiply); radius == 0 maps to a zero scale.
+                T lthr = T(0), gamma = T(0), nrm = T(1), rnrm = T(1);
+                bool shrink = false;
+                if (!enet) {
+                    nrm = (sv2 <= radius) ? T(1) : t_sqrt(sv2 / radius);
+                    rnrm = (radius == T(0)) ? T(0) : T(1) / nrm;
+                } else if (radius == T(0)) {
+                    rnrm = T(0);
+                } else {
+                    gamma = T(2) / P.l1_ratio - T(2);
+                    const T *vr = P.vrow + (int64_t)par * s;
+                    bool ins;
+                    const T l = enet_threshold_warp<T>([&](int jj) { return __ldcg(vr + jj); }, s, radius / P.l1_ratio, gamma, &ins);
+                    shrink = !ins;
+                    lthr = l;
+                }
+#pragma unroll
+                for (int m = 0; m < NCL; ++m) {
+                    const int c = lane + 32 * m;
+                    T q = v[m];
+                    if (enet && shrink) {
+                        q = enet_shrink(q, lthr, gamma);
+                    } else {
+                        const T t = q * rnrm;
+                        q = fma(fma(-t, nrm, q), rnrm, t);          // v / nrm [ref: enet.pyx:69-70]; 0 when radius == 0
+                    }
+                    vcur[j * ncp + c] = q;
+                    dcur[j * ncp + c] = q - dold[m];
+                }
+                BP_STAMP(6);
+                BP_STAMP(7);
+            }
+            tstamp = nullptr;
+        }
+#undef BP_STAMP
+    }
+    // ---- epilogue: commit the last two staged blocks, norms of the new atoms, write-back ----
+    if (xstamp) xstamp[2] = clock64();
+    __syncthreads();
+    if (xstamp) xstamp[3] = clock64();
+    for (int bb = max(0, nbk - 2); bb < nbk; ++bb) {
+        const int mb = min(BP_M, k - bb * BP_M);
+        const T *vs = vnew + (bb & 1) * BP_M * ncp;
+        for (int e = tid; e < mb * ncp; e += BP_THREADS) {
+            const int jp = e / ncp, c = e % ncp;
+            Ds[P.order[bb * BP_M + jp] * ncp + c] = vs[e];
+        }
+    }
+    __syncthreads();
+    // comp_norm_[a] = radius_a - enet_norm(new atom) [ref: :690-692]: per-CTA partial norms -> global -> CTA 0
+    T *napart = P.part;                                        // [nblk][k]
+    for (int i = wid; i < k; i += BP_THREADS / 32) {
+        T acc = T(0);
+        for (int c = lane; c < nc; c += 32) acc += enet_term(Ds[i * ncp + c], P.l1_ratio);
+        acc = warp_sum(acc);
+        if (lane == 0) napart[(int64_t)g * k + i] = acc;
+    }
+    if (vec_ok) {
+        const int nv = ncp / VE;
+#pragma unroll 4
+        for (int e = tid; e < k * nv; e += BP_THREADS) {
+            const int i = e / nv, cv = (e % nv) * VE;
+            if (cv + VE <= nc) {
+                *reinterpret_cast<uint4 *>(P.Dp + (int64_t)i * lds + c0 + cv) = *reinterpret_cast<const uint4 *>(Ds + i * ncp + cv);
+            } else {
+                for (int u = 0; u < VE; ++u)
+                    if (cv + u < nc) P.Dp[(int64_t)i * lds + c0 + cv + u] = Ds[i * ncp + cv + u];
+            }
+        }
+    } else {
+        for (int e = tid; e < k * ncp; e += BP_THREADS) {
+            const int i = e / ncp, c = e % ncp;
+            if (c < nc) P.Dp[(int64_t)i * lds + c0 + c] = Ds[e];
+        }
+    }
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    if (g == 0) {
+        for (int i = tid; i < k; i += BP_THREADS) {
+            T na = T(0);
+            for (int q = 0; q < nblk; ++q) na += __ldcg(napart + (int64_t)q * k + i);   // fixed order
+            P.comp_norm[i] = rad[i] - na;
+        }
+    }
+    if (xstamp) xstamp[4] = clock64();
+}
+
+}  // namespace modl

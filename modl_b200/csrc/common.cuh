@@ -82,6 +82,9 @@ struct modl_ctx {
     int opt_bcd_cluster = 16;     // largest thread-block cluster tried by the dictionary update (0 = never)
     int opt_cd_warps = 0;         // warps per CTA of the CD kernel (0 = auto)
     int opt_force_global_gram = 0;// debug: never keep the Gram in shared memory
+    int opt_bcd_pilot = 1;        // use the warp-specialised look-ahead dictionary kernel when the panel fits a cluster
+    int opt_bcd_timing = 0;       // debug: record clock64 stamps inside the dictionary update
+    int bcd_timing_k = 0;
     // optional per-phase device timing of the fused step (modl_ctx_profile)
     int prof_on = 0;
     int prof_n = 0;                       // marks recorded in the current step
