@@ -287,18 +287,35 @@ def run_b200(args, rank, world):
         e2e_ms = float(t.item())
     e2e_value = steps * b_global / (e2e_ms * 1e-3)
 
+    # pinned host -> device bandwidth of this box (what bounds the end-to-end number once the kernels are fast)
+    h2d_gbps = None
+    if rank == 0:
+        buf_h = Xp[:b_local]
+        buf_d = torch.empty_like(buf_h, device=dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            buf_d.copy_(buf_h, non_blocking=True)
+        ev0.record()
+        for _ in range(10):
+            buf_d.copy_(buf_h, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        h2d_gbps = 10 * buf_h.numel() * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+
     # ---- (3) per-phase device times (separate profiled pass, CUDA events on the stream) ----
     phases_ms, roof = None, None
+    # every rank runs the pass (the sharded step contains a collective); rank 0 reports
+    ctx.profile(True)
+    nprof = min(steps, 10)
+    for i in range(nprof):
+        j = warmup + i
+        est.partial_fit(Xd[j * b_local:(j + 1) * b_local], idx_of(j))
+    torch.cuda.synchronize(dev)
+    tot, nst = ctx.profile_read()
+    ctx.profile(False)
+    barrier()
     if rank == 0:
-        ctx.profile(True)
-        nprof = min(steps, 10)
-        for i in range(nprof):
-            j = warmup + i
-            est.partial_fit(Xd[j * b_local:(j + 1) * b_local], idx_of(j))
-        torch.cuda.synchronize(dev)
-        tot, nst = ctx.profile_read()
-        ctx.profile(False)
-        phases_ms = {k_: v / max(nst, 1) for k_, v in tot.items()}
+        phases_ms = {k_: v / max(nprof, 1) for k_, v in tot.items()}
         work = algorithmic_work(s_mean, sweeps_mean, b_local)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -357,7 +374,8 @@ def run_b200(args, rank, world):
                        "mean_cd_sweeps": sweeps_mean, "code_density": density, "subset_len_last": s_mean},
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms / steps,
                     "h2d_bytes_per_step": int(b_local * P * 4 + b_local * 8), "d2h_bytes_per_step": int(b_local * K * 4),
-                    "api": "DictFact.partial_fit(pinned host rows, sample_indices) + read-back of the batch code"},
+                    "api": "DictFact.partial_fit(pinned host rows, sample_indices) + read-back of the batch code",
+                    "pinned_h2d_GBps": h2d_gbps},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": roof,

@@ -1,0 +1,35 @@
+"""N-GPU parity of the sample-sharded step (NCCL all-reduce of the statistics increments): the
+replicas stay bit-identical and match the single-GPU estimator run on the concatenated batch.
+Needs >= 2 GPUs (gpurun --gpus 2); skipped otherwise."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sharded_matches_single_gpu():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 CUDA devices")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_dist_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("DIST_RESULT ")][-1]
+    out = json.loads(line[len("DIST_RESULT "):])
+    for name, r in out.items():
+        assert r["spread"] == 0.0, (name, r)                 # replicas bit-identical
+        assert r["n_iter"][0] == r["n_iter"][1]
+        for key in ("D", "C", "B", "code_rank0_rows"):
+            assert r[key] < 2e-5, (name, key, r)
