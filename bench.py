@@ -261,6 +261,8 @@ def run_b200(args, rank, world):
     s_mean = float(est.last_subset_.shape[0])
 
     # ---- (2) end-to-end pass: host (pinned) rows in, batch code out, copies timed ----------
+    if args.no_e2e:      # profiler runs only (ncu): skip the end-to-end and CPU legs
+        args.no_cpu = True
     est2 = new_est()
     Xp = torch.from_numpy(X).pin_memory()
     code_host = torch.empty((b_local, K), dtype=torch.float32).pin_memory()
@@ -271,7 +273,7 @@ def run_b200(args, rank, world):
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     wall0 = time.perf_counter()
-    for i in range(warmup, total):
+    for i in range(warmup, warmup + 1 if args.no_e2e else total):
         ids = idx_of(i)
         est2.partial_fit(Xp[i * b_local:(i + 1) * b_local], ids)
         code_host.copy_(est2.code_dev[ids[0]:ids[0] + b_local] if ids[-1] - ids[0] == b_local - 1
@@ -395,6 +397,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-steps", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiler runs: shortest possible e2e leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -18,7 +18,7 @@ def sources():
 
 def headers():
     inc = os.path.join(os.path.dirname(HERE), "include", "modl_b200.h")
-    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [inc]
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh") or f.endswith(".h")] + [inc]
 
 
 def _stale(target, deps):

@@ -8,12 +8,8 @@
 #include <vector>
 
 #include "basic_kernels.cuh"
-#include "bcd_kernels.cuh"
-#include "bcd_pilot.cuh"
-#include "cd_kernels.cuh"
 #include "common.cuh"
-#include "gemm_simt.cuh"
-#include "ridge_kernels.cuh"
+#include "launch.h"
 
 namespace modl {
 
@@ -172,16 +168,6 @@ int modl_ctx_check_info(modl_ctx *ctx, void *stream)
 
 namespace modl {
 
-// leading dimension of the gathered subset panels: padded so that rows start 16-byte aligned
-static inline int64_t panel_ld(int64_t s) { return s > 0 ? round_up(s, 4) : 4; }
-
-static inline int grid_for(modl_ctx *ctx, int64_t work, int per_sm = 8)
-{
-    int64_t cap = (int64_t)ctx->sm_count * per_sm;
-    int64_t g = work < cap ? work : cap;
-    return (int)(g < 1 ? 1 : g);
-}
-
 // ---------------------------------------------------------------------------------------
 // gathers
 // ---------------------------------------------------------------------------------------
@@ -207,111 +193,6 @@ static int scatter_cols(modl_ctx *ctx, const T *src, int64_t lds, int64_t rows, 
     return MODL_OK;
 }
 
-// ---------------------------------------------------------------------------------------
-// coordinate descent launch
-// ---------------------------------------------------------------------------------------
-template <typename T, int TILES, bool PACKED>
-static int cd_launch_inst(modl_ctx *ctx, const T *G, int64_t g_stride, const T *Dx, const T *xnorm2, T *code,
-                          const int64_t *indices, T *code_batch, int64_t b, int64_t k, T alpha, T beta, T tol,
-                          int max_iter, int positive, int32_t *sweeps, cudaStream_t st)
-{
-    auto kern = cd_regression_kernel<T, TILES, PACKED>;
-    size_t smem = PACKED ? cd_packed_elems(TILES) * sizeof(T) : 0;
-    int warps, grid;
-    if (PACKED) {
-        warps = ctx->opt_cd_warps > 0 ? ctx->opt_cd_warps : (int)ceil_div(b, ctx->sm_count);
-        if (warps < 4) warps = 4;
-        if (warps > 16) warps = 16;
-        grid = (int)ceil_div(b, warps);
-        if (grid > ctx->sm_count) grid = ctx->sm_count;
-        MODL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // tile-packed lower triangle of G in global memory, pulled by TMA bulk copies
-        T *packed = nullptr;
-        MODL_TRY(ws<T>(ctx, WS_GPACK, cd_packed_elems(TILES), &packed));
-        cd_pack_gram_kernel<T><<<cd_tri(TILES), 256, 0, st>>>(G, (int)k, TILES, packed);
-        MODL_LAUNCH_CHECK(ctx);
-        G = packed;
-    } else {
-        warps = ctx->opt_cd_warps > 0 ? ctx->opt_cd_warps : 4;
-        if (warps > 8) warps = 8;
-        grid = (int)ceil_div(b, warps);
-        if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
-    }
-    kern<<<grid, warps * 32, smem, st>>>(G, g_stride, Dx, xnorm2, code, indices, code_batch, (int)b, (int)k,
-                                         alpha, beta, tol, max_iter, positive, sweeps);
-    MODL_LAUNCH_CHECK(ctx);
-    return MODL_OK;
-}
-
-template <typename T>
-static int cd_launch(modl_ctx *ctx, const T *G, int64_t g_stride, const T *Dx, const T *xnorm2, T *code,
-                     const int64_t *indices, T *code_batch, int64_t b, int64_t k, T alpha, T beta, T tol,
-                     int max_iter, int positive, int32_t *sweeps, cudaStream_t st)
-{
-    if (b <= 0) return MODL_OK;
-    MODL_REQUIRE(k >= 1 && k <= 1024, "n_components must be in [1, 1024]");
-    const int tiles = (int)ceil_div(k, 32);
-    const bool packed = g_stride == 0 && !ctx->opt_force_global_gram && tiles <= 10 &&
-                        cd_packed_elems(tiles) * sizeof(T) + 1024 <= (size_t)ctx->max_smem_optin;
-#define MODL_CD_CASE(TL, PK)                                                                              \
-    return cd_launch_inst<T, TL, PK>(ctx, G, g_stride, Dx, xnorm2, code, indices, code_batch, b, k, alpha, \
-                                     beta, tol, max_iter, positive, sweeps, st)
-    if (packed) {
-        switch (tiles) {
-            case 1: MODL_CD_CASE(1, true);
-            case 2: MODL_CD_CASE(2, true);
-            case 3: MODL_CD_CASE(3, true);
-            case 4: MODL_CD_CASE(4, true);
-            case 5: MODL_CD_CASE(5, true);
-            case 6: MODL_CD_CASE(6, true);
-            case 7: MODL_CD_CASE(7, true);
-            case 8: MODL_CD_CASE(8, true);
-            case 9: MODL_CD_CASE(9, true);
-            default: MODL_CD_CASE(10, true);
-        }
-    }
-    if (tiles <= 1) MODL_CD_CASE(1, false);
-    if (tiles <= 2) MODL_CD_CASE(2, false);
-    if (tiles <= 4) MODL_CD_CASE(4, false);
-    if (tiles <= 8) MODL_CD_CASE(8, false);
-    if (tiles <= 16) MODL_CD_CASE(16, false);
-    MODL_CD_CASE(32, false);
-#undef MODL_CD_CASE
-}
-
-// ---------------------------------------------------------------------------------------
-// ridge launch
-// ---------------------------------------------------------------------------------------
-template <typename T>
-static int ridge_solve(modl_ctx *ctx, const T *G, int64_t g_stride, T *Dx, T *code, const int64_t *indices,
-                       T *code_batch, int64_t b, int64_t k, T alpha, cudaStream_t st)
-{
-    if (b <= 0) return MODL_OK;
-    MODL_REQUIRE(k >= 1 && k <= 1024, "n_components must be in [1, 1024]");
-    const int64_t nfac = g_stride == 0 ? 1 : b;
-    T *F = nullptr;
-    MODL_TRY(ws<T>(ctx, WS_CHOL, (size_t)(nfac * k * k), &F));
-    int *info = static_cast<int *>(ctx->slot_ptr[WS_INFO]);
-    chol_factor_kernel<T><<<(unsigned)nfac, 1024, 0, st>>>(G, g_stride, alpha, F, (int)k, info);
-    MODL_LAUNCH_CHECK(ctx);
-    const int tiles = (int)ceil_div(k, 32);
-    const int warps = 4;
-    int grid = (int)ceil_div(b, warps);
-    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-    const int64_t fs = g_stride == 0 ? 0 : k * k;
-#define MODL_RS_CASE(TL) \
-    chol_solve_kernel<T, TL><<<grid, warps * 32, 0, st>>>(F, fs, Dx, code, indices, code_batch, (int)b, (int)k)
-    if (tiles <= 1) MODL_RS_CASE(1);
-    else if (tiles <= 2) MODL_RS_CASE(2);
-    else if (tiles <= 4) MODL_RS_CASE(4);
-    else if (tiles <= 8) MODL_RS_CASE(8);
-    else if (tiles <= 16) MODL_RS_CASE(16);
-    else MODL_RS_CASE(32);
-#undef MODL_RS_CASE
-    MODL_LAUNCH_CHECK(ctx);
-    return MODL_OK;
-}
-
 // regression front: CD or ridge.  xnorm2 is required for CD.
 template <typename T>
 static int regression(modl_ctx *ctx, const T *G, int64_t g_stride, T *Dx, const T *xnorm2, T *code,
@@ -324,146 +205,6 @@ static int regression(modl_ctx *ctx, const T *G, int64_t g_stride, T *Dx, const 
     }
     return cd_launch<T>(ctx, G, g_stride, Dx, xnorm2, code, indices, code_batch, b, k, alpha * l1_ratio,
                         alpha * (T(1) - l1_ratio), tol, max_iter, positive, sweeps, st);
-}
-
-// ---------------------------------------------------------------------------------------
-// dictionary update
-// ---------------------------------------------------------------------------------------
-template <typename T, bool ENET>
-static const void *pilot_kernel_for_e(int ncl)
-{
-    switch (ncl) {
-        case 1: return (const void *)bcd_pilot_kernel<T, 1, ENET>;
-        case 2: return (const void *)bcd_pilot_kernel<T, 2, ENET>;
-        case 3: return (const void *)bcd_pilot_kernel<T, 3, ENET>;
-        case 4: return (const void *)bcd_pilot_kernel<T, 4, ENET>;
-        case 5: return (const void *)bcd_pilot_kernel<T, 5, ENET>;
-        default: return (const void *)bcd_pilot_kernel<T, 6, ENET>;
-    }
-}
-template <typename T>
-static const void *pilot_kernel_for(int ncl, bool enet)
-{
-    return enet ? pilot_kernel_for_e<T, true>(ncl) : pilot_kernel_for_e<T, false>(ncl);
-}
-
-template <typename T>
-static int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *comp_norm,
-                      const int32_t *d_order, int64_t k, int64_t s, T l1_ratio, int positive, cudaStream_t st)
-{
-    if (s <= 0 || k <= 0) return MODL_OK;
-    auto kern = bcd_update_kernel<T>;
-    const size_t budget = (size_t)ctx->max_smem_optin - 1024;
-    auto base_smem = [&](int64_t ncp) {
-        return (size_t)(4 * round_up(k, 32) + bcd_red_elems(ncp) + 4 * ncp + 2 * BCD_MAX_CLUSTER * BCD_NPART + 64) * sizeof(T) +
-               40 * sizeof(double);
-    };
-    BcdParams<T> P;
-    P.Dp = Dp; P.Bp = Bp; P.C = C; P.comp_norm = comp_norm; P.order = d_order;
-    P.k = (int)k; P.s = (int)s; P.lds = (int)lds; P.l1_ratio = l1_ratio; P.positive = positive;
-
-    int nblk = 0, use_cluster = 0, d_in_smem = 0, use_pilot = 0;
-    int64_t cols = 0;
-    size_t smem = 0;
-    // 1) a single thread-block cluster with the panel resident in shared memory
-    if (ctx->cluster_ok && ctx->opt_bcd_cluster >= 2) {
-        for (int cs = 16; cs >= 2 && !nblk; cs >>= 1) {
-            if (cs > ctx->opt_bcd_cluster) continue;
-            const int64_t c = round_up(ceil_div(s, cs), 4), ncp = round_up(c, 32);
-            for (int pilot = ctx->opt_bcd_pilot ? 1 : 0; pilot >= 0 && !nblk; --pilot) {
-                size_t need;
-                if (pilot) {
-                    if (ncp > 192) continue;
-                    need = bcd_pilot_smem_bytes<T>(k, ncp);
-                } else {
-                    need = base_smem(ncp) + (size_t)k * ncp * sizeof(T);
-                    if (ncp > 2 * BCD_THREADS) continue;
-                }
-                if (need > budget) continue;
-                const void *fn = pilot ? pilot_kernel_for<T>((int)(ncp / 32), l1_ratio != T(0)) : (const void *)kern;
-                if (cs > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-                    cudaGetLastError();
-                    continue;
-                }
-                if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess) {
-                    cudaGetLastError();
-                    continue;
-                }
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(cs); cfg.blockDim = dim3(pilot ? BP_THREADS : BCD_THREADS);
-                cfg.dynamicSmemBytes = need; cfg.stream = st;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                cfg.attrs = at; cfg.numAttrs = 1;
-                int nclusters = 0;
-                if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters < 1) {
-                    cudaGetLastError();
-                    continue;
-                }
-                nblk = cs; use_cluster = 1; d_in_smem = 1; cols = c; smem = need; use_pilot = pilot;
-            }
-        }
-    }
-    // 2) cooperative launch over the SMs with a global barrier
-    if (!nblk) {
-        int64_t want = ceil_div(s, 32);
-        if (want > ctx->sm_count) want = ctx->sm_count;
-        if (want < 1) want = 1;
-        cols = ceil_div(s, want);
-        const int64_t ncp = round_up(cols, 32);
-        size_t need = base_smem(ncp) + (size_t)k * ncp * sizeof(T);
-        d_in_smem = need <= budget && ncp <= 2 * BCD_THREADS;
-        if (!d_in_smem) need = base_smem(ncp);
-        MODL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-        int per_sm = 0;
-        MODL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BCD_THREADS, need));
-        MODL_REQUIRE(per_sm >= 1, "dictionary-update kernel does not fit on an SM");
-        nblk = (int)ceil_div(s, cols);
-        MODL_REQUIRE(nblk <= per_sm * ctx->sm_count, "cooperative grid too large");
-        smem = need;
-    }
-    const int64_t nchunks = ceil_div(cols, 128);
-    int64_t cw = round_up(ceil_div(cols, nchunks), 32);
-    if (cw > 128) cw = 128;
-    P.cols_per_cta = (int)cols; P.chunk = (int)cw; P.d_in_smem = d_in_smem; P.use_cluster = use_cluster;
-
-    // exchange workspace: [barrier 256 B][part 2*nblk*4][vrow 2*s]
-    const size_t n_t = (size_t)(2 * nblk * BCD_NPART) + (size_t)nblk * k + 2 * (size_t)s;
-    unsigned char *base = nullptr;
-    MODL_TRY(ws<unsigned char>(ctx, WS_BCD_SYNC, 256 + n_t * sizeof(T), &base));
-    P.bar = reinterpret_cast<unsigned *>(base);
-    T *tb = reinterpret_cast<T *>(base + 256);
-    P.part = tb; tb += 2 * nblk * BCD_NPART + (size_t)nblk * k;
-    P.vrow = tb;
-    MODL_CUDA_TRY(cudaMemsetAsync(P.bar, 0, 256, st));
-    P.timing = nullptr;
-    if (ctx->opt_bcd_timing) {
-        long long *tbuf = nullptr;
-        MODL_TRY(ws<long long>(ctx, WS_MISC, (size_t)(8 * k + 16 + 2 * ceil_div(k, 8) + 8), &tbuf));
-        P.timing = tbuf;
-        ctx->bcd_timing_k = (int)k;
-    }
-
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(use_pilot ? BP_THREADS : BCD_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    if (use_cluster) {
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = nblk; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    } else {
-        at[0].id = cudaLaunchAttributeCooperative;
-        at[0].val.cooperative = 1;
-    }
-    cfg.attrs = at; cfg.numAttrs = 1;
-    if (use_pilot) {
-        void *args[] = {&P};
-        MODL_CUDA_TRY(cudaLaunchKernelExC(&cfg, pilot_kernel_for<T>((int)(round_up(cols, 32) / 32), l1_ratio != T(0)), args));
-    } else {
-        MODL_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P));
-    }
-    MODL_LAUNCH_CHECK(ctx);
-    return MODL_OK;
 }
 
 // upload the atom order as int32

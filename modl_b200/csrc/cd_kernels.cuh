@@ -204,13 +204,27 @@ __device__ __forceinline__ int cd_solve_warp(unsigned sbase, const T *__restrict
 #pragma unroll
         for (int J = 0; J < TILES; ++J) {
             const int lmax = min(CD_TILE, k - J * CD_TILE);
-            const bool my_dead = (dead >> J) & 1u;
-#pragma unroll 2
-            for (int l = 0; l < lmax; ++l) {
+            const bool my_live = !((dead >> J) & 1u) && lane < lmax;   // Q[c,c] == 0: coordinate skipped [ref: :357-358]
+            // Active-set walk over the 32 coordinates of tile J.  A coordinate whose weight is zero
+            // and whose soft-threshold candidate is zero is an exact no-op of the reference's step
+            // (neither axpy runs, :359 and :374 test w[ii] != 0), and H is untouched by no-ops, so
+            // every lane can test its own coordinate against the CURRENT H in parallel; the warp
+            // then jumps to the first coordinate that does something, executes it exactly like the
+            // sequential loop would, and re-tests the lanes after it.  Sparse codes (a few percent
+            // of non-zeros) therefore cost a few dependent steps per tile instead of 32.
+            unsigned todo = kFullMask;
+            while (true) {
+                const T tmp0 = q[J] - h[J];
+                const T mag0 = t_abs(tmp0) - alpha;
+                const bool moves = mag0 > T(0) && !(positive && tmp0 < T(0));
+                const unsigned act = __ballot_sync(kFullMask, my_live && (w[J] != T(0) || moves)) & todo;
+                if (act == 0u) break;
+                const int l = __ffs(act) - 1;
+                todo = (l == 31) ? 0u : (kFullMask << (l + 1));
                 if (PACKED) cd_row_packed<T, TILES>(sbase, J, l, lane, r);
                 else        cd_row_global<T, TILES>(Gs, k, J * CD_TILE + l, lane, r);
                 const T w_old = __shfl_sync(kFullMask, w[J], l);
-                // H -= w_old Q[c,:] -- branch-free: a zero coefficient leaves H bit-unchanged
+                // H -= w_old Q[c,:] -- a zero coefficient leaves H bit-unchanged
                 cd_axpy_tiles<TILES>(h, r, -w_old);
                 // candidate for "my" coordinate of tile J; only lane l's value is consumed
                 const T tmp = q[J] - h[J];
@@ -220,7 +234,6 @@ __device__ __forceinline__ int cd_solve_warp(unsigned sbase, const T *__restrict
                 const T den = r[J] + beta;                             // r[J] on lane l is Q[c,c]
                 T cand = ms * inv[J];
                 cand = fma(fma(-cand, den, ms), inv[J], cand);         // Newton step: ms / den
-                cand = my_dead ? w[J] : cand;                          // Q[c,c] == 0: coordinate skipped [ref: :357-358]
                 const T w_new = __shfl_sync(kFullMask, cand, l);
                 w[J] = (lane == l) ? w_new : w[J];
                 cd_axpy_tiles<TILES>(h, r, w_new);

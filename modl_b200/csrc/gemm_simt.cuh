@@ -15,10 +15,9 @@
 //   G_ -/+= D_sub D_sub^T                             KMAJOR x KMAJOR   dict_fact.py:668,713
 #pragma once
 #include "common.cuh"
+#include "launch.h"
 
 namespace modl {
-
-enum GemmLayout { A_KMAJOR = 0, A_MMAJOR = 1, B_KMAJOR = 0, B_NMAJOR = 1 };
 
 constexpr int GEMM_BM = 64, GEMM_BN = 64, GEMM_BK = 16, GEMM_THREADS = 256;
 

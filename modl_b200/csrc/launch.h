@@ -1,0 +1,42 @@
+// launch.h -- host-side launchers shared between the translation units of libmodl_b200.so.
+// Each kernel family is compiled in its own .cu (parallel nvcc, shorter rebuilds); api.cu only
+// sees these declarations.
+#pragma once
+#include "common.cuh"
+
+namespace modl {
+
+enum GemmLayout { A_KMAJOR = 0, A_MMAJOR = 1, B_KMAJOR = 0, B_NMAJOR = 1 };
+
+// leading dimension of the gathered subset panels: padded so that rows start 16-byte aligned
+static inline int64_t panel_ld(int64_t s) { return s > 0 ? round_up(s, 4) : 4; }
+
+static inline int grid_for(modl_ctx *ctx, int64_t work, int per_sm = 8)
+{
+    int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    int64_t g = work < cap ? work : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+// gemm_simt.cu
+template <typename T>
+int gemm_simt(modl_ctx *ctx, int la, int lb, int64_t M, int64_t N, int64_t K, T alpha, const T *A,
+              int64_t lda, const T *B, int64_t ldb, T beta, T *C, int64_t ldc, cudaStream_t st);
+
+// cd_launch.cu
+template <typename T>
+int cd_launch(modl_ctx *ctx, const T *G, int64_t g_stride, const T *Dx, const T *xnorm2, T *code,
+              const int64_t *indices, T *code_batch, int64_t b, int64_t k, T alpha, T beta, T tol,
+              int max_iter, int positive, int32_t *sweeps, cudaStream_t st);
+
+// ridge_launch.cu
+template <typename T>
+int ridge_solve(modl_ctx *ctx, const T *G, int64_t g_stride, T *Dx, T *code, const int64_t *indices,
+                T *code_batch, int64_t b, int64_t k, T alpha, cudaStream_t st);
+
+// bcd_launch.cu
+template <typename T>
+int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *comp_norm,
+               const int32_t *d_order, int64_t k, int64_t s, T l1_ratio, int positive, cudaStream_t st);
+
+}  // namespace modl
