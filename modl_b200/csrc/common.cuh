@@ -65,6 +65,10 @@ enum WsSlot {
     WS_CHOL,         // k x k factor (x b for per-sample Grams)
     WS_GROWS,        // gathered per-sample Gram matrices
     WS_GPACK,        // tile-packed lower triangle of the shared Gram
+    WS_TC_A,         // packed split panel [D_sub ; X_sub]
+    WS_TC_CODE,      // packed split panel code^T
+    WS_TC_X,         // packed split panel X^T
+    WS_GDX,          // [G ; Dx] of the tensor-core path, (k + b) x k
     WS_MISC,         // small scalars
     WS_INFO,         // int status flags
     WS_COUNT
@@ -83,6 +87,7 @@ struct modl_ctx {
     int opt_cd_warps = 0;         // warps per CTA of the CD kernel (0 = auto)
     int opt_force_global_gram = 0;// debug: never keep the Gram in shared memory
     int opt_bcd_pilot = 1;        // use the warp-specialised look-ahead dictionary kernel when the panel fits a cluster
+    int opt_tc_gemm = 1;          // float contractions on the tensor cores (tcgen05 3xTF32); 0 = CUDA-core FFMA GEMM
     int opt_bcd_timing = 0;       // debug: record clock64 stamps inside the dictionary update
     int bcd_timing_k = 0;
     // optional per-phase device timing of the fused step (modl_ctx_profile)

@@ -1,0 +1,68 @@
+// tc_gemm.cu -- launchers of the tcgen05 3xTF32 GEMM and its pack kernels (tc_gemm.cuh).
+#include "gemm_simt.cuh"
+#include "launch.h"
+#include "tc_gemm.cuh"
+
+namespace modl {
+
+size_t tc_packed_elems(int64_t rows, int64_t kd) { return tc_packed_floats(rows, kd); }
+int64_t tc_rows_padded(int64_t rows) { return tc_row_blocks(rows) * TC_ROWS; }
+
+int tc_pack_rows(modl_ctx *ctx, const float *src, int64_t ld, int64_t rows, int64_t p, const int64_t *subset,
+                 int64_t kd, float *packed, int64_t row0, int64_t rows_pad_end, float *plain, int64_t ldp,
+                 float *norm2, cudaStream_t st)
+{
+    const int64_t n = rows_pad_end - row0;
+    if (n <= 0 || kd <= 0) return MODL_OK;
+    tc_pack_rows_kernel<<<grid_for(ctx, n, 16), 256, 0, st>>>(src, ld, (int)rows, (int)p, subset, (int)kd, packed, row0,
+                                                               rows_pad_end, plain, ldp, norm2);
+    MODL_LAUNCH_CHECK(ctx);
+    return MODL_OK;
+}
+
+int tc_pack_cols(modl_ctx *ctx, const float *src, int64_t ld, int64_t kd, int64_t rows, float *packed, cudaStream_t st)
+{
+    if (rows <= 0 || kd <= 0) return MODL_OK;
+    const int64_t total = tc_row_blocks(rows) * TC_ROWS * tc_k_blocks(kd) * TC_CHUNKS;
+    tc_pack_cols_kernel<<<grid_for(ctx, ceil_div(total, 256), 16), 256, 0, st>>>(src, ld, (int)kd, (int)rows, packed);
+    MODL_LAUNCH_CHECK(ctx);
+    return MODL_OK;
+}
+
+int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M, int64_t N, int64_t Kd, float alpha,
+            float beta, float *C, int64_t ldc, cudaStream_t st)
+{
+    if (M <= 0 || N <= 0) return MODL_OK;
+    MODL_REQUIRE(Kd >= 1, "tc_gemm needs a non-empty contraction");
+    static bool configured = false;
+    if (!configured) {
+        MODL_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+        configured = true;
+    }
+    TcGemmParams P;
+    P.A = Apacked; P.B = Bpacked; P.C = C; P.ldc = ldc; P.M = (int)M; P.N = (int)N;
+    P.nkb = (int)tc_k_blocks(Kd);
+    P.alpha = alpha; P.beta = beta;
+    const int64_t tiles = tc_row_blocks(M) * tc_row_blocks(N);
+    // split the contraction until the grid covers the SMs (one CTA per SM: 193 KB of shared memory each)
+    int64_t splits = ceil_div((int64_t)ctx->sm_count, tiles);
+    if (splits > P.nkb) splits = P.nkb;
+    if (splits > 32) splits = 32;
+    if (splits < 1) splits = 1;
+    P.kb_per_split = (int)ceil_div(P.nkb, splits);
+    splits = ceil_div(P.nkb, P.kb_per_split);
+    P.part = nullptr;
+    if (splits > 1) MODL_TRY(ws<float>(ctx, WS_GEMM_PART, (size_t)(splits * M * N), &P.part));
+    dim3 grid((unsigned)tc_row_blocks(N), (unsigned)tc_row_blocks(M), (unsigned)splits);
+    tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(P);
+    MODL_LAUNCH_CHECK(ctx);
+    if (splits > 1) {
+        const int64_t total = M * N;
+        int blocks = (int)(ceil_div(total, 256) < 4 * ctx->sm_count ? ceil_div(total, 256) : 4 * ctx->sm_count);
+        gemm_splitk_reduce_kernel<float><<<blocks, 256, 0, st>>>((int)M, (int)N, (int)splits, alpha, P.part, beta, C, ldc);
+        MODL_LAUNCH_CHECK(ctx);
+    }
+    return MODL_OK;
+}
+
+}  // namespace modl

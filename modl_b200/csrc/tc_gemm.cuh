@@ -1,0 +1,357 @@
+// tc_gemm.cuh -- FP32-accurate dense contractions of the step on the 5th-generation tensor
+// cores: tcgen05.mma (kind::tf32) with the error-compensated 3xTF32 split, operands staged by
+// TMA bulk copies, accumulators in tensor memory.
+//
+// Which products  [ref: modl/decomposition/dict_fact.py]
+//   [G ; Dx] = r [D_sub ; X_sub] . D_sub^T        :595, :604   contraction over the feature subset
+//   C_ = (1-w) C_ + w/b code^T code               :573         contraction over the batch
+//   B_ = (1-w) B_ + w/b code^T X                  :564         contraction over the batch
+//
+// Why a split.  Single-pass TF32 (10-bit mantissa) perturbs G and Dx at 1e-3, which flips the
+// coordinate-descent stop decisions and breaks the 1e-4 parity bound.  Every fp32
+// operand x is therefore stored as  hi = x with the 13 low mantissa bits cleared  (an exact TF32
+// value) and  lo = tf32(x - hi)  (x - hi is exact in fp32), and each product is accumulated as
+//        lo_a . hi_b  +  hi_a . lo_b  +  hi_a . hi_b          (fp32 accumulation in TMEM)
+// whose dropped terms are O(2^-22) relative: fp32-level accuracy at a third of the TF32 rate,
+// which is still ~5x the FP32 FMA rate of the CUDA cores.
+//
+// Operand format ("packed split panels").  A pack kernel (one pass over the source, fused with
+// the column gather of the feature subset or with the transposition the contraction needs)
+// writes each operand in exactly the shared-memory image tcgen05 wants, so the GEMM CTA needs no
+// register staging at all: one elected thread moves whole operand blocks with cp.async.bulk
+// (TMA), one elected thread issues the MMAs, four warps drain TMEM.
+//   operand = R rows (M or N side) x Kd contraction, zero padded to 128-row x 32-k blocks;
+//   block (rb, kb) = 32 KB contiguous:  [hi | lo],  each  [8 chunks][128 rows][4 floats]
+//   i.e. the canonical K-major, no-swizzle UMMA layout: 8-row x 16-byte core matrices,
+//   SBO (next 8 rows) = 128 B, LBO (next 16-byte K chunk) = 2048 B.
+#pragma once
+#include "common.cuh"
+
+namespace modl {
+
+constexpr int TC_ROWS = 128;                 // rows of an operand block (= UMMA M, = UMMA N)
+constexpr int TC_BK = 32;                    // contraction elements per block
+constexpr int TC_CHUNKS = TC_BK / 4;         // 16-byte K chunks per block
+constexpr int TC_HALF_FLOATS = TC_ROWS * TC_BK;            // floats of the hi (or lo) half
+constexpr int TC_BLOCK_FLOATS = 2 * TC_HALF_FLOATS;        // hi + lo
+constexpr unsigned TC_BLOCK_BYTES = TC_BLOCK_FLOATS * 4;   // 32 KB
+constexpr unsigned TC_HALF_BYTES = TC_HALF_FLOATS * 4;     // 16 KB
+constexpr int TC_STAGES = 3;                 // 3 x (A block + B block) = 192 KB of shared memory
+constexpr int TC_THREADS = 192;              // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr unsigned TC_TMEM_COLS = 128;       // one 128 x 128 fp32 accumulator
+constexpr size_t TC_SMEM_BYTES = (size_t)TC_STAGES * 2 * TC_BLOCK_BYTES + 1024;
+
+__host__ __device__ inline int64_t tc_row_blocks(int64_t rows) { return ceil_div(rows, TC_ROWS); }
+__host__ __device__ inline int64_t tc_k_blocks(int64_t kd) { return ceil_div(kd, TC_BK); }
+// floats of a packed operand with `rows` rows and contraction length `kd`
+__host__ __device__ inline size_t tc_packed_floats(int64_t rows, int64_t kd)
+{
+    return (size_t)tc_row_blocks(rows) * (size_t)tc_k_blocks(kd) * TC_BLOCK_FLOATS;
+}
+
+// ---------------------------------------------------------------------------------------
+// split + pack
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_split(float x, float &hi, float &lo)
+{
+    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    lo = __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u);
+}
+
+// position (in floats) of the 16-byte unit (row r, chunk c) inside the packed operand whose
+// contraction spans `nkb` blocks; the lo copy sits TC_HALF_FLOATS further.
+__device__ __forceinline__ size_t tc_unit_offset(int64_t r, int64_t c, int64_t nkb)
+{
+    const int64_t rb = r / TC_ROWS, rr = r % TC_ROWS, kb = c / TC_CHUNKS, cc = c % TC_CHUNKS;
+    return ((size_t)(rb * nkb + kb)) * TC_BLOCK_FLOATS + (size_t)(cc * TC_ROWS + rr) * 4;
+}
+
+__device__ __forceinline__ void tc_store_unit(float *__restrict__ packed, size_t off, const float (&v)[4])
+{
+    float4 h, l;
+    tc_split(v[0], h.x, l.x); tc_split(v[1], h.y, l.y); tc_split(v[2], h.z, l.z); tc_split(v[3], h.w, l.w);
+    *reinterpret_cast<float4 *>(packed + off) = h;
+    *reinterpret_cast<float4 *>(packed + off + TC_HALF_FLOATS) = l;
+}
+
+// Rows of a row-major source become operand rows; the contraction runs along the source row,
+// optionally through a column gather:  op[row0 + r, j] = src[r, subset ? subset[j] : j].
+// grid.x: row r in [0, rows_pad) where rows_pad also covers the zero padding up to the block
+// boundary (only when pad_rows), grid-stride; one thread per 16-byte unit.
+// Optionally also emits the plain gathered panel (plain[r, j], ld = ldp) and the squared norm of
+// the FULL source row, which the CD stop test and the dictionary update need anyway.
+__global__ void __launch_bounds__(256)
+tc_pack_rows_kernel(const float *__restrict__ src, int64_t ld, int rows, int p, const int64_t *__restrict__ subset,
+                    int kd, float *__restrict__ packed, int64_t row0, int64_t rows_pad_end,
+                    float *__restrict__ plain, int64_t ldp, float *__restrict__ norm2)
+{
+    __shared__ float scratch[33];
+    const int64_t nkb = tc_k_blocks(kd);
+    const int nunits = (int)(nkb * TC_CHUNKS);
+    for (int64_t r = blockIdx.x; row0 + r < rows_pad_end; r += gridDim.x) {
+        const bool real = r < rows;
+        const float *row = src + r * ld;
+        if (real && norm2 != nullptr) {
+            float acc = 0.f;
+            for (int j = threadIdx.x; j < p; j += blockDim.x) {
+                const float v = row[j];
+                acc = fmaf(v, v, acc);
+            }
+            acc = block_sum(acc, scratch);
+            if (threadIdx.x == 0) norm2[r] = acc;
+        }
+        for (int c = threadIdx.x; c < nunits; c += blockDim.x) {
+            float v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = 4 * c + i;
+                v[i] = (real && j < kd) ? row[subset ? subset[j] : (int64_t)j] : 0.f;
+            }
+            tc_store_unit(packed, tc_unit_offset(row0 + r, c, nkb), v);
+            if (real && plain != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (4 * c + i < kd) plain[r * ldp + 4 * c + i] = v[i];
+            }
+        }
+    }
+}
+
+// Columns of a row-major source become operand rows (the contraction runs DOWN the source):
+//     op[r, j] = src[j, r],   src is kd x rows (ld).
+// One thread per 16-byte unit, consecutive threads take consecutive r: coalesced 128 B reads of
+// four source rows and coalesced 16-byte-per-thread writes.
+__global__ void __launch_bounds__(256)
+tc_pack_cols_kernel(const float *__restrict__ src, int64_t ld, int kd, int rows, float *__restrict__ packed)
+{
+    const int64_t nkb = tc_k_blocks(kd);
+    const int64_t rows_pad = tc_row_blocks(rows) * TC_ROWS;
+    const int64_t nunits = nkb * TC_CHUNKS;
+    const int64_t total = rows_pad * nunits;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = e / rows_pad, r = e % rows_pad;
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t j = 4 * c + i;
+            v[i] = (r < rows && j < kd) ? src[j * ld + r] : 0.f;
+        }
+        tc_store_unit(packed, tc_unit_offset(r, c, nkb), v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol error becomes a trap (launch failure), never a hung GPU.
+__device__ __forceinline__ void tc_mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tc_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_tmem_alloc(unsigned smem_dst, unsigned cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tc_tmem_dealloc(unsigned taddr, unsigned cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+// D[tmem] (+)= A[smem] . B[smem]^T, 128 x 128 x 8, TF32 inputs, FP32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(unsigned tmem_d, uint64_t desc_a, uint64_t desc_b, unsigned idesc, unsigned accumulate)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// all MMAs issued so far by this thread arrive on `bar` when they complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void tc_commit(unsigned bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_tmem_ld32(unsigned taddr, float (&v)[32])
+{
+    unsigned r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor of a [8 chunks][128 rows][16 B] half block
+// starting at shared address `saddr` (+ the K offset of the MMA inside the block).
+__device__ __forceinline__ uint64_t tc_smem_desc(unsigned saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);                      // start address,            bits [0,14)
+    d |= (uint64_t)((TC_ROWS * 16u) >> 4) << 16;                   // leading byte offset (K),  bits [16,30)
+    d |= (uint64_t)(128u >> 4) << 32;                              // stride byte offset (M/N), bits [32,46)
+    d |= (uint64_t)1 << 46;                                        // descriptor version (sm_100)
+    return d;                                                      // layout type 0 = no swizzle
+}
+
+// kind::tf32 instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+constexpr unsigned TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TC_ROWS >> 3) << 17) | ((unsigned)(TC_ROWS >> 4) << 24);
+
+// ---------------------------------------------------------------------------------------
+// C[M x N] = alpha * A . B^T + beta * C      (A: M x Kd, B: N x Kd, packed split panels)
+// grid = (n blocks, m blocks, split-K slices).  With part != NULL every slice writes its raw
+// partial tile to part[z][M][N] and a fixed-order reduction applies alpha/beta afterwards.
+// ---------------------------------------------------------------------------------------
+struct TcGemmParams {
+    const float *A;      // packed, tc_row_blocks(M) x nkb blocks
+    const float *B;      // packed, tc_row_blocks(N) x nkb blocks
+    float *C;
+    int64_t ldc;
+    float *part;         // split-K partials or NULL
+    int M, N;
+    int nkb;             // k blocks of the whole contraction
+    int kb_per_split;    // k blocks per grid.z slice
+    float alpha, beta;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(TcGemmParams P)
+{
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 1];
+    __shared__ unsigned tmem_base_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(tc_smem) + 1023u) & ~1023u;
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * (unsigned)s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (unsigned)(TC_STAGES + s); };
+    const unsigned done_bar = bar0 + 8u * (unsigned)(2 * TC_STAGES);
+
+    const int nb = blockIdx.x, mb = blockIdx.y;
+    const int kb0 = blockIdx.z * P.kb_per_split;
+    const int kb1 = min(P.nkb, kb0 + P.kb_per_split);
+    const int nk = kb1 - kb0;                 // >= 1 by construction of the grid
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(full_bar(s), 1); tc_mbar_init(empty_bar(s), 1); }
+        tc_mbar_init(done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) tc_tmem_alloc((unsigned)__cvta_generic_to_shared(&tmem_base_s), TC_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const float *Ab = P.A + ((size_t)mb * P.nkb + kb0) * TC_BLOCK_FLOATS;
+            const float *Bb = P.B + ((size_t)nb * P.nkb + kb0) * TC_BLOCK_FLOATS;
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % TC_STAGES;
+                const unsigned ph = (unsigned)(i / TC_STAGES) & 1u;
+                tc_mbar_wait(empty_bar(s), ph ^ 1u);                 // slot free (first pass: immediately)
+                tc_mbar_expect_tx(full_bar(s), 2 * TC_BLOCK_BYTES);
+                const unsigned sa = smem0 + (unsigned)s * 2u * TC_BLOCK_BYTES;
+                tc_bulk_g2s(sa, Ab + (size_t)i * TC_BLOCK_FLOATS, TC_BLOCK_BYTES, full_bar(s));
+                tc_bulk_g2s(sa + TC_BLOCK_BYTES, Bb + (size_t)i * TC_BLOCK_FLOATS, TC_BLOCK_BYTES, full_bar(s));
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % TC_STAGES;
+                const unsigned ph = (unsigned)(i / TC_STAGES) & 1u;
+                tc_mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const unsigned sa = smem0 + (unsigned)s * 2u * TC_BLOCK_BYTES;   // A: hi | lo
+                const unsigned sb = sa + TC_BLOCK_BYTES;                          // B: hi | lo
+#pragma unroll
+                for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+                    const unsigned koff = (unsigned)k8 * 2u * (TC_ROWS * 16u);    // two 16-byte chunks per MMA
+                    const uint64_t a_hi = tc_smem_desc(sa + koff), a_lo = tc_smem_desc(sa + TC_HALF_BYTES + koff);
+                    const uint64_t b_hi = tc_smem_desc(sb + koff), b_lo = tc_smem_desc(sb + TC_HALF_BYTES + koff);
+                    tc_mma_tf32(tmem, a_lo, b_hi, TC_IDESC, (i | k8) != 0);       // small terms first
+                    tc_mma_tf32(tmem, a_hi, b_lo, TC_IDESC, 1u);
+                    tc_mma_tf32(tmem, a_hi, b_hi, TC_IDESC, 1u);
+                }
+                tc_commit(empty_bar(s));                                          // smem slot reusable when these finish
+            }
+            tc_commit(done_bar);                                                  // accumulator complete
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        tc_mbar_wait(done_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;                        // TMEM lane quadrant this warp may read
+        const int m = mb * TC_ROWS + q * 32 + lane;    // accumulator row = TMEM lane
+        const unsigned trow = tmem + ((unsigned)(q * 32) << 16);
+        for (int c0 = 0; c0 < TC_ROWS; c0 += 32) {
+            float v[32];
+            __syncwarp();                              // tcgen05.ld is warp-collective (.sync.aligned)
+            tc_tmem_ld32(trow + (unsigned)c0, v);
+            const int n0 = nb * TC_ROWS + c0;
+            if (m >= P.M || n0 >= P.N) {
+                // nothing of this strip belongs to the matrix
+            } else if (P.part != nullptr) {
+                float *dst = P.part + ((size_t)blockIdx.z * P.M + m) * P.N + n0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n0 + j < P.N) dst[j] = v[j];
+            } else {
+                float *dst = P.C + (int64_t)m * P.ldc + n0;
+                const bool vec = (n0 + 32 <= P.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+                if (vec) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(P.alpha * v[j], P.alpha * v[j + 1], P.alpha * v[j + 2], P.alpha * v[j + 3]);
+                        if (P.beta != 0.f) {
+                            const float4 c = *reinterpret_cast<const float4 *>(dst + j);
+                            o.x = fmaf(P.beta, c.x, o.x); o.y = fmaf(P.beta, c.y, o.y);
+                            o.z = fmaf(P.beta, c.z, o.z); o.w = fmaf(P.beta, c.w, o.w);
+                        }
+                        *reinterpret_cast<float4 *>(dst + j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (n0 + j >= P.N) continue;
+                        float o = P.alpha * v[j];
+                        if (P.beta != 0.f) o = fmaf(P.beta, dst[j], o);
+                        dst[j] = o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc_tmem_dealloc(tmem, TC_TMEM_COLS);
+}
+
+}  // namespace modl
