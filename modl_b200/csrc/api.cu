@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 #include "basic_kernels.cuh"
@@ -65,6 +66,8 @@ int modl_ctx_create(int device, modl_ctx **out)
     if (const char *e = getenv("MODL_BCD_CLUSTER")) c->opt_bcd_cluster = atoi(e);
     if (const char *e = getenv("MODL_CD_WARPS")) c->opt_cd_warps = atoi(e);
     if (const char *e = getenv("MODL_FORCE_GLOBAL_GRAM")) c->opt_force_global_gram = atoi(e);
+    if (const char *e = getenv("MODL_TC_GEMM")) c->opt_tc_gemm = atoi(e);
+    if (const char *e = getenv("MODL_TC_DESC_MODE")) c->opt_tc_desc_mode = atoi(e);
     int *info = nullptr;
     if (ws<int>(c, WS_INFO, 4, &info) != MODL_OK) { delete c; return MODL_ECUDA; }
     MODL_CUDA_TRY(cudaMemset(info, 0, 4 * sizeof(int)));
@@ -91,6 +94,8 @@ int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "cd_warps")) ctx->opt_cd_warps = value;
     else if (!strcmp(name, "force_global_gram")) ctx->opt_force_global_gram = value;
     else if (!strcmp(name, "bcd_timing")) ctx->opt_bcd_timing = value;
+    else if (!strcmp(name, "tc_gemm")) ctx->opt_tc_gemm = value;
+    else if (!strcmp(name, "tc_desc_mode")) ctx->opt_tc_desc_mode = value;
     else if (!strcmp(name, "bcd_pilot")) ctx->opt_bcd_pilot = value;
     else { set_error("unknown option %s", name); return MODL_EINVAL; }
     return MODL_OK;
@@ -312,6 +317,41 @@ static int enet_scale_impl(modl_ctx *ctx, T *X, int64_t rows, int64_t n, int64_t
     return MODL_OK;
 }
 
+// [G ; Dx] = scale [D' ; X'] . D'^T on the tensor cores (float only), D' = D[:, subset] (or D when
+// subset == NULL), contraction length kd.  The pack kernels fuse the column gather, the hi/lo split
+// and (for X) the full-row squared norm; plain_D (optional) receives the plain k x kd panel the
+// dictionary update works on.
+static int gram_dx_tc(modl_ctx *ctx, const float *D, int64_t ldd, const float *X, int64_t ldx, const int64_t *subset,
+                      int64_t kd, int64_t k, int64_t b, int64_t p, float scale, float *G, float *Dx, float *xnorm2,
+                      float *plain_D, int64_t lds, cudaStream_t st)
+{
+    const bool want_dx = Dx != nullptr && b > 0;
+    const int64_t rows = k + (want_dx ? b : 0);
+    float *packed = nullptr;
+    MODL_TRY(ws<float>(ctx, WS_TC_A, tc_packed_elems(rows, kd), &packed));
+    prof_mark(ctx, st, MODL_PROF_GATHER);
+    MODL_TRY(tc_pack_rows(ctx, D, ldd, k, p, subset, kd, packed, 0, want_dx ? k : tc_rows_padded(k), plain_D, lds, nullptr, st));
+    if (want_dx)
+        MODL_TRY(tc_pack_rows(ctx, X, ldx, b, p, subset, kd, packed, k, tc_rows_padded(k + b), nullptr, 0, xnorm2, st));
+    else if (xnorm2 && b > 0)
+        MODL_TRY(gather_cols<float>(ctx, X, ldx, b, p, nullptr, 0, (float *)nullptr, 0, xnorm2, st));
+    prof_mark(ctx, st, MODL_PROF_GRAM);
+    if (G != nullptr && (!want_dx || Dx == G + k * k)) {
+        MODL_TRY(tc_gemm(ctx, packed, packed, rows, k, kd, scale, 0.f, G, k, st));      // G and Dx are one (k + b) x k matrix
+    } else {
+        float *gdx = nullptr;
+        MODL_TRY(ws<float>(ctx, WS_GDX, (size_t)(rows * k), &gdx));
+        MODL_TRY(tc_gemm(ctx, packed, packed, rows, k, kd, scale, 0.f, gdx, k, st));
+        if (G) MODL_CUDA_TRY(cudaMemcpyAsync(G, gdx, sizeof(float) * (size_t)(k * k), cudaMemcpyDeviceToDevice, st));
+        if (want_dx)
+            MODL_CUDA_TRY(cudaMemcpyAsync(Dx, gdx + k * k, sizeof(float) * (size_t)(b * k), cudaMemcpyDeviceToDevice, st));
+    }
+    return MODL_OK;
+}
+
+template <typename T>
+static inline bool use_tc(const modl_ctx *ctx) { return std::is_same<T, float>::value && ctx->opt_tc_gemm != 0; }
+
 // G / Dx / xnorm2 products; panel (optional out): where D_sub (k x s) was left
 template <typename T>
 static int gram_dx_impl(modl_ctx *ctx, const T *D, int64_t ldd, const T *X, int64_t ldx, const int64_t *subset, int64_t s,
@@ -320,6 +360,12 @@ static int gram_dx_impl(modl_ctx *ctx, const T *D, int64_t ldd, const T *X, int6
     MODL_REQUIRE(ctx && D && k >= 1 && p >= 1 && b >= 0, "gram_dx arguments");
     MODL_REQUIRE(X != nullptr || (Dx == nullptr && xnorm2 == nullptr), "X required for Dx / xnorm2");
     if (subset == nullptr) {
+        if constexpr (std::is_same<T, float>::value) {
+            if (use_tc<T>(ctx) && (G || (Dx && b > 0))) {
+                if (panel_out) *panel_out = nullptr;
+                return gram_dx_tc(ctx, D, ldd, X, ldx, nullptr, p, k, b, p, scale, G, Dx, xnorm2, nullptr, 0, st);
+            }
+        }
         prof_mark(ctx, st, MODL_PROF_GATHER);
         if (xnorm2 && b > 0) MODL_TRY(gather_cols<T>(ctx, X, ldx, b, p, nullptr, 0, (T *)nullptr, 0, xnorm2, st));
         prof_mark(ctx, st, MODL_PROF_GRAM);
@@ -333,6 +379,12 @@ static int gram_dx_impl(modl_ctx *ctx, const T *D, int64_t ldd, const T *X, int6
     T *panel = nullptr;
     MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)((k + b) * lds), &panel));
     T *Dsub = panel, *Xsub = panel + k * lds;
+    if constexpr (std::is_same<T, float>::value) {
+        if (use_tc<T>(ctx) && s > 0 && (G || (Dx && b > 0))) {
+            if (panel_out) *panel_out = Dsub;
+            return gram_dx_tc(ctx, D, ldd, X, ldx, subset, s, k, b, p, scale, G, Dx, xnorm2, Dsub, lds, st);
+        }
+    }
     prof_mark(ctx, st, MODL_PROF_GATHER);
     MODL_TRY(gather_cols<T>(ctx, D, ldd, k, p, subset, s, Dsub, lds, nullptr, st));
     if (b > 0 && (Dx || xnorm2))
@@ -380,11 +432,24 @@ static int update_stats_impl(modl_ctx *ctx, const T *code, const int64_t *indice
     const double bt = (double)(global_batch > 0 ? global_batch : b);
     const T a = overwrite ? (T)(1.0 / bt) : (T)(w / bt);
     const T be = (overwrite || increments_only) ? T(0) : (T)(1.0 - w);
-    if (C) MODL_TRY(gemm_simt<T>(ctx, A_MMAJOR, B_NMAJOR, k, k, b, a, cb, k, cb, k, be, C, k, st));
-    if (B) {
-        MODL_REQUIRE(X != nullptr && p >= 1, "X required for the B_ update");
-        MODL_TRY(gemm_simt<T>(ctx, A_MMAJOR, B_NMAJOR, k, p, b, a, cb, k, X, ldx, be, B, ldb, st));
+    MODL_REQUIRE(B == nullptr || (X != nullptr && p >= 1), "X required for the B_ update");
+    if constexpr (std::is_same<T, float>::value) {
+        if (use_tc<T>(ctx)) {
+            // contraction over the batch: code^T and X^T as packed split panels (transposing packs)
+            float *codeP = nullptr, *XP = nullptr;
+            MODL_TRY(ws<float>(ctx, WS_TC_CODE, tc_packed_elems(k, b), &codeP));
+            MODL_TRY(tc_pack_cols(ctx, cb, k, b, k, codeP, st));
+            if (C) MODL_TRY(tc_gemm(ctx, codeP, codeP, k, k, b, a, be, C, k, st));
+            if (B) {
+                MODL_TRY(ws<float>(ctx, WS_TC_X, tc_packed_elems(p, b), &XP));
+                MODL_TRY(tc_pack_cols(ctx, X, ldx, b, p, XP, st));
+                MODL_TRY(tc_gemm(ctx, codeP, XP, k, p, b, a, be, B, ldb, st));
+            }
+            return MODL_OK;
+        }
     }
+    if (C) MODL_TRY(gemm_simt<T>(ctx, A_MMAJOR, B_NMAJOR, k, k, b, a, cb, k, cb, k, be, C, k, st));
+    if (B) MODL_TRY(gemm_simt<T>(ctx, A_MMAJOR, B_NMAJOR, k, p, b, a, cb, k, X, ldx, be, B, ldb, st));
     return MODL_OK;
 }
 
@@ -437,8 +502,8 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
 
     T *xnorm2 = nullptr, *Gw = nullptr, *Dxw = nullptr, *cb = nullptr, *panel = nullptr;
     MODL_TRY(ws<T>(ctx, WS_XNORM, (size_t)b, &xnorm2));
-    MODL_TRY(ws<T>(ctx, WS_G, (size_t)(k * k), &Gw));
-    MODL_TRY(ws<T>(ctx, WS_DX, (size_t)(b * k), &Dxw));
+    MODL_TRY(ws<T>(ctx, WS_G, (size_t)(k * k + b * k), &Gw));   // [G ; Dx]: one (k + b) x k matrix
+    Dxw = Gw + k * k;
     MODL_TRY(ws<T>(ctx, WS_CODE_BATCH, (size_t)(b * k), &cb));
 
     T *panel_keep = nullptr;

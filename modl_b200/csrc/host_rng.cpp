@@ -77,8 +77,27 @@ public:
     // Fisher-Yates from the last slot down, j ~ U[0, i]
     template <typename V>
     void shuffle(V *x, int64_t n) {
+        if (n - 1 > 0xffffffffll) {
+            for (int64_t i = n - 1; i > 0; --i) {
+                const int64_t j = static_cast<int64_t>(bounded(static_cast<uint64_t>(i)));
+                const V t = x[i];
+                x[i] = x[j];
+                x[j] = t;
+            }
+            return;
+        }
+        // same draws as bounded(i) for every i, with the covering mask carried along instead of
+        // being rebuilt per element (it only changes when i crosses a power of two)
+        uint32_t mask = 0;
+        if (n > 1) {
+            mask = static_cast<uint32_t>(n - 1);
+            for (int sh = 1; sh < 32; sh <<= 1) mask |= mask >> sh;
+        }
         for (int64_t i = n - 1; i > 0; --i) {
-            const int64_t j = static_cast<int64_t>(bounded(static_cast<uint64_t>(i)));
+            const uint32_t top = static_cast<uint32_t>(i);
+            while ((mask >> 1) >= top) mask >>= 1;
+            uint32_t j;
+            do { j = next32() & mask; } while (j > top);
             const V t = x[i];
             x[i] = x[j];
             x[j] = t;
@@ -88,13 +107,17 @@ public:
 private:
     static constexpr uint32_t kWords = 624, kShift = 397;
 
+    static uint32_t twist(uint32_t cur, uint32_t nxt, uint32_t far) {
+        const uint32_t mix = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+        return far ^ (mix >> 1) ^ ((0u - (mix & 1u)) & 0x9908b0dfu);
+    }
+
+    // one full state transition, split at the wrap points so that the loops carry no modulo
     void refill() {
-        for (uint32_t i = 0; i < kWords; ++i) {
-            const uint32_t nxt = state_[(i + 1 == kWords) ? 0 : i + 1];
-            const uint32_t mix = (state_[i] & 0x80000000u) | (nxt & 0x7fffffffu);
-            const uint32_t far = state_[(i + kShift) % kWords];
-            state_[i] = far ^ (mix >> 1) ^ ((mix & 1u) ? 0x9908b0dfu : 0u);
-        }
+        uint32_t i = 0;
+        for (; i < kWords - kShift; ++i) state_[i] = twist(state_[i], state_[i + 1], state_[i + kShift]);
+        for (; i < kWords - 1; ++i) state_[i] = twist(state_[i], state_[i + 1], state_[i + kShift - kWords]);
+        state_[kWords - 1] = twist(state_[kWords - 1], state_[0], state_[kShift - 1]);
         cursor_ = 0;
     }
 

@@ -43,6 +43,8 @@ int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M
     P.A = Apacked; P.B = Bpacked; P.C = C; P.ldc = ldc; P.M = (int)M; P.N = (int)N;
     P.nkb = (int)tc_k_blocks(Kd);
     P.alpha = alpha; P.beta = beta;
+    P.lbo = TC_ROWS * 16u; P.sbo = 128u;
+    if (ctx->opt_tc_desc_mode == 1) { P.lbo = 128u; P.sbo = TC_ROWS * 16u; }     // bring-up probe: swapped roles
     const int64_t tiles = tc_row_blocks(M) * tc_row_blocks(N);
     // split the contraction until the grid covers the SMs (one CTA per SM: 193 KB of shared memory each)
     int64_t splits = ceil_div((int64_t)ctx->sm_count, tiles);

@@ -9,10 +9,10 @@
 //
 // Why a split.  Single-pass TF32 (10-bit mantissa) perturbs G and Dx at 1e-3, which flips the
 // coordinate-descent stop decisions and breaks the 1e-4 parity bound.  Every fp32
-// operand x is therefore stored as  hi = x with the 13 low mantissa bits cleared  (an exact TF32
-// value) and  lo = tf32(x - hi)  (x - hi is exact in fp32), and each product is accumulated as
+// operand x is therefore stored as  hi = tf32(x)  (round to nearest) and  lo = tf32(x - hi)
+// (x - hi is exact in fp32), and each product is accumulated as
 //        lo_a . hi_b  +  hi_a . lo_b  +  hi_a . hi_b          (fp32 accumulation in TMEM)
-// whose dropped terms are O(2^-22) relative: fp32-level accuracy at a third of the TF32 rate,
+// whose dropped terms are O(2^-24) relative: fp32-level accuracy at a third of the TF32 rate,
 // which is still ~5x the FP32 FMA rate of the CUDA cores.
 //
 // Operand format ("packed split panels").  A pack kernel (one pass over the source, fused with
@@ -52,10 +52,16 @@ __host__ __device__ inline size_t tc_packed_floats(int64_t rows, int64_t kd)
 // ---------------------------------------------------------------------------------------
 // split + pack
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float tc_round_tf32(float x)
+{
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));           // round to nearest, low 13 bits zero
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ void tc_split(float x, float &hi, float &lo)
 {
-    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-    lo = __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u);
+    hi = tc_round_tf32(x);                 // |x - hi| <= 2^-12 |x|, and x - hi is exact in fp32
+    lo = tc_round_tf32(x - hi);            // residual after both terms <= 2^-24 |x|
 }
 
 // position (in floats) of the 16-byte unit (row r, chunk c) inside the packed operand whose
@@ -207,12 +213,12 @@ __device__ __forceinline__ void tc_tmem_ld32(unsigned taddr, float (&v)[32])
 
 // K-major, no-swizzle shared-memory matrix descriptor of a [8 chunks][128 rows][16 B] half block
 // starting at shared address `saddr` (+ the K offset of the MMA inside the block).
-__device__ __forceinline__ uint64_t tc_smem_desc(unsigned saddr)
+__device__ __forceinline__ uint64_t tc_smem_desc(unsigned saddr, unsigned lbo, unsigned sbo)
 {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3ffffu) >> 4);                      // start address,            bits [0,14)
-    d |= (uint64_t)((TC_ROWS * 16u) >> 4) << 16;                   // leading byte offset (K),  bits [16,30)
-    d |= (uint64_t)(128u >> 4) << 32;                              // stride byte offset (M/N), bits [32,46)
+    d |= (uint64_t)(lbo >> 4) << 16;                               // leading byte offset (K),  bits [16,30)
+    d |= (uint64_t)(sbo >> 4) << 32;                               // stride byte offset (M/N), bits [32,46)
     d |= (uint64_t)1 << 46;                                        // descriptor version (sm_100)
     return d;                                                      // layout type 0 = no swizzle
 }
@@ -235,6 +241,7 @@ struct TcGemmParams {
     int nkb;             // k blocks of the whole contraction
     int kb_per_split;    // k blocks per grid.z slice
     float alpha, beta;
+    unsigned lbo, sbo;   // descriptor byte offsets: next 16-byte K chunk (2048), next 8-row group (128)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -294,8 +301,8 @@ tc_gemm_kernel(TcGemmParams P)
 #pragma unroll
                 for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
                     const unsigned koff = (unsigned)k8 * 2u * (TC_ROWS * 16u);    // two 16-byte chunks per MMA
-                    const uint64_t a_hi = tc_smem_desc(sa + koff), a_lo = tc_smem_desc(sa + TC_HALF_BYTES + koff);
-                    const uint64_t b_hi = tc_smem_desc(sb + koff), b_lo = tc_smem_desc(sb + TC_HALF_BYTES + koff);
+                    const uint64_t a_hi = tc_smem_desc(sa + koff, P.lbo, P.sbo), a_lo = tc_smem_desc(sa + TC_HALF_BYTES + koff, P.lbo, P.sbo);
+                    const uint64_t b_hi = tc_smem_desc(sb + koff, P.lbo, P.sbo), b_lo = tc_smem_desc(sb + TC_HALF_BYTES + koff, P.lbo, P.sbo);
                     tc_mma_tf32(tmem, a_lo, b_hi, TC_IDESC, (i | k8) != 0);       // small terms first
                     tc_mma_tf32(tmem, a_hi, b_lo, TC_IDESC, 1u);
                     tc_mma_tf32(tmem, a_hi, b_hi, TC_IDESC, 1u);

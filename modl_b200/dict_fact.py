@@ -313,8 +313,10 @@ class DictFact(CodingMixin, BaseEstimator):
         return self
 
     def _partial_fit_host(self, Xt, batches, sample_indices, stream):
-        """Host rows -> device, double-buffered on a side stream so that the copy of batch i+1
-        overlaps the kernels of batch i."""
+        """Host rows -> device through two device staging slots on a side stream, so that the copy
+        of batch i+1 overlaps the kernels of batch i -- also ACROSS calls: the slot counter and
+        the events persist, and the call returns as soon as the host buffer has been consumed (its
+        last copy has landed), not when the kernels are done."""
         dev = self._device
         pipe = self.__dict__.get("_pipeline")
         bs, p = self.batch_size, Xt.shape[1]
@@ -325,35 +327,39 @@ class DictFact(CodingMixin, BaseEstimator):
                 "copy_stream": torch.cuda.Stream(device=dev),
                 "copied": [torch.cuda.Event() for _ in range(2)],
                 "done": [torch.cuda.Event() for _ in range(2)],
+                "n": 0,
             }
             self.__dict__["_pipeline"] = pipe
         pinned = Xt.is_pinned()
         if not pinned and pipe["pin"] is None:
             pipe["pin"] = [torch.empty((bs, p), dtype=Xt.dtype, pin_memory=True) for _ in range(2)]
         cs = pipe["copy_stream"]
-        for i, batch in enumerate(batches):
-            slot = i & 1
+        for batch in batches:
+            n = pipe["n"]
+            slot = n & 1
             rows = Xt[batch]
             nb = rows.shape[0]
-            if i >= 2:
-                pipe["done"][slot].synchronize()      # kernels of batch i-2 no longer read this slot
             if pinned:
-                src = rows
+                src = rows                                # DMA straight from the caller's pinned rows
             else:
+                if n >= 2:
+                    pipe["copied"][slot].synchronize()    # the previous DMA out of this staging buffer is over
                 src = pipe["pin"][slot][:nb]
                 src.copy_(rows)
             dst = pipe["dev"][slot][:nb]
             with torch.cuda.stream(cs):
-                if i >= 2:
-                    cs.wait_event(pipe["done"][slot])
+                if n >= 2:
+                    cs.wait_event(pipe["done"][slot])     # kernels of batch n-2 no longer read this slot
                 dst.copy_(src, non_blocking=True)
                 pipe["copied"][slot].record(cs)
             stream.wait_event(pipe["copied"][slot])
             self._single_batch_fit(dst, get_sub_slice(sample_indices, batch))
             pipe["done"][slot].record(stream)
-        # the staging buffers may be reused by the next call only after these kernels finished
-        for ev in pipe["done"]:
-            ev.synchronize()
+            pipe["n"] = n + 1
+        if pinned:
+            # the caller may reuse its buffer once the copies have read it
+            for ev in pipe["copied"]:
+                ev.synchronize()
 
     def set_params(self, **params):
         """[ref: dict_fact.py:339-357] -- including its quirk: only a switch to G_agg='full' is
