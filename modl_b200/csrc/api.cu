@@ -67,6 +67,7 @@ int modl_ctx_create(int device, modl_ctx **out)
     if (const char *e = getenv("MODL_CD_WARPS")) c->opt_cd_warps = atoi(e);
     if (const char *e = getenv("MODL_FORCE_GLOBAL_GRAM")) c->opt_force_global_gram = atoi(e);
     if (const char *e = getenv("MODL_TC_GEMM")) c->opt_tc_gemm = atoi(e);
+    if (const char *e = getenv("MODL_BCD_BLOCK")) c->opt_bcd_block = atoi(e);
     if (const char *e = getenv("MODL_TC_DESC_MODE")) c->opt_tc_desc_mode = atoi(e);
     int *info = nullptr;
     if (ws<int>(c, WS_INFO, 4, &info) != MODL_OK) { delete c; return MODL_ECUDA; }
@@ -95,6 +96,7 @@ int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "force_global_gram")) ctx->opt_force_global_gram = value;
     else if (!strcmp(name, "bcd_timing")) ctx->opt_bcd_timing = value;
     else if (!strcmp(name, "tc_gemm")) ctx->opt_tc_gemm = value;
+    else if (!strcmp(name, "bcd_block")) ctx->opt_bcd_block = value;
     else if (!strcmp(name, "tc_desc_mode")) ctx->opt_tc_desc_mode = value;
     else if (!strcmp(name, "bcd_pilot")) ctx->opt_bcd_pilot = value;
     else { set_error("unknown option %s", name); return MODL_EINVAL; }
@@ -149,6 +151,15 @@ int modl_debug_bcd_timing(modl_ctx *ctx, double *h_gaps7)
         fprintf(stderr, "bcd pilot: mean wait for workers %.0f, mean block period %.0f cycles; atom 8->9 gap %lld, atom 7 end -> block1 start %lld\n",
                 wsync / nb, blk / (nb - 1), t[9 * 8] - t[8 * 8 + 7], x[16 + 2] - t[7 * 8 + 7]);
     }
+    return MODL_OK;
+}
+
+// debug: raw clock64 stamps of the last dictionary-update launch
+int modl_debug_bcd_stamps(modl_ctx *ctx, long long *h_out, int n)
+{
+    MODL_REQUIRE(ctx && h_out && n > 0 && ctx->slot_ptr[WS_MISC], "no timing recorded");
+    MODL_CUDA_TRY(cudaDeviceSynchronize());
+    MODL_CUDA_TRY(cudaMemcpy(h_out, ctx->slot_ptr[WS_MISC], sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost));
     return MODL_OK;
 }
 

@@ -1,5 +1,6 @@
 // bcd_launch.cu -- launch geometry of the dictionary-update kernels (bcd_kernels.cuh, bcd_pilot.cuh).
 #include "bcd_kernels.cuh"
+#include "bcd_block.cuh"
 #include "bcd_pilot.cuh"
 #include "launch.h"
 
@@ -49,9 +50,16 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
         for (int cs = 16; cs >= 2 && !nblk; cs >>= 1) {
             if (cs > ctx->opt_bcd_cluster) continue;
             const int64_t c = round_up(ceil_div(s, cs), 4), ncp = round_up(c, 32);
-            for (int pilot = ctx->opt_bcd_pilot ? 1 : 0; pilot >= 0 && !nblk; --pilot) {
+            // variant 2 = blocked update with deferred projection scalars (L2 ball, no positivity clamp),
+            // 1 = per-atom look-ahead pilot, 0 = plain per-atom kernel
+            const bool block_ok = ctx->opt_bcd_block && l1_ratio == T(0) && !positive;
+            for (int pilot = block_ok ? 2 : (ctx->opt_bcd_pilot ? 1 : 0); pilot >= 0 && !nblk; --pilot) {
+                if (pilot == 1 && !ctx->opt_bcd_pilot) continue;
                 size_t need;
-                if (pilot) {
+                if (pilot == 2) {
+                    if (ncp > BB_THREADS) continue;
+                    need = bcd_block_smem_bytes<T>(k, ncp);
+                } else if (pilot) {
                     if (ncp > 192) continue;
                     need = bcd_pilot_smem_bytes<T>(k, ncp);
                 } else {
@@ -59,7 +67,8 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
                     if (ncp > 2 * BCD_THREADS) continue;
                 }
                 if (need > budget) continue;
-                const void *fn = pilot ? pilot_kernel_for<T>((int)(ncp / 32), l1_ratio != T(0)) : (const void *)kern;
+                const void *fn = pilot == 2 ? (const void *)bcd_block_kernel<T>
+                                 : pilot ? pilot_kernel_for<T>((int)(ncp / 32), l1_ratio != T(0)) : (const void *)kern;
                 if (cs > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
                     cudaGetLastError();
                     continue;
@@ -69,7 +78,7 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
                     continue;
                 }
                 cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(cs); cfg.blockDim = dim3(pilot ? BP_THREADS : BCD_THREADS);
+                cfg.gridDim = dim3(cs); cfg.blockDim = dim3(pilot == 2 ? BB_THREADS : pilot ? BP_THREADS : BCD_THREADS);
                 cfg.dynamicSmemBytes = need; cfg.stream = st;
                 cudaLaunchAttribute at[1];
                 at[0].id = cudaLaunchAttributeClusterDimension;
@@ -125,7 +134,8 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
     }
 
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(use_pilot ? BP_THREADS : BCD_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(use_pilot == 2 ? BB_THREADS : use_pilot ? BP_THREADS : BCD_THREADS);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     if (use_cluster) {
         at[0].id = cudaLaunchAttributeClusterDimension;
@@ -135,7 +145,10 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
         at[0].val.cooperative = 1;
     }
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (use_pilot) {
+    if (use_pilot == 2) {
+        void *args[] = {&P};
+        MODL_CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void *)bcd_block_kernel<T>, args));
+    } else if (use_pilot) {
         void *args[] = {&P};
         MODL_CUDA_TRY(cudaLaunchKernelExC(&cfg, pilot_kernel_for<T>((int)(round_up(cols, 32) / 32), l1_ratio != T(0)), args));
     } else {

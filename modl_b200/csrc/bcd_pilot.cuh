@@ -24,8 +24,13 @@
 namespace modl {
 
 constexpr int BP_M = 8;                       // atoms per look-ahead block
-constexpr int BP_THREADS = 256;               // warp 0 = pilot, warps 1..7 = workers
-constexpr int BP_WORKERS = BP_THREADS - 32;
+constexpr int BP_THREADS = 256;               // warp 0 = pilot, warps 1-3 and 5-7 = workers, warp 4 idles
+// Warp w issues from scheduler w % 4.  The pilot's dependent chain is latency bound, so the other
+// warps of ITS scheduler (4, 8, ...) stay idle during the atom loop: the pilot then never waits
+// for an issue slot behind a worker's FFMA2 / LDS stream.
+constexpr int BP_WORKER_WARPS = BP_THREADS / 32 - 1 - (BP_THREADS / 32 - 1) / 4;
+constexpr int BP_WORKERS = BP_WORKER_WARPS * 32;
+constexpr int BP_SYNCED = BP_WORKERS + 32;    // threads that meet at the pilot <-> worker barriers
 enum { BP_BAR_PRODUCT = 1, BP_BAR_SNAPSHOT = 2, BP_BAR_WORKERS = 3 };
 
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
@@ -161,13 +166,15 @@ bcd_pilot_kernel(BcdParams<T> P)
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     if (xstamp) xstamp[1] = clock64();
 
-    if (wid != 0) {
+    if (wid != 0 && (wid & 3) == 0) {
+        // idle warp: leaves the pilot's scheduler alone, joins again at the epilogue
+    } else if (wid != 0) {
         // =========================== workers: everything off the critical path ===========================
-        const int wt = tid - 32;
+        const int wt = (wid - 1 - (wid >> 2)) * 32 + lane;
         const int pr = wt % NP, ig = wt / NP;
         const int RB = (((k + IGW - 1) / IGW) + 3) & ~3;
         for (int b = 0; b < nbk; ++b) {
-            if (b > 0) named_sync(BP_BAR_SNAPSHOT, BP_THREADS);     // pilot is done with block b-2 and its buffers
+            if (b > 0) named_sync(BP_BAR_SNAPSHOT, BP_SYNCED);     // pilot is done with block b-2 and its buffers
             const int nb = b & 1;
             const int mb = min(BP_M, k - b * BP_M);
             T *Cb = Cblk + nb * kp * BP_M;
@@ -238,7 +245,7 @@ bcd_pilot_kernel(BcdParams<T> P)
                 Rb[e] = sum;
             }
             __threadfence_block();
-            named_arrive(BP_BAR_PRODUCT, BP_THREADS);
+            named_arrive(BP_BAR_PRODUCT, BP_SYNCED);
         }
     } else {
         // =========================== pilot: the dependent chain ===========================
@@ -291,9 +298,9 @@ bcd_pilot_kernel(BcdParams<T> P)
             T *dcur = delta + cur * BP_M * ncp;
             const T *dprev = delta + (cur ^ 1) * BP_M * ncp;
             if (xstamp) xstamp[16 + 2 * b] = clock64();
-            named_sync(BP_BAR_PRODUCT, BP_THREADS);               // look-ahead product, B rows and tables of block b are ready
+            named_sync(BP_BAR_PRODUCT, BP_SYNCED);               // look-ahead product, B rows and tables of block b are ready
             if (xstamp) xstamp[16 + 2 * b + 1] = clock64();
-            if (b + 1 < nbk) named_arrive(BP_BAR_SNAPSHOT, BP_THREADS);   // workers may recycle the buffers of block b-1
+            if (b + 1 < nbk) named_arrive(BP_BAR_SNAPSHOT, BP_SYNCED);   // workers may recycle the buffers of block b-1
 
             for (int j = 0; j < mb; ++j) {
                 tstamp = (P.timing && g == 0) ? P.timing + (int64_t)(b * BP_M + j) * 8 : nullptr;

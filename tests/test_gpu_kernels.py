@@ -180,13 +180,15 @@ def test_ridge_reports_non_spd(dev):
                                      np.ones((3, 8), np.float32), np.arange(3), 0., 0.1, False, 1e-2, 10)
 
 
-def _run_update_dict(dev, D0, B, C, norm0, subset, order, l1, pos, G0=None, mode=0, w=0.5, step=1.0, cluster=None):
+def _run_update_dict(dev, D0, B, C, norm0, subset, order, l1, pos, G0=None, mode=0, w=0.5, step=1.0, cluster=None,
+                     block=1):
     from modl_b200 import _lib
     from modl_b200._util import ptr, stream_of
     k, p = D0.shape
     ctx = _lib.get_context(0)
     if cluster is not None:
         ctx.set_option("bcd_cluster", cluster)
+    ctx.set_option("bcd_block", block)
     try:
         Dd, Bd, Cd, nd, sd = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (D0, B, C, norm0, subset))
         Gd = torch.from_numpy(G0.copy()).to(dev) if G0 is not None else None
@@ -198,20 +200,24 @@ def _run_update_dict(dev, D0, B, C, norm0, subset, order, l1, pos, G0=None, mode
     finally:
         if cluster is not None:
             ctx.set_option("bcd_cluster", 16)
+        ctx.set_option("bcd_block", 0)
     return Dd.cpu().numpy(), nd.cpu().numpy(), (Gd.cpu().numpy() if Gd is not None else None)
 
 
+@pytest.mark.parametrize("block", [1, 0])
 @pytest.mark.parametrize("cluster", [16, 8, 2, 0])
-def test_update_dict_golden(dev, golden, cluster):
+def test_update_dict_golden(dev, golden, cluster, block):
     """One BCD dictionary step vs the reference's _update_dict (golden), for every barrier
-    flavour: 16/8/2-CTA clusters and the cooperative global barrier."""
+    flavour (16/8/2-CTA clusters, cooperative global barrier) and both L2-ball kernels
+    (block=1: blocked update with deferred projection scalars; block=0: per-atom kernels)."""
     g = golden("update_dict.npz")
     for dt in (np.float32, np.float64):
         for ci, (l1, pos, full) in enumerate(g["cases"]):
             tag = "%s_%d" % (dt.__name__, ci)
             G0 = g["G0_" + tag] if full else None
             D1, n1, G1 = _run_update_dict(dev, g["D0_" + tag], g["B_" + tag], g["C_" + tag], g["norm0_" + tag],
-                                          g["subset_" + tag], g["order_" + tag], l1, pos, G0, cluster=cluster)
+                                          g["subset_" + tag], g["order_" + tag], l1, pos, G0, cluster=cluster,
+                                          block=block)
             tol = 2e-5 if dt == np.float32 else 1e-11
             assert rel_err(D1, g["D1_" + tag]) < tol, (tag, cluster, rel_err(D1, g["D1_" + tag]))
             assert np.abs(n1 - g["norm1_" + tag]).max() < 10 * tol, (tag, cluster)
@@ -223,8 +229,9 @@ def test_update_dict_golden(dev, golden, cluster):
             np.testing.assert_array_equal(D1[:, mask], g["D0_" + tag][:, mask])
 
 
-@pytest.mark.parametrize("shape", [(256, 10000, 1250), (70, 30000, 2500), (64, 4000, 4000), (256, 6000, 300)])
-def test_update_dict_bench_shapes(dev, oracle, shape):
+@pytest.mark.parametrize("block", [1, 0])
+@pytest.mark.parametrize("shape", [(256, 10000, 1250), (70, 30000, 2500), (64, 4000, 4000), (256, 6000, 300), (37, 900, 333)])
+def test_update_dict_bench_shapes(dev, oracle, shape, block):
     """Config-2 / config-4-like panels against the oracle's BCD, L2 and L1 balls."""
     k, p, s = shape
     rng = np.random.RandomState(5)
@@ -246,7 +253,7 @@ def test_update_dict_bench_shapes(dev, oracle, shape):
         oracle.update_dict_panel(Dw, gw, C, nw, order, l1, pos)
         want = D0.copy()
         want[:, subset] = Dw
-        D1, n1, _ = _run_update_dict(dev, D0, B, C, norm0, subset, order, l1, pos)
+        D1, n1, _ = _run_update_dict(dev, D0, B, C, norm0, subset, order, l1, pos, block=block)
         assert rel_err(D1, want) < 5e-5, (shape, l1, pos, rel_err(D1, want))
         assert np.abs(n1 - nw).max() < 5e-4, (shape, l1, np.abs(n1 - nw).max())
 
