@@ -348,11 +348,11 @@ static int gram_dx_tc(modl_ctx *ctx, const float *D, int64_t ldd, const float *X
         MODL_TRY(gather_cols<float>(ctx, X, ldx, b, p, nullptr, 0, (float *)nullptr, 0, xnorm2, st));
     prof_mark(ctx, st, MODL_PROF_GRAM);
     if (G != nullptr && (!want_dx || Dx == G + k * k)) {
-        MODL_TRY(tc_gemm(ctx, packed, packed, rows, k, kd, scale, 0.f, G, k, st));      // G and Dx are one (k + b) x k matrix
+        MODL_TRY(tc_gemm(ctx, packed, packed, rows, k, kd, scale, 0.f, G, k, 128, st)); // G and Dx are one (k + b) x k matrix
     } else {
         float *gdx = nullptr;
         MODL_TRY(ws<float>(ctx, WS_GDX, (size_t)(rows * k), &gdx));
-        MODL_TRY(tc_gemm(ctx, packed, packed, rows, k, kd, scale, 0.f, gdx, k, st));
+        MODL_TRY(tc_gemm(ctx, packed, packed, rows, k, kd, scale, 0.f, gdx, k, 128, st));
         if (G) MODL_CUDA_TRY(cudaMemcpyAsync(G, gdx, sizeof(float) * (size_t)(k * k), cudaMemcpyDeviceToDevice, st));
         if (want_dx)
             MODL_CUDA_TRY(cudaMemcpyAsync(Dx, gdx + k * k, sizeof(float) * (size_t)(b * k), cudaMemcpyDeviceToDevice, st));
@@ -449,12 +449,13 @@ static int update_stats_impl(modl_ctx *ctx, const T *code, const int64_t *indice
             // contraction over the batch: code^T and X^T as packed split panels (transposing packs)
             float *codeP = nullptr, *XP = nullptr;
             MODL_TRY(ws<float>(ctx, WS_TC_CODE, tc_packed_elems(k, b), &codeP));
-            MODL_TRY(tc_pack_cols(ctx, cb, k, b, k, codeP, st));
-            if (C) MODL_TRY(tc_gemm(ctx, codeP, codeP, k, k, b, a, be, C, k, st));
+            MODL_TRY(tc_pack_cols(ctx, cb, k, b, k, codeP, 128, st));
+            if (C) MODL_TRY(tc_gemm(ctx, codeP, codeP, k, k, b, a, be, C, k, 128, st));
             if (B) {
-                MODL_TRY(ws<float>(ctx, WS_TC_X, tc_packed_elems(p, b), &XP));
-                MODL_TRY(tc_pack_cols(ctx, X, ldx, b, p, XP, st));
-                MODL_TRY(tc_gemm(ctx, codeP, XP, k, p, b, a, be, B, ldb, st));
+                const int bn = tc_pick_bn(ctx, p, ceil_div(k, 128));       // e.g. p = 10000, k = 256: 144 -> 140 CTAs, one wave
+                MODL_TRY(ws<float>(ctx, WS_TC_X, tc_packed_elems(p, b, bn), &XP));
+                MODL_TRY(tc_pack_cols(ctx, X, ldx, b, p, XP, bn, st));
+                MODL_TRY(tc_gemm(ctx, codeP, XP, k, p, b, a, be, B, ldb, bn, st));
             }
             return MODL_OK;
         }

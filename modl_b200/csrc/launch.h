@@ -40,13 +40,16 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
                const int32_t *d_order, int64_t k, int64_t s, T l1_ratio, int positive, cudaStream_t st);
 
 // tc_gemm.cu -- tcgen05 3xTF32 GEMM on packed split panels (float only)
-size_t tc_packed_elems(int64_t rows, int64_t kd);
+size_t tc_packed_elems(int64_t rows, int64_t kd, int64_t rows_per_block = 128);
+int tc_pick_bn(const modl_ctx *ctx, int64_t N, int64_t mtiles);
 int64_t tc_rows_padded(int64_t rows);
 int tc_pack_rows(modl_ctx *ctx, const float *src, int64_t ld, int64_t rows, int64_t p, const int64_t *subset,
                  int64_t kd, float *packed, int64_t row0, int64_t rows_pad_end, float *plain, int64_t ldp,
                  float *norm2, cudaStream_t st);
-int tc_pack_cols(modl_ctx *ctx, const float *src, int64_t ld, int64_t kd, int64_t rows, float *packed, cudaStream_t st);
+int tc_pack_cols(modl_ctx *ctx, const float *src, int64_t ld, int64_t kd, int64_t rows, float *packed,
+                 int rows_per_block, cudaStream_t st);
+// bn = accumulator tile width = rows per block of the packed B operand (multiple of 16, <= 256)
 int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M, int64_t N, int64_t Kd, float alpha,
-            float beta, float *C, int64_t ldc, cudaStream_t st);
+            float beta, float *C, int64_t ldc, int bn, cudaStream_t st);
 
 }  // namespace modl

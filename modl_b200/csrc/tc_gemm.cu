@@ -5,7 +5,23 @@
 
 namespace modl {
 
-size_t tc_packed_elems(int64_t rows, int64_t kd) { return tc_packed_floats(rows, kd); }
+size_t tc_packed_elems(int64_t rows, int64_t kd, int64_t rpb) { return tc_packed_floats(rows, kd, rpb); }
+
+// Accumulator tile width for an N-column output produced by `mtiles` row tiles: the multiple of 16
+// in [128, 160] whose tile count wastes the least of the last wave over the SMs (one CTA per SM).
+// p = 10000, M = 256: bn = 144 -> 70 x 2 = 140 CTAs in ONE wave instead of 158 in two.
+int tc_pick_bn(const modl_ctx *ctx, int64_t N, int64_t mtiles)
+{
+    int best = TC_ROWS;
+    double best_cost = 1e300;
+    for (int bn = 128; bn <= 160; bn += 16) {
+        const int64_t ctas = ceil_div(N, bn) * mtiles;
+        const int64_t waves = ceil_div(ctas, ctx->sm_count);
+        const double cost = (double)waves * bn;            // time ~ waves x tile width
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
 int64_t tc_rows_padded(int64_t rows) { return tc_row_blocks(rows) * TC_ROWS; }
 
 int tc_pack_rows(modl_ctx *ctx, const float *src, int64_t ld, int64_t rows, int64_t p, const int64_t *subset,
@@ -20,34 +36,43 @@ int tc_pack_rows(modl_ctx *ctx, const float *src, int64_t ld, int64_t rows, int6
     return MODL_OK;
 }
 
-int tc_pack_cols(modl_ctx *ctx, const float *src, int64_t ld, int64_t kd, int64_t rows, float *packed, cudaStream_t st)
+int tc_pack_cols(modl_ctx *ctx, const float *src, int64_t ld, int64_t kd, int64_t rows, float *packed, int rpb,
+                 cudaStream_t st)
 {
     if (rows <= 0 || kd <= 0) return MODL_OK;
-    const int64_t total = tc_row_blocks(rows) * TC_ROWS * tc_k_blocks(kd) * TC_CHUNKS;
-    tc_pack_cols_kernel<<<grid_for(ctx, ceil_div(total, 256), 16), 256, 0, st>>>(src, ld, (int)kd, (int)rows, packed);
+    const int64_t total = tc_row_blocks(rows, rpb) * rpb * tc_k_blocks(kd) * TC_CHUNKS;
+    tc_pack_cols_kernel<<<grid_for(ctx, ceil_div(total, 256), 16), 256, 0, st>>>(src, ld, (int)kd, (int)rows, packed, rpb);
     MODL_LAUNCH_CHECK(ctx);
     return MODL_OK;
 }
 
 int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M, int64_t N, int64_t Kd, float alpha,
-            float beta, float *C, int64_t ldc, cudaStream_t st)
+            float beta, float *C, int64_t ldc, int bn, cudaStream_t st)
 {
     if (M <= 0 || N <= 0) return MODL_OK;
     MODL_REQUIRE(Kd >= 1, "tc_gemm needs a non-empty contraction");
-    static bool configured = false;
-    if (!configured) {
-        MODL_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-        configured = true;
-    }
+    MODL_REQUIRE(bn >= 16 && bn <= TC_MAX_BN && bn % 16 == 0, "tc_gemm tile width");
     TcGemmParams P;
     P.A = Apacked; P.B = Bpacked; P.C = C; P.ldc = ldc; P.M = (int)M; P.N = (int)N;
     P.nkb = (int)tc_k_blocks(Kd);
     P.alpha = alpha; P.beta = beta;
-    P.lbo = TC_ROWS * 16u; P.sbo = 128u;
-    if (ctx->opt_tc_desc_mode == 1) { P.lbo = 128u; P.sbo = TC_ROWS * 16u; }     // bring-up probe: swapped roles
-    const int64_t tiles = tc_row_blocks(M) * tc_row_blocks(N);
+    P.sbo = 128u;
+    P.bn = bn;
+    P.tmem_cols = 32;
+    while ((int)P.tmem_cols < bn) P.tmem_cols <<= 1;
+    const size_t stage_bytes = TC_BLOCK_BYTES + (size_t)2 * bn * TC_BK * 4;
+    P.stages = (int)((TC_SMEM_BUDGET - 1024) / stage_bytes);
+    if (P.stages > TC_MAX_STAGES) P.stages = TC_MAX_STAGES;
+    MODL_REQUIRE(P.stages >= 2, "tc_gemm tile does not fit shared memory");
+    const size_t smem_bytes = (size_t)P.stages * stage_bytes + 1024;
+    static size_t configured = 0;
+    if (configured < smem_bytes) {
+        MODL_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET));
+        configured = TC_SMEM_BUDGET;
+    }
+    const int64_t tiles = tc_row_blocks(M) * tc_row_blocks(N, bn);
     // split the contraction until the grid covers the SMs (one CTA per SM: 193 KB of shared memory each)
-    int64_t splits = ceil_div((int64_t)ctx->sm_count, tiles);
+    int64_t splits = (int64_t)ctx->sm_count / tiles;            // never more CTAs than SMs: a second wave costs a whole tile time
     if (splits > P.nkb) splits = P.nkb;
     if (splits > 32) splits = 32;
     if (splits < 1) splits = 1;
@@ -55,8 +80,8 @@ int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M
     splits = ceil_div(P.nkb, P.kb_per_split);
     P.part = nullptr;
     if (splits > 1) MODL_TRY(ws<float>(ctx, WS_GEMM_PART, (size_t)(splits * M * N), &P.part));
-    dim3 grid((unsigned)tc_row_blocks(N), (unsigned)tc_row_blocks(M), (unsigned)splits);
-    tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(P);
+    dim3 grid((unsigned)tc_row_blocks(N, bn), (unsigned)tc_row_blocks(M), (unsigned)splits);
+    tc_gemm_kernel<<<grid, TC_THREADS, smem_bytes, st>>>(P);
     MODL_LAUNCH_CHECK(ctx);
     if (splits > 1) {
         const int64_t total = M * N;

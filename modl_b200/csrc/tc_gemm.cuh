@@ -36,17 +36,20 @@ constexpr int TC_HALF_FLOATS = TC_ROWS * TC_BK;            // floats of the hi (
 constexpr int TC_BLOCK_FLOATS = 2 * TC_HALF_FLOATS;        // hi + lo
 constexpr unsigned TC_BLOCK_BYTES = TC_BLOCK_FLOATS * 4;   // 32 KB
 constexpr unsigned TC_HALF_BYTES = TC_HALF_FLOATS * 4;     // 16 KB
-constexpr int TC_STAGES = 3;                 // 3 x (A block + B block) = 192 KB of shared memory
+constexpr int TC_MAX_STAGES = 3;
 constexpr int TC_THREADS = 192;              // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
-constexpr unsigned TC_TMEM_COLS = 128;       // one 128 x 128 fp32 accumulator
-constexpr size_t TC_SMEM_BYTES = (size_t)TC_STAGES * 2 * TC_BLOCK_BYTES + 1024;
+constexpr int TC_MAX_BN = 256;               // widest accumulator tile (UMMA N)
+constexpr size_t TC_SMEM_BUDGET = 226 * 1024;
 
-__host__ __device__ inline int64_t tc_row_blocks(int64_t rows) { return ceil_div(rows, TC_ROWS); }
+// An operand is cut into blocks of `rpb` rows (rows-per-block: 128 on the M side; the UMMA N of
+// the launch, a multiple of 16, on the N side) x 32 contraction elements.
+__host__ __device__ inline int64_t tc_row_blocks(int64_t rows, int64_t rpb = TC_ROWS) { return ceil_div(rows, rpb); }
 __host__ __device__ inline int64_t tc_k_blocks(int64_t kd) { return ceil_div(kd, TC_BK); }
+__host__ __device__ inline size_t tc_block_floats(int64_t rpb) { return (size_t)(2 * rpb * TC_BK); }
 // floats of a packed operand with `rows` rows and contraction length `kd`
-__host__ __device__ inline size_t tc_packed_floats(int64_t rows, int64_t kd)
+__host__ __device__ inline size_t tc_packed_floats(int64_t rows, int64_t kd, int64_t rpb = TC_ROWS)
 {
-    return (size_t)tc_row_blocks(rows) * (size_t)tc_k_blocks(kd) * TC_BLOCK_FLOATS;
+    return (size_t)tc_row_blocks(rows, rpb) * (size_t)tc_k_blocks(kd) * tc_block_floats(rpb);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -66,18 +69,18 @@ __device__ __forceinline__ void tc_split(float x, float &hi, float &lo)
 
 // position (in floats) of the 16-byte unit (row r, chunk c) inside the packed operand whose
 // contraction spans `nkb` blocks; the lo copy sits TC_HALF_FLOATS further.
-__device__ __forceinline__ size_t tc_unit_offset(int64_t r, int64_t c, int64_t nkb)
+__device__ __forceinline__ size_t tc_unit_offset(int64_t r, int64_t c, int64_t nkb, int64_t rpb)
 {
-    const int64_t rb = r / TC_ROWS, rr = r % TC_ROWS, kb = c / TC_CHUNKS, cc = c % TC_CHUNKS;
-    return ((size_t)(rb * nkb + kb)) * TC_BLOCK_FLOATS + (size_t)(cc * TC_ROWS + rr) * 4;
+    const int64_t rb = r / rpb, rr = r % rpb, kb = c / TC_CHUNKS, cc = c % TC_CHUNKS;
+    return ((size_t)(rb * nkb + kb)) * tc_block_floats(rpb) + (size_t)(cc * rpb + rr) * 4;
 }
 
-__device__ __forceinline__ void tc_store_unit(float *__restrict__ packed, size_t off, const float (&v)[4])
+__device__ __forceinline__ void tc_store_unit(float *__restrict__ packed, size_t off, const float (&v)[4], int64_t rpb)
 {
     float4 h, l;
     tc_split(v[0], h.x, l.x); tc_split(v[1], h.y, l.y); tc_split(v[2], h.z, l.z); tc_split(v[3], h.w, l.w);
     *reinterpret_cast<float4 *>(packed + off) = h;
-    *reinterpret_cast<float4 *>(packed + off + TC_HALF_FLOATS) = l;
+    *reinterpret_cast<float4 *>(packed + off + rpb * TC_BK) = l;
 }
 
 // Rows of a row-major source become operand rows; the contraction runs along the source row,
@@ -98,12 +101,24 @@ tc_pack_rows_kernel(const float *__restrict__ src, int64_t ld, int rows, int p, 
         const bool real = r < rows;
         const float *row = src + r * ld;
         if (real && norm2 != nullptr) {
-            float acc = 0.f;
-            for (int j = threadIdx.x; j < p; j += blockDim.x) {
+            float acc = 0.f, acc1 = 0.f;
+            int j0 = 0;
+            if (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {     // 128-bit streaming loads
+                const float4 *row4 = reinterpret_cast<const float4 *>(row);
+                const int n4 = p >> 2;
+#pragma unroll 4
+                for (int j = threadIdx.x; j < n4; j += blockDim.x) {
+                    const float4 v = __ldg(row4 + j);
+                    acc = fmaf(v.x, v.x, acc); acc1 = fmaf(v.y, v.y, acc1);
+                    acc = fmaf(v.z, v.z, acc); acc1 = fmaf(v.w, v.w, acc1);
+                }
+                j0 = n4 << 2;
+            }
+            for (int j = j0 + threadIdx.x; j < p; j += blockDim.x) {
                 const float v = row[j];
                 acc = fmaf(v, v, acc);
             }
-            acc = block_sum(acc, scratch);
+            acc = block_sum(acc + acc1, scratch);
             if (threadIdx.x == 0) norm2[r] = acc;
         }
         for (int c = threadIdx.x; c < nunits; c += blockDim.x) {
@@ -113,7 +128,7 @@ tc_pack_rows_kernel(const float *__restrict__ src, int64_t ld, int rows, int p, 
                 const int j = 4 * c + i;
                 v[i] = (real && j < kd) ? row[subset ? subset[j] : (int64_t)j] : 0.f;
             }
-            tc_store_unit(packed, tc_unit_offset(row0 + r, c, nkb), v);
+            tc_store_unit(packed, tc_unit_offset(row0 + r, c, nkb, TC_ROWS), v, TC_ROWS);
             if (real && plain != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -128,10 +143,10 @@ tc_pack_rows_kernel(const float *__restrict__ src, int64_t ld, int rows, int p, 
 // One thread per 16-byte unit, consecutive threads take consecutive r: coalesced 128 B reads of
 // four source rows and coalesced 16-byte-per-thread writes.
 __global__ void __launch_bounds__(256)
-tc_pack_cols_kernel(const float *__restrict__ src, int64_t ld, int kd, int rows, float *__restrict__ packed)
+tc_pack_cols_kernel(const float *__restrict__ src, int64_t ld, int kd, int rows, float *__restrict__ packed, int rpb)
 {
     const int64_t nkb = tc_k_blocks(kd);
-    const int64_t rows_pad = tc_row_blocks(rows) * TC_ROWS;
+    const int64_t rows_pad = tc_row_blocks(rows, rpb) * rpb;
     const int64_t nunits = nkb * TC_CHUNKS;
     const int64_t total = rows_pad * nunits;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -142,7 +157,7 @@ tc_pack_cols_kernel(const float *__restrict__ src, int64_t ld, int kd, int rows,
             const int64_t j = 4 * c + i;
             v[i] = (r < rows && j < kd) ? src[j * ld + r] : 0.f;
         }
-        tc_store_unit(packed, tc_unit_offset(r, c, nkb), v);
+        tc_store_unit(packed, tc_unit_offset(r, c, nkb, rpb), v, rpb);
     }
 }
 
@@ -223,8 +238,11 @@ __device__ __forceinline__ uint64_t tc_smem_desc(unsigned saddr, unsigned lbo, u
     return d;                                                      // layout type 0 = no swizzle
 }
 
-// kind::tf32 instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
-constexpr unsigned TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TC_ROWS >> 3) << 17) | ((unsigned)(TC_ROWS >> 4) << 24);
+// kind::tf32 instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = bn
+__host__ __device__ inline unsigned tc_idesc(unsigned bn)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((bn >> 3) << 17) | ((unsigned)(TC_ROWS >> 4) << 24);
+}
 
 // ---------------------------------------------------------------------------------------
 // C[M x N] = alpha * A . B^T + beta * C      (A: M x Kd, B: N x Kd, packed split panels)
@@ -232,8 +250,11 @@ constexpr unsigned TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(T
 // partial tile to part[z][M][N] and a fixed-order reduction applies alpha/beta afterwards.
 // ---------------------------------------------------------------------------------------
 struct TcGemmParams {
-    const float *A;      // packed, tc_row_blocks(M) x nkb blocks
-    const float *B;      // packed, tc_row_blocks(N) x nkb blocks
+    const float *A;      // packed, 128-row blocks: tc_row_blocks(M) x nkb
+    const float *B;      // packed, bn-row blocks:  tc_row_blocks(N, bn) x nkb
+    int bn;              // accumulator tile width (UMMA N): multiple of 16, 16..256
+    int stages;          // smem pipeline depth (<= TC_MAX_STAGES)
+    unsigned tmem_cols;  // power of two >= bn
     float *C;
     int64_t ldc;
     float *part;         // split-K partials or NULL
@@ -241,21 +262,25 @@ struct TcGemmParams {
     int nkb;             // k blocks of the whole contraction
     int kb_per_split;    // k blocks per grid.z slice
     float alpha, beta;
-    unsigned lbo, sbo;   // descriptor byte offsets: next 16-byte K chunk (2048), next 8-row group (128)
+    unsigned sbo;        // descriptor stride byte offset: next 8-row group (128)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(TcGemmParams P)
 {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
-    __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 1];
+    __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_STAGES + 1];
     __shared__ unsigned tmem_base_s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(tc_smem) + 1023u) & ~1023u;
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * (unsigned)s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (unsigned)(TC_STAGES + s); };
-    const unsigned done_bar = bar0 + 8u * (unsigned)(2 * TC_STAGES);
+    auto empty_bar = [&](int s) { return bar0 + 8u * (unsigned)(TC_MAX_STAGES + s); };
+    const unsigned done_bar = bar0 + 8u * (unsigned)(2 * TC_MAX_STAGES);
+    const int STAGES = P.stages;
+    const unsigned a_bytes = TC_BLOCK_BYTES, b_half = (unsigned)P.bn * TC_BK * 4u, b_bytes = 2u * b_half;
+    const unsigned stage_bytes = a_bytes + b_bytes;
+    const size_t b_block_floats = (size_t)2 * P.bn * TC_BK;
 
     const int nb = blockIdx.x, mb = blockIdx.y;
     const int kb0 = blockIdx.z * P.kb_per_split;
@@ -263,11 +288,11 @@ tc_gemm_kernel(TcGemmParams P)
     const int nk = kb1 - kb0;                 // >= 1 by construction of the grid
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(full_bar(s), 1); tc_mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < STAGES; ++s) { tc_mbar_init(full_bar(s), 1); tc_mbar_init(empty_bar(s), 1); }
         tc_mbar_init(done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (warp == 1) tc_tmem_alloc((unsigned)__cvta_generic_to_shared(&tmem_base_s), TC_TMEM_COLS);
+    if (warp == 1) tc_tmem_alloc((unsigned)__cvta_generic_to_shared(&tmem_base_s), P.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -277,80 +302,113 @@ tc_gemm_kernel(TcGemmParams P)
         // ===== TMA producer =====
         if (lane == 0) {
             const float *Ab = P.A + ((size_t)mb * P.nkb + kb0) * TC_BLOCK_FLOATS;
-            const float *Bb = P.B + ((size_t)nb * P.nkb + kb0) * TC_BLOCK_FLOATS;
+            const float *Bb = P.B + ((size_t)nb * P.nkb + kb0) * b_block_floats;
             for (int i = 0; i < nk; ++i) {
-                const int s = i % TC_STAGES;
-                const unsigned ph = (unsigned)(i / TC_STAGES) & 1u;
+                const int s = i % STAGES;
+                const unsigned ph = (unsigned)(i / STAGES) & 1u;
                 tc_mbar_wait(empty_bar(s), ph ^ 1u);                 // slot free (first pass: immediately)
-                tc_mbar_expect_tx(full_bar(s), 2 * TC_BLOCK_BYTES);
-                const unsigned sa = smem0 + (unsigned)s * 2u * TC_BLOCK_BYTES;
-                tc_bulk_g2s(sa, Ab + (size_t)i * TC_BLOCK_FLOATS, TC_BLOCK_BYTES, full_bar(s));
-                tc_bulk_g2s(sa + TC_BLOCK_BYTES, Bb + (size_t)i * TC_BLOCK_FLOATS, TC_BLOCK_BYTES, full_bar(s));
+                tc_mbar_expect_tx(full_bar(s), stage_bytes);
+                const unsigned sa = smem0 + (unsigned)s * stage_bytes;
+                tc_bulk_g2s(sa, Ab + (size_t)i * TC_BLOCK_FLOATS, a_bytes, full_bar(s));
+                tc_bulk_g2s(sa + a_bytes, Bb + (size_t)i * b_block_floats, b_bytes, full_bar(s));
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
+            const unsigned idesc = tc_idesc((unsigned)P.bn);
+            const unsigned lbo_a = TC_ROWS * 16u, lbo_b = (unsigned)P.bn * 16u;   // next 16-byte K chunk of the block
             for (int i = 0; i < nk; ++i) {
-                const int s = i % TC_STAGES;
-                const unsigned ph = (unsigned)(i / TC_STAGES) & 1u;
+                const int s = i % STAGES;
+                const unsigned ph = (unsigned)(i / STAGES) & 1u;
                 tc_mbar_wait(full_bar(s), ph);
                 tc_fence_after();
-                const unsigned sa = smem0 + (unsigned)s * 2u * TC_BLOCK_BYTES;   // A: hi | lo
-                const unsigned sb = sa + TC_BLOCK_BYTES;                          // B: hi | lo
+                const unsigned sa = smem0 + (unsigned)s * stage_bytes;            // A: hi | lo
+                const unsigned sb = sa + a_bytes;                                 // B: hi | lo
 #pragma unroll
                 for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
-                    const unsigned koff = (unsigned)k8 * 2u * (TC_ROWS * 16u);    // two 16-byte chunks per MMA
-                    const uint64_t a_hi = tc_smem_desc(sa + koff, P.lbo, P.sbo), a_lo = tc_smem_desc(sa + TC_HALF_BYTES + koff, P.lbo, P.sbo);
-                    const uint64_t b_hi = tc_smem_desc(sb + koff, P.lbo, P.sbo), b_lo = tc_smem_desc(sb + TC_HALF_BYTES + koff, P.lbo, P.sbo);
-                    tc_mma_tf32(tmem, a_lo, b_hi, TC_IDESC, (i | k8) != 0);       // small terms first
-                    tc_mma_tf32(tmem, a_hi, b_lo, TC_IDESC, 1u);
-                    tc_mma_tf32(tmem, a_hi, b_hi, TC_IDESC, 1u);
+                    const unsigned ka = (unsigned)k8 * 2u * lbo_a, kb = (unsigned)k8 * 2u * lbo_b;   // two chunks per MMA
+                    const uint64_t a_hi = tc_smem_desc(sa + ka, lbo_a, P.sbo), a_lo = tc_smem_desc(sa + TC_HALF_BYTES + ka, lbo_a, P.sbo);
+                    const uint64_t b_hi = tc_smem_desc(sb + kb, lbo_b, P.sbo), b_lo = tc_smem_desc(sb + b_half + kb, lbo_b, P.sbo);
+                    tc_mma_tf32(tmem, a_lo, b_hi, idesc, (i | k8) != 0);          // small terms first
+                    tc_mma_tf32(tmem, a_hi, b_lo, idesc, 1u);
+                    tc_mma_tf32(tmem, a_hi, b_hi, idesc, 1u);
                 }
                 tc_commit(empty_bar(s));                                          // smem slot reusable when these finish
             }
             tc_commit(done_bar);                                                  // accumulator complete
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> global =====
+        // ===== epilogue: TMEM -> registers -> shared (transpose) -> coalesced global =====
+        // A thread of tcgen05.ld owns one accumulator ROW; storing rows straight to global would
+        // touch 32 different rows per warp instruction.  The operand stages are free once the
+        // last MMA has completed, so the tile is staged there and written out row by row, one
+        // 512-byte segment per warp instruction (and C is read the same way when beta != 0).
         tc_mbar_wait(done_bar, 0);
         tc_fence_after();
         const int q = warp & 3;                        // TMEM lane quadrant this warp may read
-        const int m = mb * TC_ROWS + q * 32 + lane;    // accumulator row = TMEM lane
         const unsigned trow = tmem + ((unsigned)(q * 32) << 16);
-        for (int c0 = 0; c0 < TC_ROWS; c0 += 32) {
+        const int pitch = P.bn + 4;                    // floats; 16-byte aligned rows, conflict-free quarter-warps
+        const unsigned tile0 = smem0;
+        for (int c0 = 0; c0 < P.bn; c0 += 32) {
             float v[32];
             __syncwarp();                              // tcgen05.ld is warp-collective (.sync.aligned)
             tc_tmem_ld32(trow + (unsigned)c0, v);
-            const int n0 = nb * TC_ROWS + c0;
-            if (m >= P.M || n0 >= P.N) {
-                // nothing of this strip belongs to the matrix
-            } else if (P.part != nullptr) {
-                float *dst = P.part + ((size_t)blockIdx.z * P.M + m) * P.N + n0;
+            const unsigned dst = tile0 + 4u * (unsigned)((q * 32 + lane) * pitch + c0);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (n0 + j < P.N) dst[j] = v[j];
-            } else {
-                float *dst = P.C + (int64_t)m * P.ldc + n0;
-                const bool vec = (n0 + 32 <= P.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-                if (vec) {
+            for (int jj = 0; jj < 32; jj += 4)
+                if (c0 + jj < P.bn)                    // bn is a multiple of 16: the last strip may be half valid
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + 4u * jj), "f"(v[jj]), "f"(v[jj + 1]),
+                                 "f"(v[jj + 2]), "f"(v[jj + 3]) : "memory");
+        }
+        asm volatile("bar.sync 2, 128;\n" ::: "memory");        // the four epilogue warps
+        const int ew = warp - 2;
+        const int n_tile = nb * P.bn;
+        const bool raw = P.part != nullptr;
+        const bool use_c = !raw && P.beta != 0.f;
+        // 8 rows per batch (r0, r0 + 4, ..., r0 + 28): their C reads are all in flight before the first is consumed
+        for (int r0 = ew; r0 < TC_ROWS; r0 += 32) {
+            if (mb * TC_ROWS + r0 >= P.M) break;       // uniform per warp
+            for (int c = lane * 4; c < P.bn; c += 128) {
+                const int n = n_tile + c;
+                float4 t[8], cc[8];
+                float *dst[8];
+                bool fast[8];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 o = make_float4(P.alpha * v[j], P.alpha * v[j + 1], P.alpha * v[j + 2], P.alpha * v[j + 3]);
-                        if (P.beta != 0.f) {
-                            const float4 c = *reinterpret_cast<const float4 *>(dst + j);
-                            o.x = fmaf(P.beta, c.x, o.x); o.y = fmaf(P.beta, c.y, o.y);
-                            o.z = fmaf(P.beta, c.z, o.z); o.w = fmaf(P.beta, c.w, o.w);
+                for (int u = 0; u < 8; ++u) {
+                    const int r = r0 + 4 * u, m = mb * TC_ROWS + r;
+                    float *grow = raw ? P.part + ((size_t)blockIdx.z * P.M + m) * P.N : P.C + (int64_t)m * P.ldc;
+                    dst[u] = grow + n;
+                    const bool live = m < P.M && n < P.N;
+                    fast[u] = live && n + 4 <= P.N && ((reinterpret_cast<uintptr_t>(dst[u]) & 15) == 0);
+                    if (!live) dst[u] = nullptr;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(t[u].x), "=f"(t[u].y), "=f"(t[u].z), "=f"(t[u].w)
+                                 : "r"(tile0 + 4u * (unsigned)(r * pitch + c)));
+                    cc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (fast[u] && use_c) cc[u] = *reinterpret_cast<const float4 *>(dst[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (dst[u] == nullptr) continue;
+                    if (fast[u]) {
+                        float4 o = t[u];
+                        if (!raw) {
+                            o.x = fmaf(P.beta, cc[u].x, P.alpha * o.x); o.y = fmaf(P.beta, cc[u].y, P.alpha * o.y);
+                            o.z = fmaf(P.beta, cc[u].z, P.alpha * o.z); o.w = fmaf(P.beta, cc[u].w, P.alpha * o.w);
                         }
-                        *reinterpret_cast<float4 *>(dst + j) = o;
-                    }
-                } else {
+                        *reinterpret_cast<float4 *>(dst[u]) = o;
+                    } else {
+                        const float e[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (n0 + j >= P.N) continue;
-                        float o = P.alpha * v[j];
-                        if (P.beta != 0.f) o = fmaf(P.beta, dst[j], o);
-                        dst[j] = o;
+                        for (int w = 0; w < 4; ++w) {
+                            if (n + w >= P.N) continue;
+                            float o = e[w];
+                            if (!raw) {
+                                o *= P.alpha;
+                                if (P.beta != 0.f) o = fmaf(P.beta, dst[u][w], o);
+                            }
+                            dst[u][w] = o;
+                        }
                     }
                 }
             }
@@ -358,7 +416,7 @@ tc_gemm_kernel(TcGemmParams P)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc_tmem_dealloc(tmem, TC_TMEM_COLS);
+    if (warp == 1) tc_tmem_dealloc(tmem, P.tmem_cols);
 }
 
 }  // namespace modl

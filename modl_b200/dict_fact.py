@@ -192,8 +192,13 @@ class DictFact(CodingMixin, BaseEstimator):
     """Stochastic-subsampled online matrix factorisation [ref: dict_fact.py:127-250].
 
     Parameters are those of the reference (see its docstring, :154-222).  `n_threads` is
-    accepted and ignored.  One extra keyword: `device` (torch device or index, default: the
-    current CUDA device).
+    accepted and ignored.  Two extra keywords: `device` (torch device or index, default: the
+    current CUDA device) and `async_host_copy` (default False).  With `async_host_copy=True`,
+    `partial_fit` on PINNED host rows returns as soon as the copies and kernels are enqueued --
+    the usual contract of an asynchronous pinned-memory copy: the caller must leave those rows
+    untouched until `synchronize()` (or any later read of a fitted attribute, which
+    synchronises) -- so that the copy of the next batch overlaps the kernels of this one even
+    when every call carries a single batch.
     """
 
     code_ = _DeviceArray("code_")
@@ -208,7 +213,7 @@ class DictFact(CodingMixin, BaseEstimator):
                  G_agg='masked', optimizer='variational', dict_init=None, code_alpha=1, code_l1_ratio=1,
                  comp_l1_ratio=0, step_size=1, tol=1e-2, max_iter=100, code_pos=False, comp_pos=False,
                  random_state=None, n_epochs=1, n_components=10, batch_size=10, verbose=0, callback=None,
-                 n_threads=1, rand_size=True, replacement=True, device=None):
+                 n_threads=1, rand_size=True, replacement=True, device=None, async_host_copy=False):
         self.batch_size = batch_size
         self.learning_rate = learning_rate
         self.sample_learning_rate = sample_learning_rate
@@ -230,6 +235,7 @@ class DictFact(CodingMixin, BaseEstimator):
         self.rand_size = rand_size
         self.replacement = replacement
         self.device = device
+        self.async_host_copy = async_host_copy
 
     # ------------------------------------------------------------------ device views
     code_dev = property(lambda self: self.__dict__.get("_d_code_"))
@@ -356,10 +362,18 @@ class DictFact(CodingMixin, BaseEstimator):
             self._single_batch_fit(dst, get_sub_slice(sample_indices, batch))
             pipe["done"][slot].record(stream)
             pipe["n"] = n + 1
-        if pinned:
+        if pinned and not getattr(self, "async_host_copy", False):
             # the caller may reuse its buffer once the copies have read it
             for ev in pipe["copied"]:
                 ev.synchronize()
+
+    def synchronize(self):
+        """Block until every enqueued copy and kernel of this estimator has finished."""
+        pipe = self.__dict__.get("_pipeline")
+        if pipe is not None:
+            pipe["copy_stream"].synchronize()
+        torch.cuda.current_stream(self._device).synchronize()
+        return self
 
     def set_params(self, **params):
         """[ref: dict_fact.py:339-357] -- including its quirk: only a switch to G_agg='full' is
