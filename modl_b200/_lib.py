@@ -29,10 +29,10 @@ class StepParams(C.Structure):
         ("max_iter", ci), ("code_pos", ci), ("comp_pos", ci), ("Dx_agg", ci), ("G_agg", ci),
         ("optimizer_sgd", ci),
         ("sweeps", vp),
-        ("phases", ci), ("global_batch", i64), ("stats_inc", vp),
+        ("phases", ci), ("global_batch", i64), ("stats_inc", vp), ("inc_sub", vp),
     ]
 
-PHASE_CODE, PHASE_STATS, PHASE_APPLY, PHASE_DICT = 1, 2, 4, 8
+PHASE_CODE, PHASE_STATS, PHASE_APPLY, PHASE_DICT, PHASE_APPLY_SUB, PHASE_APPLY_B = 1, 2, 4, 8, 16, 32
 
 
 class ModlError(RuntimeError):

@@ -243,7 +243,7 @@ template <typename T>
 static int update_dict_impl(modl_ctx *ctx, T *components, int64_t ldd, const T *B, int64_t ldb, const T *C,
                             T *comp_norm, T *G_full, const int64_t *subset, int64_t s, const int64_t *h_order,
                             int64_t k, int64_t p, T comp_l1_ratio, int comp_pos, int mode, double w,
-                            double step_size, T *Dpanel, bool panel_ready, cudaStream_t st)
+                            double step_size, T *Dpanel, bool panel_ready, cudaStream_t st, bool bpanel_ready = false)
 {
     MODL_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (variational) or 1 (sgd)");
     if (k <= 0) return MODL_OK;
@@ -252,7 +252,8 @@ static int update_dict_impl(modl_ctx *ctx, T *components, int64_t ldd, const T *
     prof_mark(ctx, st, MODL_PROF_DICT_PREP);
     MODL_TRY(ws<T>(ctx, WS_PANEL_B, (size_t)(k * lds), &Bp));
     if (!panel_ready) MODL_TRY(gather_cols<T>(ctx, components, ldd, k, p, subset, s, Dpanel, lds, nullptr, st));
-    MODL_TRY(gather_cols<T>(ctx, B, ldb, k, p, subset, s, Bp, lds, nullptr, st));   // gradient_[:, subset] = B_[:, subset]
+    if (!bpanel_ready)
+        MODL_TRY(gather_cols<T>(ctx, B, ldb, k, p, subset, s, Bp, lds, nullptr, st));   // gradient_[:, subset] = B_[:, subset]
     const bool small_subset = (double)s < (double)p / 2.;
     if (G_full && small_subset && s > 0)        // G_ -= D_sub D_sub^T   [ref: :667-668]
         MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, k, k, s, T(-1), Dpanel, lds, Dpanel, lds, T(1), G_full, k, st));
@@ -502,6 +503,18 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     const T r = (T)q->reduction;
     const int phases = q->phases ? q->phases : (MODL_PHASE_CODE | MODL_PHASE_STATS | MODL_PHASE_APPLY | MODL_PHASE_DICT);
     T *inc = static_cast<T *>(q->stats_inc);
+    T *inc_sub = static_cast<T *>(q->inc_sub);
+    if (phases == MODL_PHASE_APPLY_B) {
+        // B_ = (1-w) B_ + all-reduced increments; touches no workspace, so it may run on a side stream
+        MODL_REQUIRE(inc != nullptr, "APPLY_B without stats_inc");
+        const T keep = q->optimizer_sgd ? T(0) : (T)(1.0 - q->w);
+        xpby_kernel<T><<<grid_for(ctx, ceil_div(k * p, 256), 8), 256, 0, st>>>(static_cast<T *>(q->B), inc + k * k, k * p, keep);
+        MODL_LAUNCH_CHECK(ctx);
+        ctx->prof_n = 0;
+        return MODL_OK;
+    }
+    MODL_REQUIRE(!(phases & MODL_PHASE_APPLY_B), "APPLY_B runs in a call of its own");
+    MODL_REQUIRE(!(phases & MODL_PHASE_APPLY_SUB) || inc_sub, "APPLY_SUB without inc_sub");
     MODL_REQUIRE(!(phases & MODL_PHASE_STATS) || (phases & MODL_PHASE_CODE), "STATS phase needs CODE in the same call");
     MODL_REQUIRE(inc != nullptr || q->phases == 0 || !(phases & MODL_PHASE_APPLY) || (phases & MODL_PHASE_STATS),
                  "APPLY without stats_inc");
@@ -567,8 +580,14 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     if (phases & MODL_PHASE_STATS) {
         prof_mark(ctx, st, MODL_PROF_STATS);
         if (inc)
+        {
             MODL_TRY(update_stats_impl<T>(ctx, cb, nullptr, X, q->ldx, inc, inc + k * k, p, q->w, b, k, p, q->optimizer_sgd,
                                           st, q->global_batch, true));
+            if (inc_sub) {   // compact copy of what the dictionary update needs first: [C inc | B inc[:, subset]]
+                MODL_CUDA_TRY(cudaMemcpyAsync(inc_sub, inc, sizeof(T) * (size_t)(k * k), cudaMemcpyDeviceToDevice, st));
+                MODL_TRY(gather_cols<T>(ctx, inc + k * k, p, k, p, d_subset, s, inc_sub + k * k, panel_ld(s), nullptr, st));
+            }
+        }
         else
             MODL_TRY(update_stats_impl<T>(ctx, cb, nullptr, X, q->ldx, static_cast<T *>(q->C), static_cast<T *>(q->B), p,
                                           q->w, b, k, p, q->optimizer_sgd, st, q->global_batch, false));
@@ -582,6 +601,21 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
         xpby_kernel<T><<<grid_for(ctx, ceil_div(k * p, 256), 8), 256, 0, st>>>(static_cast<T *>(q->B), inc + k * k, k * p, keep);
         MODL_LAUNCH_CHECK(ctx);
     }
+    if (phases & MODL_PHASE_APPLY_SUB) {
+        prof_mark(ctx, st, MODL_PROF_STATS);
+        const T keep = q->optimizer_sgd ? T(0) : (T)(1.0 - q->w);
+        const int64_t lds = panel_ld(s);
+        xpby_kernel<T><<<grid_for(ctx, ceil_div(k * k, 256), 4), 256, 0, st>>>(static_cast<T *>(q->C), inc_sub, k * k, keep);
+        MODL_LAUNCH_CHECK(ctx);
+        T *Bp = nullptr;
+        MODL_TRY(ws<T>(ctx, WS_PANEL_B, (size_t)(k * lds), &Bp));
+        if (s > 0) {
+            gather_axpby_kernel<T><<<grid_for(ctx, k, 16), 256, 0, st>>>(static_cast<const T *>(q->B), p, (int)k, d_subset, (int)s,
+                                                                          keep, inc_sub + k * k, lds, Bp, lds);
+            MODL_LAUNCH_CHECK(ctx);
+        }
+        ctx->panel_b_ready = 1;
+    }
     if (phases & MODL_PHASE_DICT) {
     // ---- _update_dict [ref: :650-715] ----
     T *Dpanel = panel_keep;
@@ -590,7 +624,8 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     MODL_TRY(update_dict_impl<T>(ctx, D, p, static_cast<const T *>(q->B), p, static_cast<const T *>(q->C),
                                  static_cast<T *>(q->comp_norm), q->G_agg == MODL_AGG_FULL ? static_cast<T *>(q->G_full) : (T *)nullptr,
                                  d_subset, s, q->h_order, k, p, (T)q->comp_l1_ratio, q->comp_pos, q->optimizer_sgd ? 1 : 0, q->w,
-                                 q->step_size, Dpanel, ready, st));
+                                 q->step_size, Dpanel, ready, st, ctx->panel_b_ready != 0));
+    ctx->panel_b_ready = 0;
     }   // MODL_PHASE_DICT
     if (ctx->prof_on && ctx->prof_n > 0) {
         cudaEventRecord(ctx->prof_ev[ctx->prof_n], st);

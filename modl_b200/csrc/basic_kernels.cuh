@@ -50,6 +50,22 @@ scatter_cols_kernel(const T *__restrict__ src, int64_t lds, int rows,
     }
 }
 
+// out[r, j] = keep * B[r, subset[j]] + inc[r, j]: the B_[:, subset] panel as it will be once the
+// all-reduced increments are folded in (same fma as xpby_kernel)   [ref: dict_fact.py:532, :559-566]
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_axpby_kernel(const T *__restrict__ B, int64_t ldb, int rows, const int64_t *__restrict__ subset, int s, T keep,
+                    const T *__restrict__ inc, int64_t ldi, T *__restrict__ out, int64_t ldo)
+{
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const T *row = B + (int64_t)r * ldb;
+        for (int j = threadIdx.x; j < s; j += blockDim.x) {
+            const T x = inc[(int64_t)r * ldi + j];
+            out[(int64_t)r * ldo + j] = (keep != T(0)) ? fma(keep, row[subset[j]], x) : x;
+        }
+    }
+}
+
 // dst[ii, :] = src[indices[ii], :]
 template <typename T>
 __global__ void gather_rows_kernel(const T *__restrict__ src, int64_t ld, const int64_t *__restrict__ indices,

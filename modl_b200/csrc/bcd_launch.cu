@@ -4,6 +4,9 @@
 #include "bcd_pilot.cuh"
 #include "launch.h"
 
+#include <mutex>
+#include <vector>
+
 namespace modl {
 
 // ---------------------------------------------------------------------------------------
@@ -69,6 +72,20 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
                 if (need > budget) continue;
                 const void *fn = pilot == 2 ? (const void *)bcd_block_kernel<T>
                                  : pilot ? pilot_kernel_for<T>((int)(ncp / 32), l1_ratio != T(0)) : (const void *)kern;
+                // (kernel, cluster size, shared memory) combinations already validated on this device: skip the
+                // attribute and occupancy queries (tens of microseconds of host time per step)
+                struct Seen { const void *fn; int cs; size_t need; int device; };
+                static std::vector<Seen> seen;
+                static std::mutex seen_mu;
+                bool known = false;
+                {
+                    std::lock_guard<std::mutex> lk(seen_mu);
+                    for (const Seen &e : seen) known = known || (e.fn == fn && e.cs == cs && e.need >= need && e.device == ctx->device);
+                }
+                if (known) {
+                    nblk = cs; use_cluster = 1; d_in_smem = 1; cols = c; smem = need; use_pilot = pilot;
+                    continue;
+                }
                 if (cs > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
                     cudaGetLastError();
                     continue;
@@ -90,6 +107,10 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
                     continue;
                 }
                 nblk = cs; use_cluster = 1; d_in_smem = 1; cols = c; smem = need; use_pilot = pilot;
+                {
+                    std::lock_guard<std::mutex> lk(seen_mu);
+                    seen.push_back(Seen{fn, cs, need, ctx->device});
+                }
             }
         }
     }

@@ -21,7 +21,11 @@ static int cd_launch_inst(modl_ctx *ctx, const T *G, int64_t g_stride, const T *
         if (warps > 16) warps = 16;
         grid = (int)ceil_div(b, warps);
         if (grid > ctx->sm_count) grid = ctx->sm_count;
-        MODL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static bool configured = false;     // per instantiation; the attribute is per function, not per call
+        if (!configured) {
+            MODL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
         // tile-packed lower triangle of G in global memory, pulled by TMA bulk copies
         T *packed = nullptr;
         MODL_TRY(ws<T>(ctx, WS_GPACK, cd_packed_elems(TILES), &packed));

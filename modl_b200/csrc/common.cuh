@@ -92,6 +92,7 @@ struct modl_ctx {
     int opt_bcd_block = 0;        // experimental: blocked dictionary update (deferred projection scalars, bcd_block.cuh)
     int opt_bcd_timing = 0;       // debug: record clock64 stamps inside the dictionary update
     int bcd_timing_k = 0;
+    int panel_b_ready = 0;        // MODL_PHASE_APPLY_SUB left (1-w) B_[:, subset] + increments in WS_PANEL_B
     // optional per-phase device timing of the fused step (modl_ctx_profile)
     int prof_on = 0;
     int prof_n = 0;                       // marks recorded in the current step

@@ -10,7 +10,10 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/modl_b200.h"
@@ -314,9 +317,78 @@ private:
 }  // namespace
 
 struct modl_rng { Mt19937Stream impl; explicit modl_rng(uint64_t s) : impl(s) {} };
+// The sampler stream does not depend on the data, so the NEXT subset (10^4 Mersenne-twister draws at
+// the benchmark shape, ~0.1 ms) is drawn by a helper thread on a COPY of the state while the caller
+// launches the kernels of the current step.  yield_subset() adopts the copy when it was drawn with
+// the same `reduction`, otherwise drops it and draws from the untouched original: the integer
+// stream handed out is exactly the sequential one.
 struct modl_sampler {
     FeatureSampler impl;
-    modl_sampler(int64_t r, bool rs, bool rp, uint64_t s) : impl(r, rs, rp, s) {}
+    int64_t range;
+    // look-ahead state (guarded by mu)
+    FeatureSampler ahead;
+    std::vector<int64_t> ahead_out;
+    int64_t ahead_len = 0;
+    double ahead_reduction = 0;
+    bool job = false, ready = false, stop = false, started = false;
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+
+    modl_sampler(int64_t r, bool rs, bool rp, uint64_t s)
+        : impl(r, rs, rp, s), range(r), ahead(impl), ahead_out(static_cast<size_t>(r > 0 ? r : 1)) {}
+
+    ~modl_sampler() {
+        if (started) {
+            { std::lock_guard<std::mutex> lk(mu); stop = true; }
+            cv.notify_all();
+            worker.join();
+        }
+    }
+
+    void run() {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv.wait(lk, [&] { return job || stop; });
+            if (stop) return;
+            job = false;
+            const double red = ahead_reduction;
+            lk.unlock();
+            ahead = impl;                                   // the caller does not touch impl until it has waited for us
+            const int64_t len = ahead.draw(red, ahead_out.data());
+            lk.lock();
+            ahead_len = len;
+            ready = true;
+            cv.notify_all();
+        }
+    }
+
+    void start_ahead(double reduction) {
+        if (!started) {
+            started = true;
+            worker = std::thread([this] { run(); });
+        }
+        { std::lock_guard<std::mutex> lk(mu); ahead_reduction = reduction; ready = false; job = true; }
+        cv.notify_all();
+    }
+
+    int64_t yield(double reduction, int64_t *out) {
+        int64_t len = -1;
+        if (started) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return ready; });            // a look-ahead is always pending once started
+            if (ahead_reduction == reduction) {
+                len = ahead_len;
+                std::memcpy(out, ahead_out.data(), sizeof(int64_t) * static_cast<size_t>(len));
+                std::swap(impl, ahead);                     // commit: the copy becomes the state
+            }
+        }
+        if (len < 0) len = impl.draw(reduction, out);
+        if (lookahead) start_ahead(reduction);
+        return len;
+    }
+
+    bool lookahead = true;
 };
 
 extern "C" {
@@ -348,11 +420,16 @@ void modl_rs_shuffle_with_trace(modl_rng *rs, int64_t n, int64_t *h_swap, int64_
 
 modl_sampler *modl_sampler_create(int64_t range, int rand_size, int replacement, uint64_t seed) {
     if (range < 0) return nullptr;
-    return new (std::nothrow) modl_sampler(range, rand_size != 0, replacement != 0, seed);
+    modl_sampler *s = new (std::nothrow) modl_sampler(range, rand_size != 0, replacement != 0, seed);
+    if (s) {
+        const char *e = std::getenv("MODL_SAMPLER_LOOKAHEAD");
+        if (e && std::atoi(e) == 0) s->lookahead = false;
+    }
+    return s;
 }
 void modl_sampler_destroy(modl_sampler *s) { delete s; }
 int64_t modl_sampler_yield_subset(modl_sampler *s, double reduction, int64_t *h_out) {
-    return s->impl.draw(reduction, h_out);
+    return s->yield(reduction, h_out);
 }
 
 double modl_batch_weight(int64_t count, int64_t batch_size, double learning_rate, double offset) {

@@ -60,6 +60,9 @@ class _DeviceArray(object):
         t = obj.__dict__.get(self.slot)
         if t is None:
             raise AttributeError(self.name)
+        settle = getattr(obj, "_settle", None)
+        if settle is not None:
+            settle()                # work enqueued on side streams lands before the state is read
         return t.detach().cpu().numpy()
 
     def __set__(self, obj, value):
@@ -169,7 +172,7 @@ class CodingMixin(TransformerMixin):
     def __getstate__(self):
         state = {}
         for key, val in self.__dict__.items():
-            if key in ("_pipeline", "_time_events"):
+            if key in ("_pipeline", "_time_events", "_keepalive", "_ovl", "_prm", "_step_fn"):
                 continue
             if isinstance(val, torch.Tensor):
                 state[key] = ("__tensor__", val.detach().cpu().numpy())
@@ -508,9 +511,9 @@ class DictFact(CodingMixin, BaseEstimator):
             w_sample = np.power(this_n_iter, -self.sample_learning_rate).astype(self._np_dtype)   # [ref: :513]
         return subset, sample_indices, w, order, w_sample
 
-    def _launch_step(self, X, sample_indices, subset, order, w, w_sample, phases=0, stats_inc=None,
-                     global_batch=0):
-        """One call into the C ABI (`modl_batch_fit_*`): all device work of the step."""
+    def _step_params(self, X, sample_indices, subset, order, w, w_sample, stats_inc=None, global_batch=0,
+                     inc_sub=None):
+        """Fill the C-ABI parameter block of one minibatch step (reused by every phase call of the step)."""
         dev = self._device
         D = self._d_components_
         k, p = D.shape
@@ -518,28 +521,44 @@ class DictFact(CodingMixin, BaseEstimator):
         if X.stride(1) != 1:
             X = X.contiguous()
         w_dev = torch.from_numpy(w_sample).to(dev) if w_sample is not None else None
-        idx_dev = torch.from_numpy(sample_indices).to(dev, non_blocking=True)
-        prm = _lib.StepParams()
-        prm.n_samples, prm.n_features, prm.n_components, prm.batch_size = self._d_code_.shape[0], p, k, b
+        itemsize = D.element_size()
+        n_state = self._d_code_.shape[0]
+        # contiguous ascending rows (the common case: `partial_fit(X)` / a slice of sample ids): address the
+        # rows of the per-sample state through a pointer offset instead of uploading an index vector
+        base = int(sample_indices[0]) if b > 0 else 0
+        contiguous = b > 0 and int(sample_indices[-1]) - base == b - 1 and (b < 3 or bool(
+            (np.diff(sample_indices) == 1).all()))
+        idx_dev = None
+        if not contiguous:
+            idx_dev = torch.from_numpy(sample_indices).to(dev, non_blocking=True)
+            base = 0
+        prm = self.__dict__.get("_prm")
+        if prm is None:
+            prm = self.__dict__["_prm"] = _lib.StepParams()
+        prm.n_samples, prm.n_features, prm.n_components, prm.batch_size = n_state - base, p, k, b
         prm.X, prm.ldx = X.data_ptr(), X.stride(0)
-        prm.indices = idx_dev.data_ptr()
+        prm.indices = idx_dev.data_ptr() if idx_dev is not None else None
         prm.h_subset, prm.subset_len = subset.ctypes.data, subset.shape[0]
         prm.h_order = order.ctypes.data
         prm.w_sample = w_dev.data_ptr() if w_dev is not None else None
         prm.w = w
-        prm.components, prm.code = D.data_ptr(), self._d_code_.data_ptr()
+        prm.components, prm.code = D.data_ptr(), self._d_code_.data_ptr() + base * k * itemsize
         prm.C, prm.B, prm.comp_norm = self._d_C_.data_ptr(), self._d_B_.data_ptr(), self._d_comp_norm_.data_ptr()
-        for name, slot in (("G_full", "_d_G_"), ("Dx_average", "_d_Dx_average_"), ("G_average", "_d_G_average_")):
-            t = self.__dict__.get(slot)
-            setattr(prm, name, t.data_ptr() if t is not None else None)
+        t = self.__dict__.get("_d_G_")
+        prm.G_full = t.data_ptr() if t is not None else None
+        t = self.__dict__.get("_d_Dx_average_")
+        prm.Dx_average = t.data_ptr() + base * k * itemsize if t is not None else None
+        t = self.__dict__.get("_d_G_average_")
+        prm.G_average = t.data_ptr() + base * k * k * itemsize if t is not None else None
         prm.reduction, prm.code_alpha = float(self.reduction), float(self.code_alpha)
         prm.code_l1_ratio, prm.comp_l1_ratio = float(self.code_l1_ratio), float(self.comp_l1_ratio)
         prm.tol, prm.step_size, prm.max_iter = float(self.tol), float(self.step_size), int(self.max_iter)
         prm.code_pos, prm.comp_pos = int(bool(self.code_pos)), int(bool(self.comp_pos))
         prm.Dx_agg, prm.G_agg = _lib.AGG[self.Dx_agg], _lib.AGG[self.G_agg]
         prm.optimizer_sgd = int(self.optimizer == 'sgd')
-        prm.phases, prm.global_batch = int(phases), int(global_batch)
+        prm.phases, prm.global_batch = 0, int(global_batch)
         prm.stats_inc = stats_inc.data_ptr() if stats_inc is not None else None
+        prm.inc_sub = inc_sub.data_ptr() if inc_sub is not None else None
         sw = self.__dict__.get("_d_sweeps")
         if self.__dict__.get("record_sweeps", False):
             if sw is None or sw.shape[0] < b:
@@ -547,10 +566,24 @@ class DictFact(CodingMixin, BaseEstimator):
             prm.sweeps = sw.data_ptr()
         else:
             prm.sweeps = None
-        fn = getattr(_lib.lib(), "modl_batch_fit_" + _lib.sfx_of(D.dtype))
-        _lib.check(fn(self._ctx().handle, C.byref(prm), stream_of(dev)))
-        # keep the small device inputs alive until the (asynchronous) step has consumed them
-        self.__dict__["_keepalive"] = (idx_dev, w_dev, X)
+        # keep the step's inputs alive until the (asynchronous) kernels have consumed them
+        self.__dict__.setdefault("_keepalive", []).append((idx_dev, w_dev, X, subset, order))
+        del self._keepalive[:-8]
+        return prm
+
+    def _run_phases(self, prm, phases=0, stream=None):
+        """One call into the C ABI (`modl_batch_fit_*`): the selected device phases of the step."""
+        prm.phases = int(phases)
+        fn = self.__dict__.get("_step_fn")
+        if fn is None:
+            fn = self.__dict__["_step_fn"] = getattr(_lib.lib(), "modl_batch_fit_" + _lib.sfx_of(self._d_components_.dtype))
+        st = stream_of(self._device) if stream is None else C.c_void_p(stream.cuda_stream)
+        _lib.check(fn(self._ctx().handle, C.byref(prm), st))
+
+    def _launch_step(self, X, sample_indices, subset, order, w, w_sample, phases=0, stats_inc=None,
+                     global_batch=0, inc_sub=None, stream=None):
+        prm = self._step_params(X, sample_indices, subset, order, w, w_sample, stats_inc, global_batch, inc_sub)
+        self._run_phases(prm, phases, stream)
 
     def _single_batch_fit(self, X, sample_indices):
         """One minibatch step; X is a (batch x n_features) CUDA tensor of the estimator dtype

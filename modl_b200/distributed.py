@@ -51,16 +51,20 @@ class ShardedStepMixin(object):
         b_local = X.shape[0]
         b_global = b_local * world          # equal shards: every rank passes the same row count
         subset, sample_indices, w, order, w_sample = self._host_bookkeeping(b_global, sample_indices)
-        inc = self._phase_code_and_increments(X, sample_indices, subset, order, w, w_sample, b_global)
-        if world > 1:
-            dist.all_reduce(inc, op=dist.ReduceOp.SUM, group=self.process_group)
-        self._phase_apply_and_dict(X, sample_indices, subset, order, w, w_sample, inc, b_global)
+        if world > 1 and getattr(self, "overlap_exchange", False) and hasattr(self, "_overlapped_step"):
+            self._overlapped_step(X, sample_indices, subset, order, w, w_sample, b_global)
+        else:
+            inc = self._phase_code_and_increments(X, sample_indices, subset, order, w, w_sample, b_global)
+            if world > 1:
+                dist.all_reduce(inc, op=dist.ReduceOp.SUM, group=self.process_group)
+            self._phase_apply_and_dict(X, sample_indices, subset, order, w, w_sample, inc, b_global)
         self.__dict__["last_subset_"] = subset
         self.__dict__["last_order_"] = order
 
     def check_replicas(self):
         """Debug helper: max abs difference of the dictionary across ranks (should be 0.0)."""
         world, _ = self._world()
+        self._settle()
         D = self.components_dev.clone()
         lo, hi = D.clone(), D.clone()
         if world > 1:
@@ -72,13 +76,80 @@ class ShardedStepMixin(object):
 class ShardedDictFact(ShardedStepMixin, DictFact):
     """DictFact whose minibatches are sharded over the ranks of a torch.distributed group."""
 
-    def __init__(self, process_group=None, **kwargs):
+    def __init__(self, process_group=None, overlap_exchange=True, **kwargs):
         DictFact.__init__(self, **kwargs)
         self.process_group = process_group
+        self.overlap_exchange = overlap_exchange
 
     @classmethod
     def _get_param_names(cls):
-        return sorted(set(DictFact._get_param_names()) | {"process_group"})
+        return sorted(set(DictFact._get_param_names()) | {"process_group", "overlap_exchange"})
+
+    # -- overlapped exchange ---------------------------------------------------------------------
+    # The dictionary update needs C_ and only the SUBSET columns of B_ (dict_fact.py:532), so the
+    # exchange is split: a small all-reduce of [C inc | B inc[:, subset]] (1.5 MB at the benchmark
+    # shape) on the compute stream, and the all-reduce of the full B increment (10 MB) plus its
+    # fold-in on a side stream with its own NCCL communicator, hidden behind the sequential
+    # dictionary update.
+    def _overlap_state(self):
+        st = self.__dict__.get("_ovl")
+        if st is None:
+            dev = self._device
+            ranks = dist.get_process_group_ranks(self.process_group) if self.process_group is not None else None
+            st = {"stream": torch.cuda.Stream(device=dev),
+                  "group": dist.new_group(ranks=ranks, backend="nccl"),   # collective: every rank creates it at its first step
+                  "ev_inc": torch.cuda.Event(), "ev_sub": torch.cuda.Event(), "ev_applied": torch.cuda.Event(),
+                  "pending": False}
+            self.__dict__["_ovl"] = st
+        return st
+
+    def _inc_sub_buffer(self, s):
+        D = self._d_components_
+        k = D.shape[0]
+        need = k * k + k * (4 * ((s + 3) // 4) if s > 0 else 4)
+        buf = self.__dict__.get("_d_inc_sub")
+        if buf is None or buf.numel() < need or buf.dtype != D.dtype:
+            buf = self.__dict__["_d_inc_sub"] = torch.zeros(need + need // 4, dtype=D.dtype, device=D.device)
+        return buf[:need]
+
+    def _overlapped_step(self, X, sample_indices, subset, order, w, w_sample, b_global):
+        st = self._overlap_state()
+        main = torch.cuda.current_stream(self._device)
+        side = st["stream"]
+        k = self._d_components_.shape[0]
+        if st["pending"]:
+            main.wait_event(st["ev_applied"])       # B_ and the increment buffer of the previous step are settled
+        inc = self._inc_buffer()
+        inc_sub = self._inc_sub_buffer(subset.shape[0])
+        prm = self._step_params(X, sample_indices, subset, order, w, w_sample, stats_inc=inc, global_batch=b_global,
+                                inc_sub=inc_sub)
+        self._run_phases(prm, _lib.PHASE_CODE | _lib.PHASE_STATS)
+        st["ev_inc"].record(main)
+        # side stream: the full B increment travels while the dictionary update runs
+        side.wait_event(st["ev_inc"])
+        with torch.cuda.stream(side):
+            dist.all_reduce(inc[k * k:], op=dist.ReduceOp.SUM, group=st["group"])
+        # compute stream: what the dictionary update needs
+        dist.all_reduce(inc_sub, op=dist.ReduceOp.SUM, group=self.process_group)
+        self._run_phases(prm, _lib.PHASE_APPLY_SUB)
+        st["ev_sub"].record(main)                   # B_[:, subset] has been read: B_ may now be rewritten
+        self._run_phases(prm, _lib.PHASE_DICT)
+        side.wait_event(st["ev_sub"])
+        self._run_phases(prm, _lib.PHASE_APPLY_B, stream=side)
+        st["ev_applied"].record(side)
+        st["pending"] = True
+
+    def _settle(self):
+        """Make the current stream wait for the side-stream fold-in of B_ (called before state reads)."""
+        st = self.__dict__.get("_ovl")
+        if st is not None and st["pending"]:
+            torch.cuda.current_stream(self._device).wait_event(st["ev_applied"])
+
+    def synchronize(self):
+        st = self.__dict__.get("_ovl")
+        if st is not None:
+            st["stream"].synchronize()
+        return DictFact.synchronize(self)
 
     def _inc_buffer(self):
         D = self._d_components_

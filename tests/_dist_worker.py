@@ -28,10 +28,12 @@ def main():
     A = rng.randn(n, k) * (rng.rand(n, k) < 0.3)
     X = (A @ D0 + 0.1 * rng.randn(n, p)).astype(np.float32)
     out = {}
-    for name, kw in (("lasso_l2", dict(code_l1_ratio=1., code_alpha=0.5, comp_l1_ratio=0.)),
-                     ("ridge_l1", dict(code_l1_ratio=0., code_alpha=0.1, comp_l1_ratio=1.))):
+    # overlap=True: split exchange (small all-reduce first, the full B increment on a side stream)
+    for name, kw, overlap in (("lasso_l2", dict(code_l1_ratio=1., code_alpha=0.5, comp_l1_ratio=0.), True),
+                              ("lasso_l2_plain", dict(code_l1_ratio=1., code_alpha=0.5, comp_l1_ratio=0.), False),
+                              ("ridge_l1", dict(code_l1_ratio=0., code_alpha=0.1, comp_l1_ratio=1.), True)):
         base = dict(n_components=k, reduction=4, random_state=0, **kw)
-        est = ShardedDictFact(batch_size=b_local, **base)
+        est = ShardedDictFact(batch_size=b_local, overlap_exchange=overlap, **base)
         est.prepare(n_samples=n, X=X[:k])
         for t in range(steps):
             lo = t * b_local * world + rank * b_local

@@ -133,3 +133,16 @@ def test_device_entry_points_fail_loudly_without_gpu():
     from modl_b200 import DictFact
     with pytest.raises(RuntimeError):
         DictFact(n_components=2).prepare(n_samples=4, n_features=3)
+
+
+def test_sampler_lookahead_keeps_the_stream(oracle):
+    """The helper thread draws the next subset speculatively on a copy of the state; changing
+    `reduction` between calls must discard the speculation without disturbing the stream."""
+    from modl_b200 import Sampler
+    reds = [4., 4., 8., 2., 2., 2., 5., 5., 3.]
+    for rand_size in (True, False):
+        for replacement in (True, False):
+            mine = Sampler(997, rand_size, replacement, 7)
+            ref = oracle.Sampler(997, rand_size, replacement, 7)
+            for r in reds:
+                np.testing.assert_array_equal(mine.yield_subset(r), ref.yield_subset(r))
