@@ -64,5 +64,36 @@ for f in sorted(os.listdir(src)):
 for f in ("bench.json", "bench_ref.json"):
     if os.path.exists(os.path.join(src, f)) and os.path.getsize(os.path.join(src, f)) > 0:
         shutil.copy(os.path.join(src, f), os.path.join(dst, tag + "_" + f))
+# per-phase DRAM traffic of one step (bytes), summed over the captured launches of the phase's kernels
+import json
+PHASE_OF = [("bcd_pilot", "dict_bcd"), ("bcd_block", "dict_bcd"), ("cd_regression", "code"), ("tc_pack_rows", "gather"),
+            ("tc_pack_cols", "stats"), ("tc_gemm", None)]
+traffic, gemm_seen = {}, 0
+for f in sorted(os.listdir(src)):
+    if not f.endswith(".raw.csv"):
+        continue
+    rows = list(csv.reader(open(os.path.join(src, f))))
+    if len(rows) < 3:
+        continue
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    if 'dram__bytes_read.sum' not in idx:
+        continue
+    for r in rows[2:]:
+        name = r[idx['Kernel Name']]
+        def val(n):
+            v, u = float(r[idx[n]].replace(',', '')), units[idx[n]]
+            return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
+        byt = val('dram__bytes_read.sum') + val('dram__bytes_write.sum')
+        for key, ph in PHASE_OF:
+            if key in name:
+                if key == "tc_gemm":      # launches of one step in order: [G;Dx], C_, B_
+                    ph = "gram" if gemm_seen % 3 == 0 else "stats"
+                    gemm_seen += 1
+                traffic[ph] = traffic.get(ph, 0) + byt
+                break
+if traffic:
+    traffic["_source"] = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, %s" % tag
+    json.dump(traffic, open(os.path.join(dst, "ncu_traffic.json"), "w"), indent=1)
 open(os.path.join(dst, tag + "_summary.md"), "w").write("\n".join(out) + "\n")
 print("wrote profiles/%s_summary.md" % tag)
