@@ -291,8 +291,14 @@ typedef struct modl_step_params {
     void *inc_sub;             /* device real[k*k + k*lds]                                */
 } modl_step_params;
 
+/* MODL_PHASE_STATS_SUB (same call as MODL_PHASE_CODE) computes ONLY what the dictionary update waits
+ * for, straight into inc_sub:  (w/batch) code^T code  and  (w/batch) code^T X[:, subset]  -- a k x s
+ * product instead of k x p.  MODL_PHASE_STATS_B (a call of its own, any stream) then produces the
+ * full-width statistic: B_ = (1-w) B_ + (w/batch) code^T X when stats_inc == NULL, or the raw
+ * increment into stats_inc (for the caller's all-reduce + MODL_PHASE_APPLY_B) otherwise.  Run on a
+ * second stream it hides the 2.6 GFLOP / 60 MB product behind the sequential dictionary update. */
 enum { MODL_PHASE_CODE = 1, MODL_PHASE_STATS = 2, MODL_PHASE_APPLY = 4, MODL_PHASE_DICT = 8,
-       MODL_PHASE_APPLY_SUB = 16, MODL_PHASE_APPLY_B = 32 };
+       MODL_PHASE_APPLY_SUB = 16, MODL_PHASE_APPLY_B = 32, MODL_PHASE_STATS_SUB = 64, MODL_PHASE_STATS_B = 128 };
 
 int modl_batch_fit_f32(modl_ctx *, const modl_step_params *prm, void *stream);
 int modl_batch_fit_f64(modl_ctx *, const modl_step_params *prm, void *stream);

@@ -33,6 +33,7 @@ class StepParams(C.Structure):
     ]
 
 PHASE_CODE, PHASE_STATS, PHASE_APPLY, PHASE_DICT, PHASE_APPLY_SUB, PHASE_APPLY_B = 1, 2, 4, 8, 16, 32
+PHASE_STATS_SUB, PHASE_STATS_B = 64, 128
 
 
 class ModlError(RuntimeError):

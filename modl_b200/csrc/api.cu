@@ -335,7 +335,7 @@ static int enet_scale_impl(modl_ctx *ctx, T *X, int64_t rows, int64_t n, int64_t
 // dictionary update works on.
 static int gram_dx_tc(modl_ctx *ctx, const float *D, int64_t ldd, const float *X, int64_t ldx, const int64_t *subset,
                       int64_t kd, int64_t k, int64_t b, int64_t p, float scale, float *G, float *Dx, float *xnorm2,
-                      float *plain_D, int64_t lds, cudaStream_t st)
+                      float *plain_D, int64_t lds, cudaStream_t st, float *plain_X = nullptr)
 {
     const bool want_dx = Dx != nullptr && b > 0;
     const int64_t rows = k + (want_dx ? b : 0);
@@ -344,7 +344,7 @@ static int gram_dx_tc(modl_ctx *ctx, const float *D, int64_t ldd, const float *X
     prof_mark(ctx, st, MODL_PROF_GATHER);
     MODL_TRY(tc_pack_rows(ctx, D, ldd, k, p, subset, kd, packed, 0, want_dx ? k : tc_rows_padded(k), plain_D, lds, nullptr, st));
     if (want_dx)
-        MODL_TRY(tc_pack_rows(ctx, X, ldx, b, p, subset, kd, packed, k, tc_rows_padded(k + b), nullptr, 0, xnorm2, st));
+        MODL_TRY(tc_pack_rows(ctx, X, ldx, b, p, subset, kd, packed, k, tc_rows_padded(k + b), plain_X, lds, xnorm2, st));
     else if (xnorm2 && b > 0)
         MODL_TRY(gather_cols<float>(ctx, X, ldx, b, p, nullptr, 0, (float *)nullptr, 0, xnorm2, st));
     prof_mark(ctx, st, MODL_PROF_GRAM);
@@ -394,7 +394,7 @@ static int gram_dx_impl(modl_ctx *ctx, const T *D, int64_t ldd, const T *X, int6
     if constexpr (std::is_same<T, float>::value) {
         if (use_tc<T>(ctx) && s > 0 && (G || (Dx && b > 0))) {
             if (panel_out) *panel_out = Dsub;
-            return gram_dx_tc(ctx, D, ldd, X, ldx, subset, s, k, b, p, scale, G, Dx, xnorm2, Dsub, lds, st);
+            return gram_dx_tc(ctx, D, ldd, X, ldx, subset, s, k, b, p, scale, G, Dx, xnorm2, Dsub, lds, st, Xsub);
         }
     }
     prof_mark(ctx, st, MODL_PROF_GATHER);
@@ -466,6 +466,51 @@ static int update_stats_impl(modl_ctx *ctx, const T *code, const int64_t *indice
     return MODL_OK;
 }
 
+// What the dictionary update waits for, and nothing else: inc_sub = a [code^T code | code^T X[:, subset]]
+// (k x k, then k x lds).  Xsub is the plain b x lds panel of X[:, subset].
+template <typename T>
+static int stats_sub_impl(modl_ctx *ctx, const T *cb, const T *Xsub, int64_t lds, int64_t s, T *inc_sub, T a, int64_t b,
+                          int64_t k, cudaStream_t st)
+{
+    if constexpr (std::is_same<T, float>::value) {
+        if (use_tc<T>(ctx)) {
+            float *codeP = nullptr, *XsP = nullptr;
+            MODL_TRY(ws<float>(ctx, WS_TC_CODE, tc_packed_elems(k, b), &codeP));
+            MODL_TRY(tc_pack_cols(ctx, cb, k, b, k, codeP, 128, st));
+            ctx->code_packed = 1;
+            MODL_TRY(tc_gemm(ctx, codeP, codeP, k, k, b, a, 0.f, inc_sub, k, 128, st));
+            if (s > 0) {
+                MODL_TRY(ws<float>(ctx, WS_TC_XS, tc_packed_elems(s, b), &XsP));
+                MODL_TRY(tc_pack_cols(ctx, Xsub, lds, b, s, XsP, 128, st));
+                MODL_TRY(tc_gemm(ctx, codeP, XsP, k, s, b, a, 0.f, inc_sub + k * k, lds, 128, st));
+            }
+            return MODL_OK;
+        }
+    }
+    MODL_TRY(gemm_simt<T>(ctx, A_MMAJOR, B_NMAJOR, k, k, b, a, cb, k, cb, k, T(0), inc_sub, k, st));
+    if (s > 0) MODL_TRY(gemm_simt<T>(ctx, A_MMAJOR, B_NMAJOR, k, s, b, a, cb, k, Xsub, lds, T(0), inc_sub + k * k, lds, st));
+    return MODL_OK;
+}
+
+// The full-width statistic on whatever stream the caller chose: out = be * out + a * code^T X  (k x p)
+template <typename T>
+static int stats_b_impl(modl_ctx *ctx, const T *cb, const T *X, int64_t ldx, T *out, int64_t ldo, T a, T be, int64_t b,
+                        int64_t k, int64_t p, cudaStream_t st)
+{
+    if constexpr (std::is_same<T, float>::value) {
+        if (use_tc<T>(ctx)) {
+            float *codeP = nullptr, *XP = nullptr;
+            MODL_TRY(ws<float>(ctx, WS_TC_CODE, tc_packed_elems(k, b), &codeP));
+            if (!ctx->code_packed) MODL_TRY(tc_pack_cols(ctx, cb, k, b, k, codeP, 128, st));
+            const int bn = tc_pick_bn(ctx, p, ceil_div(k, 128));
+            MODL_TRY(ws<float>(ctx, WS_TC_X, tc_packed_elems(p, b, bn), &XP));
+            MODL_TRY(tc_pack_cols(ctx, X, ldx, b, p, XP, bn, st));
+            return tc_gemm(ctx, codeP, XP, k, p, b, a, be, out, ldo, bn, st, WS_GEMM_PART2);
+        }
+    }
+    return gemm_simt<T>(ctx, A_MMAJOR, B_NMAJOR, k, p, b, a, cb, k, X, ldx, be, out, ldo, st, WS_GEMM_PART2);
+}
+
 template <typename T>
 static int update_dict_entry(modl_ctx *ctx, T *components, int64_t ldd, const T *B, int64_t ldb, const T *C, T *comp_norm,
                              T *G_full, const int64_t *subset, int64_t s, const int64_t *h_order, int64_t k, int64_t p,
@@ -513,7 +558,20 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
         ctx->prof_n = 0;
         return MODL_OK;
     }
-    MODL_REQUIRE(!(phases & MODL_PHASE_APPLY_B), "APPLY_B runs in a call of its own");
+    if (phases == MODL_PHASE_STATS_B) {
+        // full-width B statistic from the batch code left in the workspace by this step's CODE phase
+        MODL_REQUIRE(ctx->slot_ptr[WS_CODE_BATCH] != nullptr, "STATS_B before any CODE phase");
+        const double bt = (double)(q->global_batch > 0 ? q->global_batch : b);
+        const T av = q->optimizer_sgd ? (T)(1.0 / bt) : (T)(q->w / bt);
+        const T *cbp = static_cast<const T *>(ctx->slot_ptr[WS_CODE_BATCH]);
+        ctx->prof_n = 0;
+        if (inc) return stats_b_impl<T>(ctx, cbp, X, q->ldx, inc + k * k, p, av, T(0), b, k, p, st);
+        const T keep = q->optimizer_sgd ? T(0) : (T)(1.0 - q->w);
+        return stats_b_impl<T>(ctx, cbp, X, q->ldx, static_cast<T *>(q->B), p, av, keep, b, k, p, st);
+    }
+    MODL_REQUIRE(!(phases & (MODL_PHASE_APPLY_B | MODL_PHASE_STATS_B)), "APPLY_B / STATS_B run in calls of their own");
+    MODL_REQUIRE(!(phases & MODL_PHASE_STATS_SUB) || ((phases & MODL_PHASE_CODE) && inc_sub && !(phases & MODL_PHASE_STATS)),
+                 "STATS_SUB needs CODE in the same call, inc_sub, and excludes STATS");
     MODL_REQUIRE(!(phases & MODL_PHASE_APPLY_SUB) || inc_sub, "APPLY_SUB without inc_sub");
     MODL_REQUIRE(!(phases & MODL_PHASE_STATS) || (phases & MODL_PHASE_CODE), "STATS phase needs CODE in the same call");
     MODL_REQUIRE(inc != nullptr || q->phases == 0 || !(phases & MODL_PHASE_APPLY) || (phases & MODL_PHASE_STATS),
@@ -576,6 +634,19 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
                            (T)q->code_alpha, q->code_pos, (T)q->tol, q->max_iter, q->sweeps, st));
 
     panel_keep = panel;
+    ctx->code_packed = 0;
+    if (phases & MODL_PHASE_STATS_SUB) {
+        prof_mark(ctx, st, MODL_PROF_STATS);
+        const int64_t lds = panel_ld(s);
+        T *pn = nullptr;
+        MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)((k + b) * lds), &pn));
+        T *Xsub = pn + k * lds;
+        if (!(need_sub && dx_sub && s > 0))       // X[:, subset] was not gathered by the code phase (Dx_agg == 'full')
+            MODL_TRY(gather_cols<T>(ctx, X, q->ldx, b, p, d_subset, s, Xsub, lds, nullptr, st));
+        const double bt = (double)(q->global_batch > 0 ? q->global_batch : b);
+        const T av = q->optimizer_sgd ? (T)(1.0 / bt) : (T)(q->w / bt);
+        MODL_TRY(stats_sub_impl<T>(ctx, cb, Xsub, lds, s, inc_sub, av, b, k, st));
+    }
     // ---- _update_C / _update_B [ref: :559-575] ----
     if (phases & MODL_PHASE_STATS) {
         prof_mark(ctx, st, MODL_PROF_STATS);

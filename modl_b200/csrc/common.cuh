@@ -69,6 +69,8 @@ enum WsSlot {
     WS_TC_CODE,      // packed split panel code^T
     WS_TC_X,         // packed split panel X^T
     WS_GDX,          // [G ; Dx] of the tensor-core path, (k + b) x k
+    WS_TC_XS,        // packed split panel X[:, subset]^T
+    WS_GEMM_PART2,   // split-K partials of the side-stream statistics product
     WS_MISC,         // small scalars
     WS_INFO,         // int status flags
     WS_COUNT
@@ -92,6 +94,7 @@ struct modl_ctx {
     int opt_bcd_block = 0;        // experimental: blocked dictionary update (deferred projection scalars, bcd_block.cuh)
     int opt_bcd_timing = 0;       // debug: record clock64 stamps inside the dictionary update
     int bcd_timing_k = 0;
+    int code_packed = 0;          // WS_TC_CODE holds the packed code^T of the current step
     int panel_b_ready = 0;        // MODL_PHASE_APPLY_SUB left (1-w) B_[:, subset] + increments in WS_PANEL_B
     // optional per-phase device timing of the fused step (modl_ctx_profile)
     int prof_on = 0;

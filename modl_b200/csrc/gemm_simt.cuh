@@ -131,7 +131,7 @@ __global__ void gemm_splitk_reduce_kernel(int M, int N, int splits, T alpha, con
 
 template <typename T>
 int gemm_simt(modl_ctx *ctx, int la, int lb, int64_t M, int64_t N, int64_t K, T alpha, const T *A,
-              int64_t lda, const T *B, int64_t ldb, T beta, T *C, int64_t ldc, cudaStream_t st)
+              int64_t lda, const T *B, int64_t ldb, T beta, T *C, int64_t ldc, cudaStream_t st, WsSlot part_slot)
 {
     if (M <= 0 || N <= 0) return MODL_OK;
     const int64_t tiles = ceil_div(M, GEMM_BM) * ceil_div(N, GEMM_BN);
@@ -146,7 +146,7 @@ int gemm_simt(modl_ctx *ctx, int la, int lb, int64_t M, int64_t N, int64_t K, T 
     int64_t k_chunk = round_up(ceil_div(K > 0 ? K : 1, splits), GEMM_BK);
     splits = K > 0 ? ceil_div(K, k_chunk) : 1;
     T *part = nullptr;
-    if (splits > 1) MODL_TRY(ws<T>(ctx, WS_GEMM_PART, (size_t)(splits * M * N), &part));
+    if (splits > 1) MODL_TRY(ws<T>(ctx, part_slot, (size_t)(splits * M * N), &part));
     dim3 grid((unsigned)ceil_div(N, GEMM_BN), (unsigned)ceil_div(M, GEMM_BM), (unsigned)splits);
 #define MODL_GEMM_LAUNCH(LA_, LB_)                                                              \
     gemm_simt_kernel<T, LA_, LB_><<<grid, GEMM_THREADS, 0, st>>>(                               \

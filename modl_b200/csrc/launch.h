@@ -21,7 +21,8 @@ static inline int grid_for(modl_ctx *ctx, int64_t work, int per_sm = 8)
 // gemm_simt.cu
 template <typename T>
 int gemm_simt(modl_ctx *ctx, int la, int lb, int64_t M, int64_t N, int64_t K, T alpha, const T *A,
-              int64_t lda, const T *B, int64_t ldb, T beta, T *C, int64_t ldc, cudaStream_t st);
+              int64_t lda, const T *B, int64_t ldb, T beta, T *C, int64_t ldc, cudaStream_t st,
+              WsSlot part_slot = WS_GEMM_PART);
 
 // cd_launch.cu
 template <typename T>
@@ -50,6 +51,6 @@ int tc_pack_cols(modl_ctx *ctx, const float *src, int64_t ld, int64_t kd, int64_
                  int rows_per_block, cudaStream_t st);
 // bn = accumulator tile width = rows per block of the packed B operand (multiple of 16, <= 256)
 int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M, int64_t N, int64_t Kd, float alpha,
-            float beta, float *C, int64_t ldc, int bn, cudaStream_t st);
+            float beta, float *C, int64_t ldc, int bn, cudaStream_t st, WsSlot part_slot = WS_GEMM_PART);
 
 }  // namespace modl

@@ -47,7 +47,7 @@ int tc_pack_cols(modl_ctx *ctx, const float *src, int64_t ld, int64_t kd, int64_
 }
 
 int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M, int64_t N, int64_t Kd, float alpha,
-            float beta, float *C, int64_t ldc, int bn, cudaStream_t st)
+            float beta, float *C, int64_t ldc, int bn, cudaStream_t st, WsSlot part_slot)
 {
     if (M <= 0 || N <= 0) return MODL_OK;
     MODL_REQUIRE(Kd >= 1, "tc_gemm needs a non-empty contraction");
@@ -79,7 +79,7 @@ int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M
     P.kb_per_split = (int)ceil_div(P.nkb, splits);
     splits = ceil_div(P.nkb, P.kb_per_split);
     P.part = nullptr;
-    if (splits > 1) MODL_TRY(ws<float>(ctx, WS_GEMM_PART, (size_t)(splits * M * N), &P.part));
+    if (splits > 1) MODL_TRY(ws<float>(ctx, part_slot, (size_t)(splits * M * N), &P.part));
     dim3 grid((unsigned)tc_row_blocks(N, bn), (unsigned)tc_row_blocks(M), (unsigned)splits);
     tc_gemm_kernel<<<grid, TC_THREADS, smem_bytes, st>>>(P);
     MODL_LAUNCH_CHECK(ctx);

@@ -64,7 +64,6 @@ class ShardedStepMixin(object):
     def check_replicas(self):
         """Debug helper: max abs difference of the dictionary across ranks (should be 0.0)."""
         world, _ = self._world()
-        self._settle()
         D = self.components_dev.clone()
         lo, hi = D.clone(), D.clone()
         if world > 1:
@@ -92,64 +91,36 @@ class ShardedDictFact(ShardedStepMixin, DictFact):
     # fold-in on a side stream with its own NCCL communicator, hidden behind the sequential
     # dictionary update.
     def _overlap_state(self):
-        st = self.__dict__.get("_ovl")
-        if st is None:
-            dev = self._device
+        st = self._side_state()
+        if "group" not in st:
             ranks = dist.get_process_group_ranks(self.process_group) if self.process_group is not None else None
-            st = {"stream": torch.cuda.Stream(device=dev),
-                  "group": dist.new_group(ranks=ranks, backend="nccl"),   # collective: every rank creates it at its first step
-                  "ev_inc": torch.cuda.Event(), "ev_sub": torch.cuda.Event(), "ev_applied": torch.cuda.Event(),
-                  "pending": False}
-            self.__dict__["_ovl"] = st
+            st["group"] = dist.new_group(ranks=ranks, backend="nccl")   # collective: every rank creates it at its first step
         return st
-
-    def _inc_sub_buffer(self, s):
-        D = self._d_components_
-        k = D.shape[0]
-        need = k * k + k * (4 * ((s + 3) // 4) if s > 0 else 4)
-        buf = self.__dict__.get("_d_inc_sub")
-        if buf is None or buf.numel() < need or buf.dtype != D.dtype:
-            buf = self.__dict__["_d_inc_sub"] = torch.zeros(need + need // 4, dtype=D.dtype, device=D.device)
-        return buf[:need]
 
     def _overlapped_step(self, X, sample_indices, subset, order, w, w_sample, b_global):
         st = self._overlap_state()
-        main = torch.cuda.current_stream(self._device)
-        side = st["stream"]
+        main, side = torch.cuda.current_stream(self._device), st["stream"]
         k = self._d_components_.shape[0]
-        if st["pending"]:
-            main.wait_event(st["ev_applied"])       # B_ and the increment buffer of the previous step are settled
         inc = self._inc_buffer()
         inc_sub = self._inc_sub_buffer(subset.shape[0])
         prm = self._step_params(X, sample_indices, subset, order, w, w_sample, stats_inc=inc, global_batch=b_global,
                                 inc_sub=inc_sub)
-        self._run_phases(prm, _lib.PHASE_CODE | _lib.PHASE_STATS)
-        st["ev_inc"].record(main)
-        # side stream: the full B increment travels while the dictionary update runs
-        side.wait_event(st["ev_inc"])
-        with torch.cuda.stream(side):
-            dist.all_reduce(inc[k * k:], op=dist.ReduceOp.SUM, group=st["group"])
-        # compute stream: what the dictionary update needs
+        # compute stream: codes, then this rank's share of [C inc | B inc[:, subset]] only
+        self._run_phases(prm, _lib.PHASE_CODE | _lib.PHASE_STATS_SUB)
+        st["ev_code"].record(main)
         dist.all_reduce(inc_sub, op=dist.ReduceOp.SUM, group=self.process_group)
         self._run_phases(prm, _lib.PHASE_APPLY_SUB)
         st["ev_sub"].record(main)                   # B_[:, subset] has been read: B_ may now be rewritten
         self._run_phases(prm, _lib.PHASE_DICT)
+        # side stream: the full-width product, its all-reduce and its fold-in, behind the dictionary update
+        side.wait_event(st["ev_code"])
+        self._run_phases(prm, _lib.PHASE_STATS_B, stream=side)
+        with torch.cuda.stream(side):
+            dist.all_reduce(inc[k * k:], op=dist.ReduceOp.SUM, group=st["group"])
         side.wait_event(st["ev_sub"])
         self._run_phases(prm, _lib.PHASE_APPLY_B, stream=side)
         st["ev_applied"].record(side)
-        st["pending"] = True
-
-    def _settle(self):
-        """Make the current stream wait for the side-stream fold-in of B_ (called before state reads)."""
-        st = self.__dict__.get("_ovl")
-        if st is not None and st["pending"]:
-            torch.cuda.current_stream(self._device).wait_event(st["ev_applied"])
-
-    def synchronize(self):
-        st = self.__dict__.get("_ovl")
-        if st is not None:
-            st["stream"].synchronize()
-        return DictFact.synchronize(self)
+        main.wait_event(st["ev_applied"])
 
     def _inc_buffer(self):
         D = self._d_components_

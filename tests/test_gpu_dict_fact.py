@@ -255,3 +255,38 @@ def test_coder_matches_dictfact_transform():
     est = DictFact(n_components=10, batch_size=50, reduction=2, random_state=0, code_alpha=0.1).fit(X)
     coder = Coder(est.components_, code_alpha=0.1)
     np.testing.assert_array_equal(coder.transform(X), est.transform(X))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(Dx_agg='full', G_agg='full'), dict(Dx_agg='average', G_agg='average'),
+                                dict(code_l1_ratio=0., comp_l1_ratio=1.), dict(optimizer='sgd', step_size=0.1)])
+def test_overlapped_statistics_equal_the_fused_step(kw):
+    """With overlap_stats the step computes the k x s slice of the B_ update first and runs the full
+    k x p product on a second stream behind the dictionary update (the phases the sharded estimator
+    uses to hide its all-reduce); it must reach the same state as the single fused call (same
+    mathematics, different GEMM splits: 1e-5)."""
+    from modl_b200 import DictFact
+    X = _planted(768, 3000, 64, seed=8)
+    res = []
+    for overlap in (True, False):
+        est = DictFact(n_components=64, batch_size=128, reduction=4, random_state=0, **kw)
+        est.prepare(n_samples=768, X=X[:64])
+        est.overlap_stats = overlap
+        est.partial_fit(X)
+        res.append((est.components_, est.B_, est.C_, est.code_, est.comp_norm_))
+    for a, c in zip(*res):
+        assert rel_err(a, c.astype(np.float64)) < 1e-5
+
+
+def test_async_host_copy_matches_synchronous():
+    from modl_b200 import DictFact
+    X = _planted(1024, 2000, 32, seed=9)
+    Xp = torch.from_numpy(X).pin_memory()
+    res = []
+    for mode in (False, True):
+        est = DictFact(n_components=32, batch_size=128, reduction=4, random_state=0, async_host_copy=mode)
+        est.prepare(n_samples=1024, X=X[:32])
+        for i in range(0, 1024, 128):                       # one batch per call
+            est.partial_fit(Xp[i:i + 128], np.arange(i, i + 128))
+        est.synchronize()
+        res.append(est.components_)
+    np.testing.assert_array_equal(res[0], res[1])
