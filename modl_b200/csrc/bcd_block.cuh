@@ -74,14 +74,6 @@ __device__ __forceinline__ uint4 ld_dsmem_v4(unsigned cluster_addr)
     return v;
 }
 
-// 1 / sqrt(x): the hardware approximation plus one Newton step (float), exact division (double)
-__device__ __forceinline__ float bb_rsqrt(float x)
-{
-    const float y = rsqrtf(x);
-    return fmaf(0.5f * y, fmaf(-x * y, y, 1.f), y);
-}
-__device__ __forceinline__ double bb_rsqrt(double x) { return 1.0 / sqrt(x); }
-
 // Sum over the 32 lanes of 16 values per lane with 16 shuffles (instead of 80): every step halves
 // the number of values a lane carries.  On return lane L holds the total of value (L >> 1).
 template <typename T>
@@ -404,7 +396,7 @@ bcd_block_kernel(BcdParams<T> P)
                 const T x = (upd ? s_r : zz) * kap;                         // |v|^2 / radius
                 // 1 / nrm, nrm = sqrt(|v|^2 / radius) when the candidate leaves the ball [ref: enet.pyx:62-70];
                 // 0 for a zero ball [ref: enet.pyx:57-59]
-                const T rnrm = zero_ball ? T(0) : (x > T(1) ? bb_rsqrt(x) : T(1));
+                const T rnrm = zero_ball ? T(0) : (x > T(1) ? bcd_rsqrt(x) : T(1));
                 const T f = upd ? rnrm * rcvj : rnrm;
                 const T ez = (m == M + jj) ? T(1) : T(0);
                 // delta_j = f r_j - z_j (updated atom)  |  (rnrm - 1) z_j (atom left alone, only projected)

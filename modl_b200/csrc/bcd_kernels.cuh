@@ -73,6 +73,14 @@ struct BcdParams {
     long long *timing;   // debug: [k][8] clock64 stamps of CTA 0 (NULL = off)
 };
 
+// 1 / sqrt(x): the hardware approximation plus one Newton step (float), exact division (double)
+__device__ __forceinline__ float bcd_rsqrt(float x)
+{
+    const float y = rsqrtf(x);
+    return fmaf(0.5f * y, fmaf(-x * y, y, 1.f), y);
+}
+__device__ __forceinline__ double bcd_rsqrt(double x) { return 1.0 / sqrt(x); }
+
 template <typename T>
 __device__ __forceinline__ void cp_async_elem(T *smem_dst, const T *gmem_src)
 {

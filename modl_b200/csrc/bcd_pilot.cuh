@@ -24,14 +24,15 @@
 namespace modl {
 
 constexpr int BP_M = 8;                       // atoms per look-ahead block
-constexpr int BP_THREADS = 256;               // warp 0 = pilot, warps 1-3 and 5-7 = workers, warp 4 idles
-// Warp w issues from scheduler w % 4.  The pilot's dependent chain is latency bound, so the other
-// warps of ITS scheduler (4, 8, ...) stay idle during the atom loop: the pilot then never waits
-// for an issue slot behind a worker's FFMA2 / LDS stream.
-constexpr int BP_WORKER_WARPS = BP_THREADS / 32 - 1 - (BP_THREADS / 32 - 1) / 4;
-constexpr int BP_WORKERS = BP_WORKER_WARPS * 32;
-constexpr int BP_SYNCED = BP_WORKERS + 32;    // threads that meet at the pilot <-> worker barriers
-enum { BP_BAR_PRODUCT = 1, BP_BAR_SNAPSHOT = 2, BP_BAR_WORKERS = 3 };
+// The per-atom chain is latency bound, and most of its length is the serial work of ONE warp over
+// its 2-6 column groups.  So the chain is carried by BP_PW pilot warps, each owning every BP_PW-th
+// 32-column group of the CTA's slice (one group per pilot at the benchmark shape); they combine
+// their two partial sums through shared memory and a 96-thread named barrier, warp 0 sends, all wait.
+constexpr int BP_PW = 3;                      // pilot warps
+constexpr int BP_THREADS = 384;               // warps 0-2 = pilots, warps 3-11 = workers
+constexpr int BP_WORKERS = BP_THREADS - 32 * BP_PW;
+constexpr int BP_SYNCED = BP_THREADS;         // threads that meet at the pilot <-> worker barriers
+enum { BP_BAR_PRODUCT = 1, BP_BAR_SNAPSHOT = 2, BP_BAR_WORKERS = 3, BP_BAR_PILOTS = 4 };
 
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
@@ -166,11 +167,9 @@ bcd_pilot_kernel(BcdParams<T> P)
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     if (xstamp) xstamp[1] = clock64();
 
-    if (wid != 0 && (wid & 3) == 0) {
-        // idle warp: leaves the pilot's scheduler alone, joins again at the epilogue
-    } else if (wid != 0) {
+    if (wid >= BP_PW) {
         // =========================== workers: everything off the critical path ===========================
-        const int wt = (wid - 1 - (wid >> 2)) * 32 + lane;
+        const int wt = tid - 32 * BP_PW;
         const int pr = wt % NP, ig = wt / NP;
         const int RB = (((k + IGW - 1) / IGW) + 3) & ~3;
         for (int b = 0; b < nbk; ++b) {
@@ -248,12 +247,15 @@ bcd_pilot_kernel(BcdParams<T> P)
             named_arrive(BP_BAR_PRODUCT, BP_SYNCED);
         }
     } else {
-        // =========================== pilot: the dependent chain ===========================
-        // Lane l owns columns l + 32 m, m < NCL, of the CTA's slice; padded columns carry zeros
-        // through every formula, so the column loops are branch-free and fully unrolled.
+        // =========================== pilots: the dependent chain ===========================
+        // Pilot warp w owns the 32-column groups m = w, w + BP_PW, ... (< NCL) of the CTA's slice, lane l
+        // the column l + 32 m; padded columns carry zeros through every formula.
+        constexpr int NCLW = (NCL + BP_PW - 1) / BP_PW;    // column groups per pilot warp
+        __shared__ double psum_raw[2 * BP_PW * 2];
+        T *psum = reinterpret_cast<T *>(psum_raw);         // [2 parities][BP_PW][2] per-warp partial sums
         unsigned xi = 0;                                   // exchange counter
         long long *tstamp = nullptr;
-#define BP_STAMP(slot) do { if (tstamp && lane == 0) tstamp[(slot)] = clock64(); } while (0)
+#define BP_STAMP(slot) do { if (tstamp && tid == 0) tstamp[(slot)] = clock64(); } while (0)
         // peer addresses of my slot and of the peer's mbarrier, per parity
         unsigned rslot[2], rbar[2];
 #pragma unroll
@@ -265,24 +267,40 @@ bcd_pilot_kernel(BcdParams<T> P)
         auto exchange = [&](T p0, T p1, T &o0, T &o1) {
             const unsigned par = xi & 1u;
             p0 = warp_sum(p0); p1 = warp_sum(p1);
+            T *ps = psum + par * (2 * BP_PW);
+            if (lane == 0) { ps[2 * wid] = p0; ps[2 * wid + 1] = p1; }
+            if (enet) __threadfence();                     // my slice of the candidate row is visible before the send
+            named_sync(BP_BAR_PILOTS, 32 * BP_PW);
             BP_STAMP(2);
-            if (enet) __threadfence();
-            if (lane == 0) mbar_expect_tx(xbar_addr + 8 * par, (unsigned)nblk * kSlotBytes);
-            if (lane < nblk) st_async_triplet(rslot[par], rbar[par], p0, p1, T(0));
+            if (wid == 0) {
+                T t0 = ps[0], t1 = ps[1];
+#pragma unroll
+                for (int w = 1; w < BP_PW; ++w) { t0 += ps[2 * w]; t1 += ps[2 * w + 1]; }   // fixed order
+                if (enet) __threadfence();
+                if (lane == 0) mbar_expect_tx(xbar_addr + 8 * par, (unsigned)nblk * kSlotBytes);
+                if (lane < nblk) st_async_triplet(rslot[par], rbar[par], t0, t1, T(0));
+            }
             BP_STAMP(3);
             mbar_wait(xbar_addr + 8 * par, (xi >> 1) & 1u);
             BP_STAMP(4);
             if (enet) __threadfence();
-            // slots of absent peers stay zero; both half-warps read the same 16 slots, so a 4-round
-            // butterfly leaves the full sum in every lane (same tree in every CTA -> bit-identical)
-            const T *src = xch + (par * BCD_MAX_CLUSTER + (lane & 15)) * BCD_NPART;
-            T q0 = src[0], q1 = src[1];
+            // slots of absent peers stay zero.  Every lane reads all 16 slots (broadcast loads) and adds them in
+            // the same fixed tree (four chains of four, then a pair of pairs): bit-identical in every CTA, and
+            // shorter than a 4-round shuffle butterfly on the dependent chain
+            const T *src = xch + (size_t)par * BCD_MAX_CLUSTER * BCD_NPART;
+            T a0[4], a1[4];
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-                q0 += __shfl_xor_sync(kFullMask, q0, o);
-                q1 += __shfl_xor_sync(kFullMask, q1, o);
+            for (int c4 = 0; c4 < 4; ++c4) {
+                a0[c4] = src[(4 * c4) * BCD_NPART];
+                a1[c4] = src[(4 * c4) * BCD_NPART + 1];
+#pragma unroll
+                for (int u = 1; u < 4; ++u) {
+                    a0[c4] += src[(4 * c4 + u) * BCD_NPART];
+                    a1[c4] += src[(4 * c4 + u) * BCD_NPART + 1];
+                }
             }
-            o0 = q0; o1 = q1;
+            o0 = (a0[0] + a0[1]) + (a0[2] + a0[3]);
+            o1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
             xi += 1;
         };
 
@@ -323,9 +341,12 @@ bcd_pilot_kernel(BcdParams<T> P)
                 }
                 // ---- candidate row on my columns [ref: :676-685] ----
                 T nb_l = T(0), sv2_l = T(0);
-                T v[NCL], dold[NCL];
+                T v[NCLW], dold[NCLW];
 #pragma unroll
-                for (int m = 0; m < NCL; ++m) {
+                for (int mm = 0; mm < NCLW; ++mm) {
+                    const int m = wid + mm * BP_PW;
+                    v[mm] = dold[mm] = T(0);
+                    if (m >= NCL) continue;
                     const int c = lane + 32 * m;
                     // look-ahead product + repairs for the <= 8 + 7 atoms updated since its snapshot
                     T dot = Rb[j * ncp + c], dot2 = T(0);
@@ -334,14 +355,14 @@ bcd_pilot_kernel(BcdParams<T> P)
 #pragma unroll
                     for (int jp = 0; jp < BP_M - 1; ++jp) dot2 = fma(cf[jp], dcur[jp * ncp + c], dot2);
                     dot += dot2;
-                    dold[m] = Ds[a * ncp + c];
-                    const T grad = (Bb[j * ncp + c] - dot) + caa * dold[m];
+                    dold[mm] = Ds[a * ncp + c];
+                    const T grad = (Bb[j * ncp + c] - dot) + caa * dold[mm];
                     T q = grad * rcaa;
                     q = fma(fma(-q, caa, grad), rcaa, q);           // grad / caa, Newton-corrected
-                    q = upd ? q : dold[m];
+                    q = upd ? q : dold[mm];
                     if (P.positive && q < T(0)) q = T(0);           // [ref: :684-685]
-                    v[m] = q;
-                    nb_l += enet_term(dold[m], P.l1_ratio);
+                    v[mm] = q;
+                    nb_l += enet_term(dold[mm], P.l1_ratio);
                     sv2_l = fma(q, q, sv2_l);
                     if (enet && c < nc) P.vrow[(int64_t)par * s + c0 + c] = q;
                 }
@@ -350,14 +371,20 @@ bcd_pilot_kernel(BcdParams<T> P)
                 exchange(nb_l, sv2_l, nb, sv2);
                 BP_STAMP(5);
                 const T radius = cnorm[a] + nb;                      // comp_norm_[k] += subset_norm  [ref: :676-678]
-                if (lane == 0) rad[a] = radius;
+                if (tid == 0) rad[a] = radius;
                 // projection of the candidate on the ball of "radius" [ref: enet.pyx:38-122].  The L2 case is a
                 // pure rescale v / nrm (Newton-corrected reciprocal multiply); radius == 0 maps to a zero scale.
                 T lthr = T(0), gamma = T(0), nrm = T(1), rnrm = T(1);
                 bool shrink = false;
                 if (!enet) {
-                    nrm = (sv2 <= radius) ? T(1) : t_sqrt(sv2 / radius);
-                    rnrm = (radius == T(0)) ? T(0) : T(1) / nrm;
+                    // nrm = sqrt(|v|^2 / radius) when the candidate leaves the ball [ref: enet.pyx:62-70]: one division,
+                    // then 1 / nrm from the hardware reciprocal square root + one Newton step, nrm = x / nrm
+                    if (radius == T(0)) {
+                        rnrm = T(0);
+                    } else {
+                        const T x = sv2 / radius;
+                        if (x > T(1)) { rnrm = bcd_rsqrt(x); nrm = x * rnrm; }
+                    }
                 } else if (radius == T(0)) {
                     rnrm = T(0);
                 } else {
@@ -369,9 +396,11 @@ bcd_pilot_kernel(BcdParams<T> P)
                     lthr = l;
                 }
 #pragma unroll
-                for (int m = 0; m < NCL; ++m) {
+                for (int mm = 0; mm < NCLW; ++mm) {
+                    const int m = wid + mm * BP_PW;
+                    if (m >= NCL) continue;
                     const int c = lane + 32 * m;
-                    T q = v[m];
+                    T q = v[mm];
                     if (enet && shrink) {
                         q = enet_shrink(q, lthr, gamma);
                     } else {
@@ -379,7 +408,7 @@ bcd_pilot_kernel(BcdParams<T> P)
                         q = fma(fma(-t, nrm, q), rnrm, t);          // v / nrm [ref: enet.pyx:69-70]; 0 when radius == 0
                     }
                     vcur[j * ncp + c] = q;
-                    dcur[j * ncp + c] = q - dold[m];
+                    dcur[j * ncp + c] = q - dold[mm];
                 }
                 BP_STAMP(6);
                 BP_STAMP(7);
@@ -432,8 +461,12 @@ bcd_pilot_kernel(BcdParams<T> P)
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     if (g == 0) {
         for (int i = tid; i < k; i += BP_THREADS) {
+            T part[BCD_MAX_CLUSTER];
+#pragma unroll
+            for (int q = 0; q < BCD_MAX_CLUSTER; ++q) part[q] = q < nblk ? __ldcg(napart + (int64_t)q * k + i) : T(0);   // all in flight
             T na = T(0);
-            for (int q = 0; q < nblk; ++q) na += __ldcg(napart + (int64_t)q * k + i);   // fixed order
+#pragma unroll
+            for (int q = 0; q < BCD_MAX_CLUSTER; ++q) na += part[q];                     // fixed order
             P.comp_norm[i] = rad[i] - na;
         }
     }
