@@ -58,8 +58,9 @@ int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M
     P.alpha = alpha; P.beta = beta;
     P.sbo = 128u;
     P.bn = bn;
+    P.nacc = 512 / bn < 4 ? 512 / bn : 4;
     P.tmem_cols = 32;
-    while ((int)P.tmem_cols < bn) P.tmem_cols <<= 1;
+    while ((int)P.tmem_cols < P.nacc * bn) P.tmem_cols <<= 1;
     const size_t stage_bytes = TC_BLOCK_BYTES + (size_t)2 * bn * TC_BK * 4;
     P.stages = (int)((TC_SMEM_BUDGET - 1024) / stage_bytes);
     if (P.stages > TC_MAX_STAGES) P.stages = TC_MAX_STAGES;

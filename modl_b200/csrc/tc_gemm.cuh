@@ -39,6 +39,11 @@ constexpr unsigned TC_HALF_BYTES = TC_HALF_FLOATS * 4;     // 16 KB
 constexpr int TC_MAX_STAGES = 3;
 constexpr int TC_THREADS = 192;              // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 constexpr int TC_MAX_BN = 256;               // widest accumulator tile (UMMA N)
+// The tensor core adds every MMA into the TMEM accumulator with truncation, so the error of one
+// accumulator grows linearly with the number of MMAs chained into it (measured: 1e-6 relative after
+// 48, 6e-6 after 228 on same-sign data).  Long contractions therefore rotate over up to 4
+// accumulators, one k-block (12 MMAs) at a time; the epilogue adds them in fp32 (RN).
+constexpr int TC_CHAIN = 1;
 constexpr size_t TC_SMEM_BUDGET = 226 * 1024;
 
 // An operand is cut into blocks of `rpb` rows (rows-per-block: 128 on the M side; the UMMA N of
@@ -254,7 +259,8 @@ struct TcGemmParams {
     const float *B;      // packed, bn-row blocks:  tc_row_blocks(N, bn) x nkb
     int bn;              // accumulator tile width (UMMA N): multiple of 16, 16..256
     int stages;          // smem pipeline depth (<= TC_MAX_STAGES)
-    unsigned tmem_cols;  // power of two >= bn
+    int nacc;            // accumulators of bn columns each, used round-robin in chains of TC_CHAIN k-blocks
+    unsigned tmem_cols;  // power of two >= nacc * bn
     float *C;
     int64_t ldc;
     float *part;         // split-K partials or NULL
@@ -326,13 +332,17 @@ tc_gemm_kernel(TcGemmParams P)
                 const unsigned sa = smem0 + (unsigned)s * stage_bytes;            // A: hi | lo
                 const unsigned sb = sa + a_bytes;                                 // B: hi | lo
 #pragma unroll
+                const int chain = i / TC_CHAIN;
+                const unsigned acc = tmem + (unsigned)((chain % P.nacc) * P.bn);  // column offset of this chain's accumulator
+                const bool fresh = chain < P.nacc && (i % TC_CHAIN) == 0;         // first k-block ever written to it
+#pragma unroll
                 for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
                     const unsigned ka = (unsigned)k8 * 2u * lbo_a, kb = (unsigned)k8 * 2u * lbo_b;   // two chunks per MMA
                     const uint64_t a_hi = tc_smem_desc(sa + ka, lbo_a, P.sbo), a_lo = tc_smem_desc(sa + TC_HALF_BYTES + ka, lbo_a, P.sbo);
                     const uint64_t b_hi = tc_smem_desc(sb + kb, lbo_b, P.sbo), b_lo = tc_smem_desc(sb + b_half + kb, lbo_b, P.sbo);
-                    tc_mma_tf32(tmem, a_lo, b_hi, idesc, (i | k8) != 0);          // small terms first
-                    tc_mma_tf32(tmem, a_hi, b_lo, idesc, 1u);
-                    tc_mma_tf32(tmem, a_hi, b_hi, idesc, 1u);
+                    tc_mma_tf32(acc, a_lo, b_hi, idesc, !(fresh && k8 == 0));      // small terms first
+                    tc_mma_tf32(acc, a_hi, b_lo, idesc, 1u);
+                    tc_mma_tf32(acc, a_hi, b_hi, idesc, 1u);
                 }
                 tc_commit(empty_bar(s));                                          // smem slot reusable when these finish
             }
@@ -350,10 +360,18 @@ tc_gemm_kernel(TcGemmParams P)
         const unsigned trow = tmem + ((unsigned)(q * 32) << 16);
         const int pitch = P.bn + 4;                    // floats; 16-byte aligned rows, conflict-free quarter-warps
         const unsigned tile0 = smem0;
+        const int nused = min(P.nacc, (nk + TC_CHAIN - 1) / TC_CHAIN);   // accumulators that received MMAs
         for (int c0 = 0; c0 < P.bn; c0 += 32) {
             float v[32];
             __syncwarp();                              // tcgen05.ld is warp-collective (.sync.aligned)
             tc_tmem_ld32(trow + (unsigned)c0, v);
+            for (int a = 1; a < nused; ++a) {          // uniform trip count
+                float u[32];
+                __syncwarp();
+                tc_tmem_ld32(trow + (unsigned)(a * P.bn + c0), u);
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) v[jj] += u[jj];
+            }
             const unsigned dst = tile0 + 4u * (unsigned)((q * 32 + lane) * pitch + c0);
 #pragma unroll
             for (int jj = 0; jj < 32; jj += 4)

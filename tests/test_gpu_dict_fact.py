@@ -290,3 +290,41 @@ def test_async_host_copy_matches_synchronous():
         est.synchronize()
         res.append(est.components_)
     np.testing.assert_array_equal(res[0], res[1])
+
+
+@pytest.mark.parametrize("name,cfg", [
+    # BASELINE configs[2]: ImageDictFact's DictFact (16 x 16 x 224 patches, NMF setting: positive codes and atoms)
+    ("config3_image_nmf", dict(p=57344, k=256, b=512, kw=dict(reduction=8, code_l1_ratio=1., code_alpha=0.1, comp_l1_ratio=0.,
+                                                                 code_pos=True, comp_pos=True, tol=1e-2))),
+    # BASELINE configs[3]: fMRIDictFact's DictFact (ridge code, L1-ball atoms), p ~ 2e5, k = 70, reduction 12
+    ("config4_fmri", dict(p=200000, k=70, b=200, kw=dict(reduction=12, code_l1_ratio=0., code_alpha=1., comp_l1_ratio=1.))),
+])
+def test_single_step_other_baseline_shapes_vs_oracle(oracle, name, cfg):
+    """One minibatch at the full feature width of BASELINE configs 3 and 4 (panels that do NOT fit one
+    cluster: the cooperative dictionary-update kernel; positive / L1-ball projections; ridge coding)."""
+    from modl_b200 import DictFact
+    p, k, b = cfg["p"], cfg["k"], cfg["b"]
+    n = b + k
+    rng = np.random.RandomState(12)
+    # sparse non-negative atoms with little overlap: a well-conditioned Gram matrix, so that the test measures
+    # the kernels and not the chaos of a slowly converging coordinate descent (dense positive atoms are so
+    # coherent that float32 and float64 REFERENCE codes already differ by percents)
+    D0 = (np.abs(rng.randn(k, p)) * (rng.rand(k, p) < 0.03)).astype(np.float32)
+    D0 /= np.linalg.norm(D0, axis=1, keepdims=True)
+    A = (np.abs(rng.randn(n, k)) * (rng.rand(n, k) < 0.1)).astype(np.float32)
+    X = A @ D0 + 0.001 * np.abs(rng.randn(n, p)).astype(np.float32)
+    Dinit = (D0 + 0.05 * np.abs(rng.randn(k, p)).astype(np.float32) * (D0 > 0)).astype(np.float32)
+    kw = dict(n_components=k, batch_size=b, random_state=0, max_iter=100, **cfg["kw"])
+    orc = oracle.OracleDictFact(**kw)
+    orc.prepare(n_samples=n, X=Dinit)
+    est = DictFact(**kw)
+    est.prepare(n_samples=n, X=Dinit)
+    idx = np.arange(k, k + b)
+    orc.partial_fit(X[k:], idx)
+    est.partial_fit(X[k:], idx)
+    np.testing.assert_array_equal(est.last_subset_, orc.subset_log_[-1])
+    np.testing.assert_array_equal(est.last_order_, orc.order_log_[-1])
+    errs = dict(code=rel_err(est.code_[idx], orc.code_[idx]), C=rel_err(est.C_, orc.C_), B=rel_err(est.B_, orc.B_),
+                D=rel_err(est.components_, orc.components_))
+    print(name, errs)
+    assert errs["code"] < 1e-4 and errs["C"] < 1e-4 and errs["B"] < 1e-4 and errs["D"] < 1e-4, errs
