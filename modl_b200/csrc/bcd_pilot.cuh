@@ -264,7 +264,11 @@ bcd_pilot_kernel(BcdParams<T> P)
             rslot[par] = mapa_u32(xch_addr + (par * BCD_MAX_CLUSTER + (unsigned)g) * kSlotBytes, peer);
             rbar[par] = mapa_u32(xbar_addr + 8 * par, peer);
         }
-        auto exchange = [&](T p0, T p1, T &o0, T &o1) {
+        // The exchange in two halves, so that independent work can sit between the send and the wait.  The
+        // pilots combine their partial sums through shared memory (96-thread named barrier) and warp 0 sends
+        // ONE slot per peer.  (Measured alternative: every pilot warp sending its own slot removes the barrier
+        // but triples the DSMEM traffic and the slots to add: 1 460 vs 1 240 cycles per atom.)
+        auto exchange_send = [&](T p0, T p1) {
             const unsigned par = xi & 1u;
             p0 = warp_sum(p0); p1 = warp_sum(p1);
             T *ps = psum + par * (2 * BP_PW);
@@ -281,6 +285,9 @@ bcd_pilot_kernel(BcdParams<T> P)
                 if (lane < nblk) st_async_triplet(rslot[par], rbar[par], t0, t1, T(0));
             }
             BP_STAMP(3);
+        };
+        auto exchange_wait = [&](T &o0, T &o1) {
+            const unsigned par = xi & 1u;
             mbar_wait(xbar_addr + 8 * par, (xi >> 1) & 1u);
             BP_STAMP(4);
             if (enet) __threadfence();
@@ -320,6 +327,35 @@ bcd_pilot_kernel(BcdParams<T> P)
             if (xstamp) xstamp[16 + 2 * b + 1] = clock64();
             if (b + 1 < nbk) named_arrive(BP_BAR_SNAPSHOT, BP_SYNCED);   // workers may recycle the buffers of block b-1
 
+            // Everything atom j needs EXCEPT the contribution of the atom updated just before it:
+            //   base = B_sub[a_j] - (look-ahead product + repairs for the previous block and for atoms < j-1 of this one)
+            // It does not depend on the projection in flight, so it is computed for atom j+1 between the send and
+            // the wait of atom j's exchange: most of the candidate's work leaves the dependent chain.
+            auto precompute = [&](int jn, T (&base)[NCLW], T (&dold)[NCLW], T &nb_l) {
+                const int a = ordc[jn];
+                nb_l = T(0);
+#pragma unroll
+                for (int mm = 0; mm < NCLW; ++mm) {
+                    const int m = wid + mm * BP_PW;
+                    base[mm] = dold[mm] = T(0);
+                    if (m >= NCL) continue;
+                    const int c = lane + 32 * m;
+                    T dot = Rb[jn * ncp + c], dot2 = T(0);
+#pragma unroll
+                    for (int jp = 0; jp < BP_M; ++jp) dot = fma(cfp[jn * BP_M + jp], dprev[jp * ncp + c], dot);
+#pragma unroll
+                    for (int jp = 0; jp < BP_M - 2; ++jp)
+                        if (jp < jn - 1) dot2 = fma(cfm[jn * BP_M + jp], dcur[jp * ncp + c], dot2);
+                    dold[mm] = Ds[a * ncp + c];
+                    base[mm] = Bb[jn * ncp + c] - (dot + dot2);
+                    nb_l += enet_term(dold[mm], P.l1_ratio);
+                }
+            };
+
+            T base[NCLW], dold[NCLW], dlast[NCLW], nb_l;
+#pragma unroll
+            for (int mm = 0; mm < NCLW; ++mm) dlast[mm] = T(0);
+            precompute(0, base, dold, nb_l);
             for (int j = 0; j < mb; ++j) {
                 tstamp = (P.timing && g == 0) ? P.timing + (int64_t)(b * BP_M + j) * 8 : nullptr;
                 BP_STAMP(0);
@@ -328,49 +364,35 @@ bcd_pilot_kernel(BcdParams<T> P)
                 const bool upd = caa > T(1e-20);                    // [ref: :681-683]
                 const T rcaa = rcv[j];
                 const unsigned par = xi & 1u;
-                T cf[BP_M], cp[BP_M];                               // C[a, .] against this block's / the previous block's atoms
-                {
-                    const Quad<T> q0 = *reinterpret_cast<const Quad<T> *>(cfm + j * BP_M);
-                    const Quad<T> q1 = *reinterpret_cast<const Quad<T> *>(cfm + j * BP_M + 4);
-                    const Quad<T> p0 = *reinterpret_cast<const Quad<T> *>(cfp + j * BP_M);
-                    const Quad<T> p1 = *reinterpret_cast<const Quad<T> *>(cfp + j * BP_M + 4);
-                    cf[0] = q0.x; cf[1] = q0.y; cf[2] = q0.z; cf[3] = q0.w;
-                    cf[4] = q1.x; cf[5] = q1.y; cf[6] = q1.z; cf[7] = q1.w;
-                    cp[0] = p0.x; cp[1] = p0.y; cp[2] = p0.z; cp[3] = p0.w;
-                    cp[4] = p1.x; cp[5] = p1.y; cp[6] = p1.z; cp[7] = p1.w;
-                }
+                const T clast = j > 0 ? cfm[j * BP_M + j - 1] : T(0);   // C[a_j, a_{j-1}]
+                const T cn_a = cnorm[a];                             // read before the wait: off the dependent chain
                 // ---- candidate row on my columns [ref: :676-685] ----
-                T nb_l = T(0), sv2_l = T(0);
-                T v[NCLW], dold[NCLW];
+                T sv2_l = T(0);
+                T v[NCLW];
 #pragma unroll
                 for (int mm = 0; mm < NCLW; ++mm) {
                     const int m = wid + mm * BP_PW;
-                    v[mm] = dold[mm] = T(0);
+                    v[mm] = T(0);
                     if (m >= NCL) continue;
                     const int c = lane + 32 * m;
-                    // look-ahead product + repairs for the <= 8 + 7 atoms updated since its snapshot
-                    T dot = Rb[j * ncp + c], dot2 = T(0);
-#pragma unroll
-                    for (int jp = 0; jp < BP_M; ++jp) dot = fma(cp[jp], dprev[jp * ncp + c], dot);
-#pragma unroll
-                    for (int jp = 0; jp < BP_M - 1; ++jp) dot2 = fma(cf[jp], dcur[jp * ncp + c], dot2);
-                    dot += dot2;
-                    dold[mm] = Ds[a * ncp + c];
-                    const T grad = (Bb[j * ncp + c] - dot) + caa * dold[mm];
+                    const T grad = fma(-clast, dlast[mm], base[mm]) + caa * dold[mm];
                     T q = grad * rcaa;
                     q = fma(fma(-q, caa, grad), rcaa, q);           // grad / caa, Newton-corrected
                     q = upd ? q : dold[mm];
                     if (P.positive && q < T(0)) q = T(0);           // [ref: :684-685]
                     v[mm] = q;
-                    nb_l += enet_term(dold[mm], P.l1_ratio);
                     sv2_l = fma(q, q, sv2_l);
                     if (enet && c < nc) P.vrow[(int64_t)par * s + c0 + c] = q;
                 }
-                T nb, sv2;
                 BP_STAMP(1);
-                exchange(nb_l, sv2_l, nb, sv2);
+                exchange_send(nb_l, sv2_l);
+                // between the send and the wait: the next atom's base row (uses atoms < j of this block only)
+                T nbase[NCLW], ndold[NCLW], nnb_l = T(0);
+                if (j + 1 < mb) precompute(j + 1, nbase, ndold, nnb_l);
+                T nb, sv2;
+                exchange_wait(nb, sv2);
                 BP_STAMP(5);
-                const T radius = cnorm[a] + nb;                      // comp_norm_[k] += subset_norm  [ref: :676-678]
+                const T radius = cn_a + nb;                          // comp_norm_[k] += subset_norm  [ref: :676-678]
                 if (tid == 0) rad[a] = radius;
                 // projection of the candidate on the ball of "radius" [ref: enet.pyx:38-122].  The L2 case is a
                 // pure rescale v / nrm (Newton-corrected reciprocal multiply); radius == 0 maps to a zero scale.
@@ -408,8 +430,12 @@ bcd_pilot_kernel(BcdParams<T> P)
                         q = fma(fma(-t, nrm, q), rnrm, t);          // v / nrm [ref: enet.pyx:69-70]; 0 when radius == 0
                     }
                     vcur[j * ncp + c] = q;
-                    dcur[j * ncp + c] = q - dold[mm];
+                    dlast[mm] = q - dold[mm];
+                    dcur[j * ncp + c] = dlast[mm];
                 }
+#pragma unroll
+                for (int mm = 0; mm < NCLW; ++mm) { base[mm] = nbase[mm]; dold[mm] = ndold[mm]; }
+                nb_l = nnb_l;
                 BP_STAMP(6);
                 BP_STAMP(7);
             }
