@@ -295,7 +295,7 @@ def run_b200(args, rank, world):
     e2e_value = steps * b_global / (e2e_ms * 1e-3)
 
     # pinned host -> device bandwidth of this box (what bounds the end-to-end number once the kernels are fast)
-    h2d_gbps = None
+    h2d_gbps = h2d_fresh_gbps = None
     if rank == 0:
         buf_h = Xp[:b_local]
         buf_d = torch.empty_like(buf_h, device=dev)
@@ -308,6 +308,14 @@ def run_b200(args, rank, world):
         ev1.record()
         torch.cuda.synchronize(dev)
         h2d_gbps = 10 * buf_h.numel() * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+        # the same copy over DISTINCT batches (what the end-to-end loop does: every step reads fresh host pages)
+        nfresh = min(total, 16)
+        ev0.record()
+        for i in range(nfresh):
+            buf_d.copy_(Xp[i * b_local:(i + 1) * b_local], non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        h2d_fresh_gbps = nfresh * buf_h.numel() * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
 
     # ---- (3) per-phase device times (separate profiled pass, CUDA events on the stream) ----
     phases_ms, roof = None, None
@@ -383,7 +391,7 @@ def run_b200(args, rank, world):
                     "h2d_bytes_per_step": int(b_local * P * 4 + b_local * 8), "d2h_bytes_per_step": int(b_local * K * 4),
                     "api": "DictFact(async_host_copy=True).partial_fit(pinned host rows, sample_indices), one batch per "
                            "call, + read-back of the batch code into pinned memory every step",
-                    "pinned_h2d_GBps": h2d_gbps},
+                    "pinned_h2d_GBps": h2d_gbps, "pinned_h2d_distinct_batches_GBps": h2d_fresh_gbps},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": roof,

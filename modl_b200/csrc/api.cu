@@ -451,6 +451,16 @@ static int update_stats_impl(modl_ctx *ctx, const T *code, const int64_t *indice
             float *codeP = nullptr, *XP = nullptr;
             MODL_TRY(ws<float>(ctx, WS_TC_CODE, tc_packed_elems(k, b), &codeP));
             MODL_TRY(tc_pack_cols(ctx, cb, k, b, k, codeP, 128, st));
+            if (C && B) {
+                // ONE launch for both statistics: [B_ | C_] = code^T [X | code].  The code rows are appended to the
+                // packed X^T operand at the next tile boundary; tiles beyond it are written to C_.
+                const int bn = tc_pick_bn(ctx, p + k, ceil_div(k, 128));
+                const int64_t n_split = round_up(p, bn), nkb = ceil_div(b, 32);
+                MODL_TRY(ws<float>(ctx, WS_TC_X, tc_packed_elems(n_split + k, b, bn), &XP));
+                MODL_TRY(tc_pack_cols(ctx, X, ldx, b, p, XP, bn, st));
+                MODL_TRY(tc_pack_cols(ctx, cb, k, b, k, XP + (size_t)(n_split / bn) * nkb * (2 * bn * 32), bn, st));
+                return tc_gemm(ctx, codeP, XP, k, n_split + k, b, a, be, B, ldb, bn, st, WS_GEMM_PART, C, k, n_split, p);
+            }
             if (C) MODL_TRY(tc_gemm(ctx, codeP, codeP, k, k, b, a, be, C, k, 128, st));
             if (B) {
                 const int bn = tc_pick_bn(ctx, p, ceil_div(k, 128));       // e.g. p = 10000, k = 256: 144 -> 140 CTAs, one wave

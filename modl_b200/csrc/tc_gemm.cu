@@ -47,7 +47,8 @@ int tc_pack_cols(modl_ctx *ctx, const float *src, int64_t ld, int64_t kd, int64_
 }
 
 int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M, int64_t N, int64_t Kd, float alpha,
-            float beta, float *C, int64_t ldc, int bn, cudaStream_t st, WsSlot part_slot)
+            float beta, float *C, int64_t ldc, int bn, cudaStream_t st, WsSlot part_slot, float *C2, int64_t ldc2,
+            int64_t n_split, int64_t N1)
 {
     if (M <= 0 || N <= 0) return MODL_OK;
     MODL_REQUIRE(Kd >= 1, "tc_gemm needs a non-empty contraction");
@@ -58,6 +59,11 @@ int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M
     P.alpha = alpha; P.beta = beta;
     P.sbo = 128u;
     P.bn = bn;
+    P.C2 = C2; P.ldc2 = ldc2;
+    P.n_split = C2 ? (int)n_split : 0;
+    P.N1 = C2 ? (int)N1 : (int)N;
+    P.N2 = C2 ? (int)(N - n_split) : 0;
+    MODL_REQUIRE(C2 == nullptr || (n_split % bn == 0 && N1 <= n_split && n_split < N), "tc_gemm second destination");
     P.nacc = 512 / bn < 4 ? 512 / bn : 4;
     P.tmem_cols = 32;
     while ((int)P.tmem_cols < P.nacc * bn) P.tmem_cols <<= 1;
@@ -76,7 +82,7 @@ int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M
     int64_t splits = (int64_t)ctx->sm_count / tiles;            // never more CTAs than SMs: a second wave costs a whole tile time
     if (splits > P.nkb) splits = P.nkb;
     if (splits > 32) splits = 32;
-    if (splits < 1) splits = 1;
+    if (splits < 1 || C2 != nullptr) splits = 1;        // the two-destination form is never split
     P.kb_per_split = (int)ceil_div(P.nkb, splits);
     splits = ceil_div(P.nkb, P.kb_per_split);
     P.part = nullptr;

@@ -269,6 +269,11 @@ struct TcGemmParams {
     int kb_per_split;    // k blocks per grid.z slice
     float alpha, beta;
     unsigned sbo;        // descriptor stride byte offset: next 8-row group (128)
+    // optional second destination: column tiles at or beyond n_split (a multiple of bn) are written to C2
+    // (column n - n_split, N2 valid columns, leading dimension ldc2); tiles below it keep N1 valid columns
+    float *C2;
+    int64_t ldc2;
+    int n_split, N1, N2;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -381,7 +386,11 @@ tc_gemm_kernel(TcGemmParams P)
         }
         asm volatile("bar.sync 2, 128;\n" ::: "memory");        // the four epilogue warps
         const int ew = warp - 2;
-        const int n_tile = nb * P.bn;
+        const bool second = P.C2 != nullptr && nb * P.bn >= P.n_split;
+        const int n_tile = second ? nb * P.bn - P.n_split : nb * P.bn;     // first column of the tile in its destination
+        const int n_lim = second ? P.N2 : P.N1;
+        float *const c_base = second ? P.C2 : P.C;
+        const int64_t c_ld = second ? P.ldc2 : P.ldc;
         const bool raw = P.part != nullptr;
         const bool use_c = !raw && P.beta != 0.f;
         // 8 rows per batch (r0, r0 + 4, ..., r0 + 28): their C reads are all in flight before the first is consumed
@@ -395,10 +404,10 @@ tc_gemm_kernel(TcGemmParams P)
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int r = r0 + 4 * u, m = mb * TC_ROWS + r;
-                    float *grow = raw ? P.part + ((size_t)blockIdx.z * P.M + m) * P.N : P.C + (int64_t)m * P.ldc;
+                    float *grow = raw ? P.part + ((size_t)blockIdx.z * P.M + m) * P.N : c_base + (int64_t)m * c_ld;
                     dst[u] = grow + n;
-                    const bool live = m < P.M && n < P.N;
-                    fast[u] = live && n + 4 <= P.N && ((reinterpret_cast<uintptr_t>(dst[u]) & 15) == 0);
+                    const bool live = m < P.M && n < n_lim;
+                    fast[u] = live && n + 4 <= n_lim && ((reinterpret_cast<uintptr_t>(dst[u]) & 15) == 0);
                     if (!live) dst[u] = nullptr;
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(t[u].x), "=f"(t[u].y), "=f"(t[u].z), "=f"(t[u].w)
                                  : "r"(tile0 + 4u * (unsigned)(r * pitch + c)));
@@ -419,7 +428,7 @@ tc_gemm_kernel(TcGemmParams P)
                         const float e[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
 #pragma unroll
                         for (int w = 0; w < 4; ++w) {
-                            if (n + w >= P.N) continue;
+                            if (n + w >= n_lim) continue;
                             float o = e[w];
                             if (!raw) {
                                 o *= P.alpha;
