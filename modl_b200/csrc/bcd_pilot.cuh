@@ -270,6 +270,7 @@ bcd_pilot_kernel(BcdParams<T> P)
         // but triples the DSMEM traffic and the slots to add: 1 460 vs 1 240 cycles per atom.)
         auto exchange_send = [&](T p0, T p1) {
             const unsigned par = xi & 1u;
+            if (tid == 0) mbar_expect_tx(xbar_addr + 8 * par, (unsigned)nblk * kSlotBytes);   // armed early, off the chain
             p0 = warp_sum(p0); p1 = warp_sum(p1);
             T *ps = psum + par * (2 * BP_PW);
             if (lane == 0) { ps[2 * wid] = p0; ps[2 * wid + 1] = p1; }
@@ -281,7 +282,6 @@ bcd_pilot_kernel(BcdParams<T> P)
 #pragma unroll
                 for (int w = 1; w < BP_PW; ++w) { t0 += ps[2 * w]; t1 += ps[2 * w + 1]; }   // fixed order
                 if (enet) __threadfence();
-                if (lane == 0) mbar_expect_tx(xbar_addr + 8 * par, (unsigned)nblk * kSlotBytes);
                 if (lane < nblk) st_async_triplet(rslot[par], rbar[par], t0, t1, T(0));
             }
             BP_STAMP(3);

@@ -87,8 +87,8 @@ for f in sorted(os.listdir(src)):
         byt = val('dram__bytes_read.sum') + val('dram__bytes_write.sum')
         for key, ph in PHASE_OF:
             if key in name:
-                if key == "tc_gemm":      # launches of one step in order: [G;Dx], C_, B_
-                    ph = "gram" if gemm_seen % 3 == 0 else "stats"
+                if key == "tc_gemm":      # launches of one step in order: [G ; Dx], then [B_ | C_]
+                    ph = "gram" if gemm_seen % 2 == 0 else "stats"
                     gemm_seen += 1
                 traffic[ph] = traffic.get(ph, 0) + byt
                 break
