@@ -289,6 +289,10 @@ typedef struct modl_step_params {
      * B_ itself is updated by MODL_PHASE_APPLY_B from the full all-reduced stats_inc, which the
      * caller may run on another stream while the dictionary update is in flight. */
     void *inc_sub;             /* device real[k*k + k*lds]                                */
+    /* cudaEvent_t (or NULL) recorded on the call's stream right after MODL_PHASE_APPLY_SUB: "B_[:, subset]
+     * has been read", so that APPLY_SUB and DICT can share one call while another stream waits for exactly
+     * that point before it rewrites B_. */
+    void *ev_after_apply_sub;
 } modl_step_params;
 
 /* MODL_PHASE_STATS_SUB (same call as MODL_PHASE_CODE) computes ONLY what the dictionary update waits
@@ -298,7 +302,9 @@ typedef struct modl_step_params {
  * increment into stats_inc (for the caller's all-reduce + MODL_PHASE_APPLY_B) otherwise.  Run on a
  * second stream it hides the 2.6 GFLOP / 60 MB product behind the sequential dictionary update. */
 enum { MODL_PHASE_CODE = 1, MODL_PHASE_STATS = 2, MODL_PHASE_APPLY = 4, MODL_PHASE_DICT = 8,
-       MODL_PHASE_APPLY_SUB = 16, MODL_PHASE_APPLY_B = 32, MODL_PHASE_STATS_SUB = 64, MODL_PHASE_STATS_B = 128 };
+       MODL_PHASE_APPLY_SUB = 16, MODL_PHASE_APPLY_B = 32, MODL_PHASE_STATS_SUB = 64, MODL_PHASE_STATS_B = 128,
+       /* the feature subset uploaded by the previous call of this context belongs to the same step: skip the upload */
+       MODL_PHASE_REUSE_SUBSET = 256 };
 
 int modl_batch_fit_f32(modl_ctx *, const modl_step_params *prm, void *stream);
 int modl_batch_fit_f64(modl_ctx *, const modl_step_params *prm, void *stream);

@@ -29,11 +29,11 @@ class StepParams(C.Structure):
         ("max_iter", ci), ("code_pos", ci), ("comp_pos", ci), ("Dx_agg", ci), ("G_agg", ci),
         ("optimizer_sgd", ci),
         ("sweeps", vp),
-        ("phases", ci), ("global_batch", i64), ("stats_inc", vp), ("inc_sub", vp),
+        ("phases", ci), ("global_batch", i64), ("stats_inc", vp), ("inc_sub", vp), ("ev_after_apply_sub", vp),
     ]
 
 PHASE_CODE, PHASE_STATS, PHASE_APPLY, PHASE_DICT, PHASE_APPLY_SUB, PHASE_APPLY_B = 1, 2, 4, 8, 16, 32
-PHASE_STATS_SUB, PHASE_STATS_B = 64, 128
+PHASE_STATS_SUB, PHASE_STATS_B, PHASE_REUSE_SUBSET = 64, 128, 256
 
 
 class ModlError(RuntimeError):

@@ -556,7 +556,9 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     T *D = static_cast<T *>(q->components);
     T *code = static_cast<T *>(q->code);
     const T r = (T)q->reduction;
-    const int phases = q->phases ? q->phases : (MODL_PHASE_CODE | MODL_PHASE_STATS | MODL_PHASE_APPLY | MODL_PHASE_DICT);
+    const bool reuse_subset = (q->phases & MODL_PHASE_REUSE_SUBSET) != 0;
+    const int phases = (q->phases & ~MODL_PHASE_REUSE_SUBSET) ? (q->phases & ~MODL_PHASE_REUSE_SUBSET)
+                                                              : (MODL_PHASE_CODE | MODL_PHASE_STATS | MODL_PHASE_APPLY | MODL_PHASE_DICT);
     T *inc = static_cast<T *>(q->stats_inc);
     T *inc_sub = static_cast<T *>(q->inc_sub);
     if (phases == MODL_PHASE_APPLY_B) {
@@ -590,7 +592,7 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     // subset -> device
     int64_t *d_subset = nullptr;
     MODL_TRY(ws<int64_t>(ctx, WS_SUBSET, (size_t)(s > 0 ? s : 1), &d_subset));
-    if (s > 0)
+    if (s > 0 && !reuse_subset)
         MODL_CUDA_TRY(cudaMemcpyAsync(d_subset, q->h_subset, sizeof(int64_t) * (size_t)s, cudaMemcpyHostToDevice, st));
 
     T *xnorm2 = nullptr, *Gw = nullptr, *Dxw = nullptr, *cb = nullptr, *panel = nullptr;
@@ -696,6 +698,7 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
             MODL_LAUNCH_CHECK(ctx);
         }
         ctx->panel_b_ready = 1;
+        if (q->ev_after_apply_sub) MODL_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(q->ev_after_apply_sub), st));
     }
     if (phases & MODL_PHASE_DICT) {
     // ---- _update_dict [ref: :650-715] ----

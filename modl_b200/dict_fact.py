@@ -560,6 +560,7 @@ class DictFact(CodingMixin, BaseEstimator):
         prm.phases, prm.global_batch = 0, int(global_batch)
         prm.stats_inc = stats_inc.data_ptr() if stats_inc is not None else None
         prm.inc_sub = inc_sub.data_ptr() if inc_sub is not None else None
+        prm.ev_after_apply_sub = None
         sw = self.__dict__.get("_d_sweeps")
         if self.__dict__.get("record_sweeps", False):
             if sw is None or sw.shape[0] < b:
@@ -614,6 +615,7 @@ class DictFact(CodingMixin, BaseEstimator):
         if st is None:
             st = self.__dict__["_ovl"] = {"stream": torch.cuda.Stream(device=self._device), "ev_code": torch.cuda.Event(),
                                           "ev_sub": torch.cuda.Event(), "ev_applied": torch.cuda.Event()}
+            st["ev_sub"].record(torch.cuda.current_stream(self._device))   # creates the CUDA event handle the C side records
         return st
 
     def _inc_sub_buffer(self, s):
@@ -632,9 +634,8 @@ class DictFact(CodingMixin, BaseEstimator):
                                 inc_sub=self._inc_sub_buffer(subset.shape[0]))
         self._run_phases(prm, _lib.PHASE_CODE | _lib.PHASE_STATS_SUB)
         st["ev_code"].record(main)
-        self._run_phases(prm, _lib.PHASE_APPLY_SUB)
-        st["ev_sub"].record(main)                   # B_[:, subset] has been read: B_ may now be rewritten
-        self._run_phases(prm, _lib.PHASE_DICT)
+        prm.ev_after_apply_sub = st["ev_sub"].cuda_event     # recorded inside the call: B_[:, subset] has been read
+        self._run_phases(prm, _lib.PHASE_APPLY_SUB | _lib.PHASE_DICT | _lib.PHASE_REUSE_SUBSET)
         if os.environ.get("MODL_STATS_B_SERIAL"):   # experiment: no concurrency, the product runs after the dictionary update
             self._run_phases(prm, _lib.PHASE_STATS_B)
             return

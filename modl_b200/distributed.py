@@ -109,9 +109,8 @@ class ShardedDictFact(ShardedStepMixin, DictFact):
         self._run_phases(prm, _lib.PHASE_CODE | _lib.PHASE_STATS_SUB)
         st["ev_code"].record(main)
         dist.all_reduce(inc_sub, op=dist.ReduceOp.SUM, group=self.process_group)
-        self._run_phases(prm, _lib.PHASE_APPLY_SUB)
-        st["ev_sub"].record(main)                   # B_[:, subset] has been read: B_ may now be rewritten
-        self._run_phases(prm, _lib.PHASE_DICT)
+        prm.ev_after_apply_sub = st["ev_sub"].cuda_event     # recorded inside the call: B_[:, subset] has been read
+        self._run_phases(prm, _lib.PHASE_APPLY_SUB | _lib.PHASE_DICT | _lib.PHASE_REUSE_SUBSET)
         # side stream: the full-width product, its all-reduce and its fold-in, behind the dictionary update
         side.wait_event(st["ev_code"])
         self._run_phases(prm, _lib.PHASE_STATS_B, stream=side)
