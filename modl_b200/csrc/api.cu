@@ -68,7 +68,6 @@ int modl_ctx_create(int device, modl_ctx **out)
     if (const char *e = getenv("MODL_FORCE_GLOBAL_GRAM")) c->opt_force_global_gram = atoi(e);
     if (const char *e = getenv("MODL_TC_GEMM")) c->opt_tc_gemm = atoi(e);
     if (const char *e = getenv("MODL_BCD_BLOCK")) c->opt_bcd_block = atoi(e);
-    if (const char *e = getenv("MODL_TC_DESC_MODE")) c->opt_tc_desc_mode = atoi(e);
     int *info = nullptr;
     if (ws<int>(c, WS_INFO, 4, &info) != MODL_OK) { delete c; return MODL_ECUDA; }
     MODL_CUDA_TRY(cudaMemset(info, 0, 4 * sizeof(int)));
@@ -97,7 +96,6 @@ int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "bcd_timing")) ctx->opt_bcd_timing = value;
     else if (!strcmp(name, "tc_gemm")) ctx->opt_tc_gemm = value;
     else if (!strcmp(name, "bcd_block")) ctx->opt_bcd_block = value;
-    else if (!strcmp(name, "tc_desc_mode")) ctx->opt_tc_desc_mode = value;
     else if (!strcmp(name, "bcd_pilot")) ctx->opt_bcd_pilot = value;
     else { set_error("unknown option %s", name); return MODL_EINVAL; }
     return MODL_OK;

@@ -90,7 +90,6 @@ struct modl_ctx {
     int opt_force_global_gram = 0;// debug: never keep the Gram in shared memory
     int opt_bcd_pilot = 1;        // use the warp-specialised look-ahead dictionary kernel when the panel fits a cluster
     int opt_tc_gemm = 1;          // float contractions on the tensor cores (tcgen05 3xTF32); 0 = CUDA-core FFMA GEMM
-    int opt_tc_desc_mode = 0;     // debug probe of the UMMA descriptor field roles
     int opt_bcd_block = 0;        // experimental: blocked dictionary update (deferred projection scalars, bcd_block.cuh)
     int opt_bcd_timing = 0;       // debug: record clock64 stamps inside the dictionary update
     int bcd_timing_k = 0;

@@ -17,7 +17,6 @@ What runs where
 There is no CPU fallback: without the built extension or without a CUDA device this raises.
 """
 import ctypes as C
-import os
 import time
 from math import ceil
 
@@ -636,9 +635,6 @@ class DictFact(CodingMixin, BaseEstimator):
         st["ev_code"].record(main)
         prm.ev_after_apply_sub = st["ev_sub"].cuda_event     # recorded inside the call: B_[:, subset] has been read
         self._run_phases(prm, _lib.PHASE_APPLY_SUB | _lib.PHASE_DICT | _lib.PHASE_REUSE_SUBSET)
-        if os.environ.get("MODL_STATS_B_SERIAL"):   # experiment: no concurrency, the product runs after the dictionary update
-            self._run_phases(prm, _lib.PHASE_STATS_B)
-            return
         side.wait_event(st["ev_sub"])
         self._run_phases(prm, _lib.PHASE_STATS_B, stream=side)
         st["ev_applied"].record(side)

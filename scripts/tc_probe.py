@@ -42,8 +42,7 @@ for (n, b, k, p) in ((50, 24, 40, 333), (1000, 512, 256, 10000)):
           rel(Bd.cpu().numpy(), 0.7 * B0 + 0.3 / b * cb.T @ X)), flush=True)
 '''
 for mode in (0,):
-    env = dict(os.environ, MODL_TC_DESC_MODE=str(mode), MODL_TC_GEMM="1")
-    print("=== descriptor mode %d" % mode, flush=True)
+    env = dict(os.environ, MODL_TC_GEMM="1")
     try:
         r = subprocess.run([sys.executable, "-c", CHILD], env=env, timeout=120, capture_output=True, text=True)
         print(r.stdout[-3000:])
