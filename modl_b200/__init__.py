@@ -19,6 +19,9 @@ def __getattr__(name):
     if name in ("DictFact", "Coder", "CodingMixin", "get_sub_slice"):
         from . import dict_fact
         return getattr(dict_fact, name)
+    if name in ("ImageDictFact", "LazyCleanPatchExtractor", "scale_patches", "DictionaryScorer"):
+        from . import image
+        return getattr(image, name)
     if name in ("enet_norm", "enet_projection", "enet_scale"):
         from . import enet
         return getattr(enet, name)

@@ -67,6 +67,8 @@ KEEP_PY = [
     "modl/utils/recsys/__init__.py",
     "modl/utils/recsys/cross_validation.py",
     "modl/input_data/image.py",
+    "modl/feature_extraction/__init__.py",
+    "modl/feature_extraction/image.py",
 ]
 EMPTY_INIT = [
     "modl/__init__.py",
@@ -78,6 +80,7 @@ EMPTY_INIT = [
 def built(dest=DEST):
     need = [
         "modl/decomposition/dict_fact.py",
+        "modl/feature_extraction/image.py",
     ]
     if not all(os.path.exists(os.path.join(dest, n)) for n in need):
         return False

@@ -195,9 +195,71 @@ def gold_fit():
     save("fit.npz", **out)
 
 
+def gold_image():
+    """ImageDictFact / LazyCleanPatchExtractor / scale_patches of the reference.
+    The reference's patch extractor imports `sklearn.feature_extraction.image.extract_patches`, which newer
+    scikit-learn only ships as `_extract_patches`; the alias below is the one-line shim that lets the
+    UNMODIFIED reference modules import."""
+    import json
+    import sklearn.feature_extraction.image as skimg
+    if not hasattr(skimg, "extract_patches"):
+        skimg.extract_patches = skimg._extract_patches
+    from modl.decomposition.image import ImageDictFact
+    from modl.feature_extraction.image import LazyCleanPatchExtractor
+    from modl.input_data.image import scale_patches
+
+    rng = np.random.RandomState(3)
+    img_a = rng.rand(26, 22, 3)                               # clean, float64
+    img_b = rng.rand(20, 20, 6)                               # missing values, 6 channels > patch width 4
+    for (r, c, ch) in ((3, 4, 0), (10, 11, 2), (15, 2, 3), (7, 16, 5), (18, 18, 4)):
+        img_b[r, c, ch] = -1
+    out = {"img_a": img_a, "img_b": img_b}
+    # extractor: selection, shuffles, patches
+    for tag, img, kw in (("a", img_a, dict(patch_size=(4, 4), max_patches=None)),
+                         ("b", img_b, dict(patch_size=(4, 4), max_patches=120)),
+                         ("c", img_a, dict(patch_size=None, max_patches=50))):
+        ex = LazyCleanPatchExtractor(random_state=5, **kw).fit(img.copy())
+        out["ex_%s_idx" % tag] = np.asarray(ex.indices_3d).copy()
+        out["ex_%s_first" % tag] = np.asarray(ex.partial_transform(batch=7)).copy()
+        ex.shuffle()
+        out["ex_%s_idx_shuffled" % tag] = np.asarray(ex.indices_3d).copy()
+        out["ex_%s_slice" % tag] = np.asarray(ex.partial_transform(batch=slice(3, 12))).copy()
+    pat = np.asarray(LazyCleanPatchExtractor(random_state=5, patch_size=(4, 4)).fit(img_a.copy()).partial_transform(batch=9))
+    for mean in (True, False):
+        out["scaled_mean%d" % mean] = scale_patches(pat, with_mean=mean, with_std=True, copy=True)
+    # whole fits
+    cases = [
+        dict(img="a", kw=dict(method="masked", setting="dictionary learning", reduction=2, n_epochs=2)),
+        dict(img="a", kw=dict(method="gram", setting="NMF", reduction=3, n_epochs=2)),
+        dict(img="a", kw=dict(method="reducing ratio", setting="dictionary learning", reduction=4, n_epochs=3)),
+        dict(img="a", kw=dict(method="average", setting="dictionary learning", reduction=2, n_epochs=2)),
+        dict(img="a", kw=dict(method="dictionary only", setting="NMF", reduction=2, n_epochs=1)),
+        dict(img="a", kw=dict(method="sgd", setting="dictionary learning", n_epochs=1, step_size=1e-2)),
+        dict(img="b", kw=dict(method="masked", setting="dictionary learning", reduction=2, n_epochs=2, max_patches=150)),
+        dict(img="a", dtype="float32", kw=dict(method="masked", setting="dictionary learning", reduction=2, n_epochs=2,
+                                                buffer_size=64)),
+    ]
+    common = dict(patch_size=(4, 4), batch_size=10, n_components=8, alpha=0.1, random_state=0)
+    for ci, case in enumerate(cases):
+        img = out["img_" + case["img"]].astype(case.get("dtype", "float64"))
+        est = ImageDictFact(**common, **case["kw"]).fit(img.copy())
+        out["fit_%d_components" % ci] = est.components_.copy()
+        out["fit_%d_n_iter" % ci] = np.array(est.n_iter_)
+        test = np.asarray(LazyCleanPatchExtractor(random_state=9, patch_size=(4, 4), max_patches=30).fit(img.copy()).transform())
+        out["fit_%d_test" % ci] = test
+        out["fit_%d_code" % ci] = est.transform(test)
+        out["fit_%d_score" % ci] = np.array(est.score(test))
+    out["cases"] = np.array(json.dumps(dict(common=common, cases=cases)))
+    save("image.npz", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "image":
+        gold_image()
+        sys.exit(0)
     gold_rng()
     gold_enet()
     gold_regression()
     gold_update_dict()
     gold_fit()
+    gold_image()
