@@ -21,10 +21,10 @@ static int cd_launch_inst(modl_ctx *ctx, const T *G, int64_t g_stride, const T *
         if (warps > 16) warps = 16;
         grid = (int)ceil_div(b, warps);
         if (grid > ctx->sm_count) grid = ctx->sm_count;
-        static bool configured = false;     // per instantiation; the attribute is per function, not per call
-        if (!configured) {
+        static bool configured[64] = {};    // per instantiation and device; the attribute is per function, not per call
+        if (ctx->device < 0 || ctx->device >= 64 || !configured[ctx->device]) {
             MODL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
+            if (ctx->device >= 0 && ctx->device < 64) configured[ctx->device] = true;
         }
         // tile-packed lower triangle of G in global memory, pulled by TMA bulk copies
         T *packed = nullptr;

@@ -72,10 +72,10 @@ int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M
     if (P.stages > TC_MAX_STAGES) P.stages = TC_MAX_STAGES;
     MODL_REQUIRE(P.stages >= 2, "tc_gemm tile does not fit shared memory");
     const size_t smem_bytes = (size_t)P.stages * stage_bytes + 1024;
-    static size_t configured = 0;
-    if (configured < smem_bytes) {
+    static bool configured[64] = {};        // per device: function attributes are per device
+    if (ctx->device < 0 || ctx->device >= 64 || !configured[ctx->device]) {
         MODL_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET));
-        configured = TC_SMEM_BUDGET;
+        if (ctx->device >= 0 && ctx->device < 64) configured[ctx->device] = true;
     }
     const int64_t tiles = tc_row_blocks(M) * tc_row_blocks(N, bn);
     // split the contraction until the grid covers the SMs (one CTA per SM: 193 KB of shared memory each)

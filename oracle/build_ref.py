@@ -60,6 +60,7 @@ KEEP_PY = [
     "modl/decomposition/dict_fact.py",
     "modl/decomposition/recsys.py",
     "modl/decomposition/image.py",
+    "modl/decomposition/fmri.py",
     "modl/decomposition/stability.py",
     "modl/utils/__init__.py",
     "modl/utils/math/__init__.py",
