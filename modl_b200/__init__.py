@@ -22,6 +22,9 @@ def __getattr__(name):
     if name in ("ImageDictFact", "LazyCleanPatchExtractor", "scale_patches", "DictionaryScorer"):
         from . import image
         return getattr(image, name)
+    if name in ("fMRIDictFact", "fMRICoder", "RecordMasker", "rfMRIDictionaryScorer"):
+        from . import fmri
+        return getattr(fmri, name)
     if name in ("enet_norm", "enet_projection", "enet_scale"):
         from . import enet
         return getattr(enet, name)

@@ -390,6 +390,13 @@ class DictFact(CodingMixin, BaseEstimator):
                 self.__dict__["_d_G_"] = G
             self.G_agg = 'full'
         BaseEstimator.set_params(self, **params)
+        # A switch to Dx_agg='average' after prepare() (the 'gram' schedules of the front-ends,
+        # image.py:142-144, fmri.py:497-499) finds no Dx_average_ in the reference and raises there;
+        # here the running average starts from zero, as prepare() would have left it.
+        if self.Dx_agg == 'average' and self.__dict__.get("_d_code_") is not None \
+                and self.__dict__.get("_d_Dx_average_") is None:
+            code = self._d_code_
+            self.__dict__["_d_Dx_average_"] = torch.zeros(code.shape, dtype=code.dtype, device=code.device)
 
     def shuffle(self):
         """Shuffle the per-sample state with one permutation and return it

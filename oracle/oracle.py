@@ -366,7 +366,18 @@ class OracleDictFact(object):
             self._single_batch_fit(X[sl], get_sub_slice(sample_indices, sl))
         return self
 
-    # -- shuffle: dict_fact.py:359-379 --
+    # -- set_params: dict_fact.py:339-357 (only a switch to G_agg='full' is honoured for G_agg) --
+    def set_params(self, **params):
+        G_agg = params.pop('G_agg', None)
+        if G_agg == 'full' and self.G_agg != 'full':
+            if hasattr(self, 'components_'):
+                self.G_ = self.components_.dot(self.components_.T)
+            self.G_agg = 'full'
+        for key, value in params.items():
+            if key not in self.__dict__:
+                raise ValueError('Invalid parameter %s' % key)
+            setattr(self, key, value)
+
     def shuffle(self):
         seed = self.random_state.randint(MAX_INT)
         rs = RandomState(seed)

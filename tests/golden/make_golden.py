@@ -253,9 +253,134 @@ def gold_image():
     save("image.npz", **out)
 
 
+def _stub_neuroimaging_stack():
+    """`modl/decomposition/fmri.py` imports nibabel, nilearn and `sklearn.externals.joblib`, none of which this
+    image has.  The fMRI row is the learning loop `_compute_components` (fmri.py:423-546),
+    which only needs: `ImageFileError` (raised by `check_niimg` for a `.npy` record so that `_lazy_scan` takes
+    its `np.load` branch, fmri.py:564-572), `check_niimg(mask).get_data()`, and a fitted masker with
+    `transform(img, confounds)`.  The stubs below provide exactly that much; fmri.py itself runs UNMODIFIED."""
+    import types
+    import joblib
+
+    class ImageFileError(Exception):
+        pass
+
+    class MaskImg(object):
+        def __init__(self, mask):
+            self._mask = np.asarray(mask)
+
+        def get_data(self):
+            return self._mask
+
+    def check_niimg(img):
+        if isinstance(img, MaskImg):
+            return img
+        raise ImageFileError("not a Niimg: %r" % (img,))
+
+    class CacheMixin(object):
+        def _cache(self, func, **kwargs):
+            return func
+
+    class Memory(object):
+        def __init__(self, *args, **kwargs):
+            pass
+
+    class NiftiMasker(object):
+        """Masker over pre-masked records: a record is a `.npy` file (n_samples, n_voxels)."""
+        def __init__(self, mask_img=None, **kwargs):
+            self.mask_img = mask_img
+
+        def fit(self, imgs=None):
+            self.mask_img_ = self.mask_img
+            return self
+
+        def _check_fitted(self):
+            assert hasattr(self, "mask_img_")
+
+        def transform(self, img, confounds=None):
+            return np.load(img)
+
+    class BaseNilearnEstimator(object):
+        pass
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    mod("nibabel"); mod("nibabel.filebasedimages", ImageFileError=ImageFileError)
+    mod("nilearn"); mod("nilearn._utils", CacheMixin=CacheMixin, check_niimg=check_niimg)
+    mod("nilearn.input_data", NiftiMasker=NiftiMasker)
+    import sklearn
+    ext = mod("sklearn.externals")
+    ext.joblib = mod("sklearn.externals.joblib", Memory=Memory, Parallel=joblib.Parallel, delayed=joblib.delayed)
+    sklearn.externals = ext
+    mod("modl.input_data.fmri"); mod("modl.input_data.fmri.base", BaseNilearnEstimator=BaseNilearnEstimator)
+    return MaskImg, NiftiMasker
+
+
+FMRI_CASES = [
+    dict(dtype="float64", kw=dict(method="masked", reduction=3, n_epochs=2, alpha=0.05)),
+    dict(dtype="float64", kw=dict(method="gram", reduction=2, n_epochs=7, alpha=0.05)),          # switches at epoch 5
+    dict(dtype="float64", kw=dict(method="reducing ratio", reduction=4, n_epochs=3, alpha=0.05)),
+    dict(dtype="float64", kw=dict(method="average", reduction=2, n_epochs=2, alpha=0.05)),
+    dict(dtype="float64", kw=dict(method="dictionary only", reduction=2, n_epochs=1, alpha=0.05, positive=True)),
+    dict(dtype="float64", kw=dict(method="sgd", n_epochs=1, alpha=0.05, step_size=1e-2)),
+    dict(dtype="float64", init=True, kw=dict(method="masked", reduction=2, n_epochs=1, alpha=0.02, n_components=9)),
+    dict(dtype="float32", kw=dict(method="masked", reduction=3, n_epochs=2, alpha=0.05)),
+]
+
+
+def fmri_records(dtype):
+    """Four 'subjects' of pre-masked records with ragged lengths, from spatially sparse planted maps."""
+    rng = np.random.RandomState(11)
+    n_voxels, k = 150, 5
+    maps = rng.randn(k, n_voxels) * (rng.rand(k, n_voxels) < 0.25)
+    lengths = (23, 17, 30, 20)
+    return [(rng.randn(n, k) @ maps + 0.05 * rng.randn(n, n_voxels)).astype(dtype) for n in lengths], n_voxels
+
+
+def gold_fmri():
+    """`_compute_components` + `_flip` of the reference (fmri.py:423-556) on `.npy` records."""
+    import json
+    import tempfile
+    MaskImg, NiftiMasker = _stub_neuroimaging_stack()
+    from modl.decomposition.fmri import _compute_components, _flip
+    from modl.decomposition.dict_fact import Coder
+    out = {}
+    common = dict(n_components=6, batch_size=8, learning_rate=0.9, random_state=0)
+    for ci, case in enumerate(FMRI_CASES):
+        records, n_voxels = fmri_records(case["dtype"])
+        masker = NiftiMasker(mask_img=MaskImg(np.ones(n_voxels, dtype=bool))).fit()
+        with tempfile.TemporaryDirectory() as tmp:
+            paths = []
+            for ri, rec in enumerate(records):
+                paths.append(os.path.join(tmp, "record_%d.npy" % ri))
+                np.save(paths[-1], rec)
+            kw = dict(common)
+            kw.update(case["kw"])
+            dict_init = None
+            if case.get("init"):
+                dict_init = np.random.RandomState(5).randn(7, n_voxels)     # fewer atoms than n_components asked
+            comp = _compute_components(masker, paths, dict_init=dict_init, **kw)
+        out["fit_%d_components" % ci] = comp
+        coder = Coder(dictionary=comp, code_alpha=kw["alpha"], code_l1_ratio=0).fit()
+        out["fit_%d_code" % ci] = coder.transform(records[0])
+        out["fit_%d_score" % ci] = np.array(coder.score(records[0]))
+    v = np.random.RandomState(2).randn(6, 31)
+    v[3] = 0
+    out["flip_in"], out["flip_out"] = v, _flip(v)
+    out["cases"] = np.array(json.dumps(dict(common=common, cases=FMRI_CASES)))
+    save("fmri.npz", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "image":
         gold_image()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "fmri":
+        gold_fmri()
         sys.exit(0)
     gold_rng()
     gold_enet()
@@ -263,3 +388,4 @@ if __name__ == "__main__":
     gold_update_dict()
     gold_fit()
     gold_image()
+    gold_fmri()
