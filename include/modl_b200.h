@@ -311,6 +311,60 @@ enum { MODL_PHASE_CODE = 1, MODL_PHASE_STATS = 2, MODL_PHASE_APPLY = 4, MODL_PHA
 int modl_batch_fit_f32(modl_ctx *, const modl_step_params *prm, void *stream);
 int modl_batch_fit_f64(modl_ctx *, const modl_step_params *prm, void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * Recsys: the missing-value path   [ref: RecsysDictFact, modl/decomposition/recsys.py:147-213,
+ * :254-265; _predict, modl/decomposition/recsys_fast.pyx:10-37]   
+ *
+ * X is a CSR matrix resident on the device: indptr int64[n+1], indices int32[nnz], data[nnz].
+ * The dictionary is held twice: components (k x p, ldd) for modl_update_dict_*, and its transpose
+ * Dt (p x k, ldt) for the column gathers below; modl_recsys_sync_transposed_* refreshes the rows
+ * `subset` of Dt (all p rows when subset == NULL) after a dictionary update.  1 <= k <= 128.
+ * ---------------------------------------------------------------------------------- */
+
+/* Per-row Gram and correlation over the row's observed columns [ref: _single_sample_update
+ * recsys.py:169-177 and _refit :254-264]:  G[ii] = D_sub D_sub^T + (alpha / reduction) I,
+ * Dx[ii] = D_sub x_sub with reduction = p / len(observed).  Rows: rows[ii] (device int64[b]), or
+ * row0 + ii when rows == NULL.  The solve itself (recsys.py:178, :265) is
+ * modl_enet_regression_multi_gram_* with l1_ratio = 0, alpha = 0 on (G, Dx). */
+int modl_recsys_gram_dx_f32(modl_ctx *, const float *Dt, int64_t ldt, const int64_t *indptr,
+                            const int32_t *indices, const float *data, const int64_t *rows, int64_t row0,
+                            int64_t b, int64_t k, int64_t p, double alpha, float *G, float *Dx, void *stream);
+int modl_recsys_gram_dx_f64(modl_ctx *, const double *Dt, int64_t ldt, const int64_t *indptr,
+                            const int32_t *indices, const double *data, const int64_t *rows, int64_t row0,
+                            int64_t b, int64_t k, int64_t p, double alpha, double *G, double *Dx, void *stream);
+
+/* The B_ update of one minibatch [ref: recsys.py:168, :182-185].  The batch's stored entries are given
+ * ordered by (column, position of the row in the batch): subset int64[s] = the sorted distinct columns
+ * (recsys.py:159-161), col_ptr int64[s+1] their entry ranges, entry_row int64[] the row of code (n x k)
+ * each entry belongs to, entry_val its value.  Per column, in that order:
+ *   feature_n_iter[j] += 1;  w_B = min(1, w * n_iter / feature_n_iter[j]);
+ *   B[:, j] = (1 - w_B) B[:, j] + code[row] * (x * w_B)        (float64 arithmetic, rounded like NumPy's) */
+int modl_recsys_update_B_f32(modl_ctx *, float *B, int64_t ldb, const float *code, const int64_t *subset,
+                             const int64_t *col_ptr, const int64_t *entry_row, const float *entry_val,
+                             int64_t *feature_n_iter, int64_t s, int64_t k, double w, int64_t n_iter, void *stream);
+int modl_recsys_update_B_f64(modl_ctx *, double *B, int64_t ldb, const double *code, const int64_t *subset,
+                             const int64_t *col_ptr, const int64_t *entry_row, const double *entry_val,
+                             int64_t *feature_n_iter, int64_t s, int64_t k, double w, int64_t n_iter, void *stream);
+
+/* C_ = (1 - w) C_ + (w / b) code[rows]^T code[rows]   [ref: recsys.py:156-157]; rows NULL = rows 0..b-1 */
+int modl_recsys_update_C_f32(modl_ctx *, float *C, const float *code, const int64_t *rows, int64_t b, int64_t k,
+                             double w, void *stream);
+int modl_recsys_update_C_f64(modl_ctx *, double *C, const double *code, const int64_t *rows, int64_t b, int64_t k,
+                             double w, void *stream);
+
+/* Dt[subset[j], :] = components[:, subset[j]] (the scatter of recsys.py:213 seen from the transposed copy) */
+int modl_recsys_sync_transposed_f32(modl_ctx *, const float *components, int64_t ldd, float *Dt, int64_t ldt,
+                                    const int64_t *subset, int64_t s, int64_t k, void *stream);
+int modl_recsys_sync_transposed_f64(modl_ctx *, const double *components, int64_t ldd, double *Dt, int64_t ldt,
+                                    const int64_t *subset, int64_t s, int64_t k, void *stream);
+
+/* out[e] = <code[u], components[:, indices[e]]> for the stored entries e of every row u
+ * [ref: _predict, recsys_fast.pyx:10-37]; out is float64 like the reference's X_data. */
+int modl_recsys_predict_f32(modl_ctx *, const float *code, const float *Dt, int64_t ldt, const int64_t *indptr,
+                            const int32_t *indices, int64_t n_rows, int64_t k, double *out, void *stream);
+int modl_recsys_predict_f64(modl_ctx *, const double *code, const double *Dt, int64_t ldt, const int64_t *indptr,
+                            const int32_t *indices, int64_t n_rows, int64_t k, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,11 @@ def _declare(L):
         fn("modl_update_dict_" + sfx, ci, [vp, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, i64, i64,
                                            real, ci, ci, f64, f64, vp])
         fn("modl_batch_fit_" + sfx, ci, [vp, C.POINTER(StepParams), vp])
+        fn("modl_recsys_gram_dx_" + sfx, ci, [vp, vp, i64, vp, vp, vp, vp, i64, i64, i64, i64, f64, vp, vp, vp])
+        fn("modl_recsys_update_B_" + sfx, ci, [vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, i64, f64, i64, vp])
+        fn("modl_recsys_update_C_" + sfx, ci, [vp, vp, vp, vp, i64, i64, f64, vp])
+        fn("modl_recsys_sync_transposed_" + sfx, ci, [vp, vp, i64, vp, i64, vp, i64, i64, vp])
+        fn("modl_recsys_predict_" + sfx, ci, [vp, vp, vp, i64, vp, vp, i64, i64, vp, vp])
 
 
 # every symbol include/modl_b200.h declares (tests check the library exports them all)
@@ -98,7 +103,8 @@ EXPORTED = (
         "modl_enet_norm_", "modl_enet_projection_", "modl_enet_scale_", "modl_gram_dx_",
         "modl_enet_regression_single_gram_", "modl_enet_regression_multi_gram_",
         "modl_update_G_average_", "modl_update_Dx_average_", "modl_update_stats_",
-        "modl_update_dict_", "modl_batch_fit_")])
+        "modl_update_dict_", "modl_batch_fit_", "modl_recsys_gram_dx_", "modl_recsys_update_B_",
+        "modl_recsys_update_C_", "modl_recsys_sync_transposed_", "modl_recsys_predict_")])
 
 _lib = None
 

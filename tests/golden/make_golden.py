@@ -375,9 +375,73 @@ def gold_fmri():
     save("fmri.npz", **out)
 
 
+RECSYS_CASES = [
+    # the reference's own test problems [ref: modl/decomposition/tests/test_recsys.py:13-35, :38-62, :65-92]
+    dict(data="dense", dtype="float64", kw=dict(n_components=3, n_epochs=1, alpha=1e-3, detrend=False)),
+    dict(data="dense", dtype="float64", kw=dict(n_components=3, n_epochs=1, alpha=1e-3, detrend=True)),
+    dict(data="missing", dtype="float64", kw=dict(n_components=4, n_epochs=1, alpha=1, detrend=True)),
+    # minibatches, several epochs, forgetting, cropping, automatic batch size
+    dict(data="ratings", dtype="float64", kw=dict(n_components=5, n_epochs=3, alpha=0.5, batch_size=7,
+                                                   learning_rate=0.8, detrend=True, crop=(1., 5.), beta=2.)),
+    dict(data="ratings", dtype="float64", kw=dict(n_components=6, n_epochs=2, alpha=0.1, batch_size=None)),
+    dict(data="ratings", dtype="float32", kw=dict(n_components=5, n_epochs=2, alpha=1., batch_size=16,
+                                                   learning_rate=0.9)),
+]
+
+
+def recsys_data(name, dtype):
+    import scipy.sparse as sp
+    rng = np.random.RandomState(0)
+    if name == "dense":
+        X = sp.csr_matrix(np.dot(rng.rand(50, 3), rng.rand(3, 20)))
+        return X.astype(dtype), X.astype(dtype)
+    if name == "missing":
+        X = np.dot(rng.rand(100, 4), rng.rand(4, 20))
+        keep = rng.rand(100, 20) < 0.85
+        keep[np.arange(100), rng.randint(20, size=100)] = True          # no empty row
+        return sp.csr_matrix(X * keep).astype(dtype), sp.csr_matrix(X * ~keep).astype(dtype)
+    # ratings-like: 120 users x 60 items, 1..5, 25 % observed, every user rates at least one item
+    U, V = rng.rand(120, 4), rng.rand(4, 60)
+    R = np.clip(np.round(1 + 4 * U.dot(V) / 2.), 1, 5)
+    seen = rng.rand(120, 60) < 0.25
+    seen[np.arange(120), rng.randint(60, size=120)] = True
+    test = ~seen & (rng.rand(120, 60) < 0.1)
+    return sp.csr_matrix(R * seen).astype(dtype), sp.csr_matrix(R * test).astype(dtype)
+
+
+def gold_recsys():
+    """RecsysDictFact of the reference (recsys.py), whole fits + predictions."""
+    import json
+    from modl.decomposition.recsys import RecsysDictFact, compute_biases
+    out = {}
+    for ci, case in enumerate(RECSYS_CASES):
+        X, X_te = recsys_data(case["data"], case["dtype"])
+        kw = dict(case["kw"])
+        if "crop" in kw:
+            kw["crop"] = tuple(kw["crop"])
+        est = RecsysDictFact(random_state=0, **kw).fit(X)
+        tag = "fit_%d_" % ci
+        for name in ("components_", "code_", "C_", "B_", "comp_norm_", "feature_n_iter_", "feature_freq_"):
+            out[tag + name] = np.asarray(getattr(est, name))
+        out[tag + "n_iter_"] = np.array(est.n_iter_)
+        if kw.get("detrend"):
+            out[tag + "row_mean_"], out[tag + "col_mean_"] = est.row_mean_, est.col_mean_
+        if case["dtype"] == "float64":          # the reference's _predict only takes float64 buffers
+            out[tag + "pred_train"] = est.predict(X.astype(np.float64)).data
+            out[tag + "pred_test"] = est.predict(X_te.astype(np.float64)).data
+            out[tag + "score_test"] = np.array(est.score(X_te.astype(np.float64)))
+    X, _ = recsys_data("ratings", "float64")
+    out["bias_row"], out["bias_col"] = compute_biases(X, beta=3., inplace=False)
+    out["cases"] = np.array(json.dumps(RECSYS_CASES))
+    save("recsys.npz", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "image":
         gold_image()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "recsys":
+        gold_recsys()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fmri":
         gold_fmri()
@@ -389,3 +453,4 @@ if __name__ == "__main__":
     gold_fit()
     gold_image()
     gold_fmri()
+    gold_recsys()
