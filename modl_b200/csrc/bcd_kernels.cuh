@@ -413,7 +413,14 @@ bcd_update_kernel(BcdParams<T> P)
             const T R = radius / P.l1_ratio;
             const T *vr = P.vrow + (int64_t)par * s;
             bool ins;
-            const T l = enet_threshold_block<T>([&](int j) { return __ldcg(vr + j); }, s, R, gamma, &ins, dscratch);
+            // the whole candidate row, redundantly in every CTA (no extra grid barrier): held in registers when it
+            // fits (96 floats / 48 doubles per thread), else re-read from L2 on every pass of the fixed point
+            constexpr int NV_BIG = sizeof(T) == 4 ? 96 : 48;
+            auto ld = [&](int j) { return __ldcg(vr + j); };
+            T l;
+            if (s <= 16 * BCD_THREADS) l = enet_threshold_block_regs<T, 16>(ld, s, R, gamma, &ins, dscratch);
+            else if (s <= NV_BIG * BCD_THREADS) l = enet_threshold_block_regs<T, NV_BIG>(ld, s, R, gamma, &ins, dscratch);
+            else l = enet_threshold_block<T>(ld, s, R, gamma, &ins, dscratch);
             if (tid == 0) { sh_inside = ins; sh_l = l; }
             __syncthreads();
             if (!sh_inside) { mode = 2; lthr = sh_l; }
