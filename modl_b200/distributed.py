@@ -61,6 +61,12 @@ class ShardedStepMixin(object):
         self.__dict__["last_subset_"] = subset
         self.__dict__["last_order_"] = order
 
+    def _replicated_step(self, X, sample_indices):
+        """One minibatch processed WHOLE by every rank, without exchange (identical inputs and kernels on every
+        rank, so the replicas stay bit-identical): the un-sharded `_single_batch_fit` of the estimator below this
+        mixin.  Used for ragged minibatches that do not divide over the ranks."""
+        return super(ShardedStepMixin, self)._single_batch_fit(X, sample_indices)
+
     def check_replicas(self):
         """Debug helper: max abs difference of the dictionary across ranks (should be 0.0)."""
         world, _ = self._world()

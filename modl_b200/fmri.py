@@ -30,6 +30,7 @@ from sklearn.utils import check_random_state
 
 from ._util import default_device
 from .dict_fact import Coder, DictFact
+from .distributed import ShardedDictFact
 
 __all__ = ["fMRIDictFact", "fMRICoder", "fMRICoderMixin", "RecordMasker", "rfMRIDictionaryScorer",
            "_compute_components", "_flip", "_lazy_scan", "_check_dict_init"]
@@ -189,23 +190,62 @@ def _flip(components):
 
 
 def _stage_record(masked_data, permutation, dtype, device):
-    """Upload one record and permute its rows there: `masked_data.astype(dtype)[permutation]`
-    [ref: fmri.py:519, 532] as one H2D copy plus one device gather."""
+    """`masked_data.astype(dtype)[permutation]` on the device [ref: fmri.py:519, 532].  A whole record is one H2D
+    copy plus one device gather; a partial row set (one rank's share under sharding) is gathered on the host
+    first, so that only those rows cross PCIe."""
     tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+    permutation = np.asarray(permutation, dtype=np.int64)
     if isinstance(masked_data, torch.Tensor):
         rows = masked_data.to(device=device, dtype=tdt)
+    elif permutation.shape[0] < masked_data.shape[0]:
+        return torch.from_numpy(np.ascontiguousarray(masked_data[permutation], dtype=dtype)).to(device)
     else:
         host = np.ascontiguousarray(masked_data, dtype=dtype)
         rows = torch.from_numpy(host).to(device)
-    return rows.index_select(0, torch.from_numpy(np.asarray(permutation, dtype=np.int64)).to(device))
+    return rows.index_select(0, torch.from_numpy(permutation).to(device))
+
+
+def _sharded_record_fit(dict_fact, masked_data, permutation, sample_indices, batch_size, world, rank, dtype, device):
+    """One record under sample sharding: minibatch m of the permuted record is rows
+    [m b, m b + t); rank g solves the g-th of `world` equal shares and the statistics increments are summed over
+    ranks (`ShardedDictFact`).  A ragged last minibatch whose size does not divide by `world` is run REPLICATED
+    -- every rank processes all of its rows, no exchange -- which keeps the replicas bit-identical without
+    unequal shards.  Sample index = position in the permuted record (fmri.py:528-531 as executed), so a
+    position is always solved by the same rank."""
+    n = permutation.shape[0]
+    plan, mine = [], []
+    for lo in range(0, n, batch_size):
+        t = min(batch_size, n - lo)
+        if t % world == 0:
+            share = t // world
+            pos = np.arange(lo + rank * share, lo + (rank + 1) * share)
+            plan.append((True, pos))
+        else:
+            pos = np.arange(lo, lo + t)
+            plan.append((False, pos))
+        mine.append(pos)
+    mine = np.concatenate(mine)
+    rows = _stage_record(masked_data, permutation[mine], dtype, device)      # this rank's rows only, one upload
+    at = 0
+    for shard, pos in plan:
+        X = rows[at:at + pos.shape[0]]
+        at += pos.shape[0]
+        idx = pos if sample_indices is None else sample_indices[pos]
+        if shard:
+            dict_fact.partial_fit(X, sample_indices=idx)                     # <= local batch rows: exactly one step
+        else:
+            dict_fact._replicated_step(X, idx)
 
 
 def _compute_components(masker, imgs, step_size=1, confounds=None, dict_init=None, alpha=1, positive=False,
                         reduction=1, learning_rate=1, n_components=20, batch_size=20, n_epochs=1,
                         method='masked', verbose=0, random_state=None, callback=None, n_jobs=1, device=None,
-                        return_estimator=False, intended_schedules=False):
+                        return_estimator=False, intended_schedules=False, sharded=False, process_group=None):
     """The learning loop [ref: fmri.py:423-546], same signature plus `device`, `return_estimator` (also hand
-    back the fitted `DictFact`) and `intended_schedules`.
+    back the fitted `DictFact`), `intended_schedules`, and `sharded` / `process_group`: with
+    `torch.distributed` initialised, every rank calls this function with the SAME arguments and seed; each
+    minibatch of `batch_size` volumes is split over the ranks (`_sharded_record_fit`), every rank returns the
+    same maps, and the result equals the single-process one up to the summation order of the all-reduce.
 
     The reference rebinds `method` to its table entry (`method = methods[method]`, fmri.py:459), so the three
     string tests that follow (:497 'gram' switch, :500 'reducing ratio' schedule, :528 per-record
@@ -238,10 +278,24 @@ def _compute_components(masker, imgs, step_size=1, confounds=None, dict_init=Non
 
     if verbose:
         print("Learning...")
-    dict_fact = DictFact(n_components=n_components, code_alpha=alpha, code_l1_ratio=0, comp_l1_ratio=1,
-                         comp_pos=positive, reduction=reduction, Dx_agg=Dx_agg, optimizer=optimizer,
-                         step_size=step_size, G_agg=G_agg, learning_rate=learning_rate, batch_size=batch_size,
-                         random_state=random_state, n_threads=n_jobs, verbose=0, device=device)
+    kw = dict(n_components=n_components, code_alpha=alpha, code_l1_ratio=0, comp_l1_ratio=1, comp_pos=positive,
+              reduction=reduction, Dx_agg=Dx_agg, optimizer=optimizer, step_size=step_size, G_agg=G_agg,
+              learning_rate=learning_rate, batch_size=batch_size, random_state=random_state, n_threads=n_jobs,
+              verbose=0, device=device)
+    world, rank = 1, 0
+    if sharded:
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("sharded=True needs an initialised torch.distributed process group")
+        world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        if batch_size % world:
+            raise ValueError("batch_size=%d does not divide over %d ranks" % (batch_size, world))
+        if 'average' in (G_agg, Dx_agg) or intended_schedules:
+            raise NotImplementedError("per-sample running averages are owned by row; not available under sharding")
+        kw.update(batch_size=batch_size // world, process_group=process_group)
+        dict_fact = ShardedDictFact(**kw)
+    else:
+        dict_fact = DictFact(**kw)
     dict_fact.prepare(n_samples=n_samples, n_features=n_voxels, X=dict_init, dtype=dtype)
     stage_device = getattr(dict_fact, '_device', None) or (torch.device(device) if device is not None else default_device())
     cpu_time = 0
@@ -279,8 +333,12 @@ def _compute_components(masker, imgs, step_size=1, confounds=None, dict_init=Non
                     sample_indices = np.arange(indices_list[record], indices_list[record + 1])[permutation]
                 else:
                     sample_indices = None
-                dict_fact.partial_fit(_stage_record(masked_data, permutation, dtype, stage_device),
-                                      sample_indices=sample_indices)
+                if sharded:
+                    _sharded_record_fit(dict_fact, masked_data, permutation, sample_indices, batch_size, world, rank,
+                                        dtype, stage_device)
+                else:
+                    dict_fact.partial_fit(_stage_record(masked_data, permutation, dtype, stage_device),
+                                          sample_indices=sample_indices)
                 current_n_records += 1
                 cpu_time += time.perf_counter() - t0
     components = _flip(dict_fact.components_)

@@ -37,26 +37,31 @@ def _make_problem(dtype):
 KW = dict(reduction=3, code_alpha=0.05, code_l1_ratio=0.9, random_state=0)
 
 
-def _worker(rank, world, port, dtype_name, out_dir):
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+def _cpu_sharded_class():
+    """ShardedStepMixin driving the oracle's numerics instead of the CUDA phases."""
     import oracle as orc
     from modl_b200.dict_fact import DictFact
     from modl_b200.distributed import ShardedStepMixin
 
-    dtype = np.dtype(dtype_name)
-
     class CpuSharded(ShardedStepMixin, orc.OracleDictFact):
-        """ShardedStepMixin driving the oracle's numerics instead of the CUDA phases."""
         _host_bookkeeping = DictFact._host_bookkeeping
+
+        def __init__(self, process_group=None, device=None, **kw):
+            orc.OracleDictFact.__init__(self, **kw)
+            self.process_group = process_group
 
         def prepare(self, **kw):
             orc.OracleDictFact.prepare(self, **kw)
             self._np_dtype = self.components_.dtype
             return self
+
+        def partial_fit(self, X, sample_indices=None):
+            X = X.numpy() if isinstance(X, torch.Tensor) else X
+            return orc.OracleDictFact.partial_fit(self, X, sample_indices)
+
+        def _replicated_step(self, X, sample_indices):
+            X = X.numpy() if isinstance(X, torch.Tensor) else X
+            return orc.OracleDictFact._single_batch_fit(self, np.ascontiguousarray(X), sample_indices)
 
         def _callback(self):
             pass
@@ -78,8 +83,32 @@ def _worker(rank, world, port, dtype_name, out_dir):
             self.B_ += inc[k * k:].reshape(k, p)
             D_sub = np.ascontiguousarray(self.components_[:, subset])
             grad = np.ascontiguousarray(self.B_[:, subset])
+            full, small = self.G_agg == 'full', subset.shape[0] < p / 2.
+            if full and small:                                # G_ down/up-date [ref: dict_fact.py:667-668, 711-715]
+                self.G_ -= D_sub.dot(D_sub.T)
             orc.update_dict_panel(D_sub, grad, self.C_, self.comp_norm_, order, self.comp_l1_ratio, self.comp_pos)
             self.components_[:, subset] = D_sub
+            if full:
+                if small:
+                    self.G_ += D_sub.dot(D_sub.T)
+                else:
+                    self.G_[:] = self.components_.dot(self.components_.T)
+
+    return CpuSharded
+
+
+def _init(rank, world, port):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+
+def _worker(rank, world, port, dtype_name, out_dir):
+    _init(rank, world, port)
+    CpuSharded = _cpu_sharded_class()
+    dtype = np.dtype(dtype_name)
 
     X, k = _make_problem(dtype)
     b_local = 8
@@ -129,3 +158,43 @@ def test_sharded_step_equals_single_process(tmp_path, oracle, dtype_name):
     assert err(got["B"], ref.B_) < tol
     solved = slice(0, (X.shape[0] // 16) * 16)
     assert err(got["code"][solved], ref.code_[solved]) < tol
+
+
+# ------------------------------------------------------------------------------------------------ fMRI loop
+def _fmri_worker(rank, world, port, case_index, out_dir):
+    _init(rank, world, port)
+    import json
+    from modl_b200 import fmri
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_fmri_frontend import _records
+    fmri.ShardedDictFact = _cpu_sharded_class()            # the oracle's numerics under the real sharding logic
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "fmri.npz"))
+    spec = json.loads(str(gold["cases"]))
+    case = spec["cases"][case_index]
+    records, n_voxels = _records(case["dtype"])
+    masker = fmri.RecordMasker(mask=np.ones(n_voxels, dtype=bool)).fit()
+    kw = dict(spec["common"])
+    kw.update(case["kw"])
+    comp = fmri._compute_components(masker, records, device="cpu", sharded=True, **kw)
+    D = torch.from_numpy(np.ascontiguousarray(comp))
+    lo_, hi_ = D.clone(), D.clone()
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "fmri_%d.npz" % case_index), D=comp, spread=float((hi_ - lo_).abs().max()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case_index", [0, 4, 7])       # masked f64, dictionary only + positive maps, masked f32
+def test_sharded_fmri_loop_equals_the_reference(tmp_path, oracle, case_index):
+    """`_compute_components(sharded=True)` on two ranks: minibatches of 8 volumes split 4 + 4, the ragged tails of
+    the 23- and 17-volume records (7 and 1 rows) replicated, those of the 30- and 20-volume ones (6 and 4) split;
+    every rank ends with the same maps, equal to what the unmodified reference computes in one process."""
+    world = 2
+    mp.spawn(_fmri_worker, args=(world, _free_port(), case_index, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(os.path.join(str(tmp_path), "fmri_%d.npz" % case_index))
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "fmri.npz"))
+    want = gold["fit_%d_components" % case_index]
+    assert float(got["spread"]) == 0.0
+    err = float(np.linalg.norm(got["D"].astype(np.float64) - want) / np.linalg.norm(want))
+    assert err < (1e-9 if want.dtype == np.float64 else 2e-3), err
