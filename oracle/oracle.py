@@ -10,7 +10,9 @@ Two layers:
     estimator imports (modl/decomposition/dict_fact.py:13-18);
   * `OracleDictFact`, a NumPy restatement of the estimator state machine
     (modl/decomposition/dict_fact.py:286-715): prepare / partial_fit / the
-    per-minibatch step / transform / score / shuffle.
+    per-minibatch step / transform / score / shuffle;
+  * `OracleRecsysDictFact`, the same for the matrix-completion estimator
+    (modl/decomposition/recsys.py, recsys_fast.pyx).
 """
 import ctypes as C
 import os
@@ -519,3 +521,131 @@ class OracleDictFact(object):
         n2 = np.sum(code ** 2)
         regul = self.code_alpha * (n1 * self.code_l1_ratio + (1 - self.code_l1_ratio) * n2 / 2)
         return (loss + regul) / X.shape[0]
+
+
+# ---------------------------------------------------------------------------------------
+# Matrix completion: RecsysDictFact (modl/decomposition/recsys.py:16-265,
+# modl/decomposition/recsys_fast.pyx:10-37).  A different algorithm from the estimator above:
+# per-row ridge solves over the row's observed columns, per-row scaled rank-1 B_ updates with
+# per-feature counters, dictionary update with a plain L2-ball projection on the union of the
+# batch's observed columns.  Pinned by tests/golden/recsys.npz (tests/test_oracle.py).
+# ---------------------------------------------------------------------------------------
+class OracleRecsysDictFact(object):
+    def __init__(self, alpha=1.0, beta=.0, n_components=30, learning_rate=1., batch_size=1,
+                 n_epochs=1, random_state=None, detrend=False, crop=None):
+        self.__dict__.update({k: v for k, v in locals().items() if k != 'self'})
+
+    @staticmethod
+    def _row(X, i):
+        lo, hi = X.indptr[i], X.indptr[i + 1]
+        return X.indices[lo:hi], X.data[lo:hi]
+
+    def _solve_row(self, X, i):
+        """recsys.py:169-178 (and :256-265): ridge code of row i over its observed columns."""
+        cols, vals = self._row(X, i)
+        D_obs = self.components_[:, cols]
+        gram = D_obs.dot(D_obs.T)
+        gram[np.diag_indices_from(gram)] += self.alpha / (X.shape[1] / cols.shape[0])
+        self.code_[i] = np.linalg.solve(gram, D_obs.dot(vals))
+
+    def fit(self, X):
+        import scipy.sparse as sp
+        X = sp.csr_matrix(X, copy=True)
+        n, p = X.shape
+        k = self.n_components
+        dtype = X.dtype
+        rng = _check_random_state(self.random_state)
+        if self.detrend:                                           # recsys.py:105-111
+            self.row_mean_, self.col_mean_ = recsys_biases(X, self.beta)
+            X.data -= np.repeat(self.row_mean_, np.diff(X.indptr))
+            X.data -= self.col_mean_[X.indices]
+        D = rng.randn(k, p).astype(dtype)                          # :113-116
+        D /= np.sqrt(np.sum(D ** 2, axis=1))[:, None]
+        self.components_ = D
+        self.code_ = np.zeros((n, k), dtype=dtype)
+        for i in range(n):                                         # _refit, :254-265
+            self._solve_row(X, i)
+        self.feature_n_iter_ = np.zeros(p, dtype=np.int64)
+        bs = self.batch_size
+        if bs is None:                                             # :123-127
+            bs = int(np.ceil(1. / (X.nnz / n / p)))
+        self.comp_norm_ = np.zeros(k, dtype=dtype)
+        self.C_ = np.zeros((k, k), dtype=dtype)
+        self.B_ = np.zeros((k, p), dtype=dtype)
+        self.n_iter_ = 0
+        for _ in range(self.n_epochs):                             # :139-143
+            perm = rng.permutation(n)
+            for lo in range(0, n, bs):
+                self._step(X, perm[lo:lo + bs], rng)
+        for i in range(n):
+            self._solve_row(X, i)
+        return self
+
+    def _step(self, X, rows, rng):
+        """One minibatch, recsys.py:151-213."""
+        b = rows.shape[0]
+        self.n_iter_ += b
+        w = batch_weight(self.n_iter_, b, self.learning_rate, 0)
+        for i in rows:                                             # _single_sample_update, :164-185
+            cols, vals = self._row(X, i)
+            self.feature_n_iter_[cols] += 1
+            self._solve_row(X, i)
+            w_B = np.minimum(1, w * self.n_iter_ / self.feature_n_iter_[cols])
+            self.B_[:, cols] *= 1 - w_B
+            self.B_[:, cols] += np.outer(self.code_[i], vals * w_B)
+        batch_code = self.code_[rows]
+        self.C_ *= 1 - w
+        self.C_ += w / b * batch_code.T.dot(batch_code)
+        union = np.unique(np.concatenate([self._row(X, i)[0] for i in rows]))
+        # _update_dict, :187-213: sequential atoms, L2 ball of squared radius comp_norm_[a]
+        D_sub = self.components_[:, union]
+        resid = self.B_[:, union] - self.C_.dot(D_sub)
+        order = rng.permutation(self.n_components)
+        self.comp_norm_ += np.sum(D_sub ** 2, axis=1)
+        for a in order:
+            resid += np.outer(self.C_[a], D_sub[a])
+            if self.C_[a, a] > 1e-20:
+                D_sub[a] = resid[a] / self.C_[a, a]
+            length, limit = np.sqrt(np.sum(D_sub[a] ** 2)), np.sqrt(self.comp_norm_[a])
+            if length > limit:
+                D_sub[a] /= length / limit
+            resid -= np.outer(self.C_[a], D_sub[a])
+        self.comp_norm_ -= np.sum(D_sub ** 2, axis=1)
+        self.components_[:, union] = D_sub
+
+    def predict_data(self, X):
+        """Values at the stored entries of X (recsys.py:215-244 with recsys_fast.pyx:10-37), as a data array."""
+        import scipy.sparse as sp
+        X = sp.csr_matrix(X)
+        out = np.zeros(X.nnz, dtype=np.float64)
+        for u in range(X.shape[0]):
+            for e in range(X.indptr[u], X.indptr[u + 1]):
+                dot = 0.
+                for a in range(self.n_components):
+                    dot += float(self.code_[u, a]) * float(self.components_[a, X.indices[e]])
+                out[e] = dot
+        if self.detrend:
+            out += np.repeat(self.row_mean_, np.diff(X.indptr))
+            out += self.col_mean_[X.indices]
+        if self.crop is not None:
+            np.clip(out, self.crop[0], self.crop[1], out=out)
+        return out
+
+
+def recsys_biases(X, beta=0):
+    """Row / column offsets by two rounds of alternating centring (recsys.py:268-303)."""
+    import scipy.sparse as sp
+    X = sp.csr_matrix(X, copy=True)
+    lens = np.diff(X.indptr)
+    n_row = np.maximum(X.getnnz(axis=1), 1)
+    n_col = np.maximum(X.getnnz(axis=0), 1)
+    row_off, col_off = np.zeros(X.shape[0]), np.zeros(X.shape[1])
+    mean = np.mean(X.data)
+    for _ in range(2):
+        r = (np.asarray(X.sum(axis=1))[:, 0] + mean * beta) / (n_row + beta)
+        X.data -= np.repeat(r, lens)
+        c = np.asarray(X.sum(axis=0))[0] / (n_col + beta)
+        X.data -= c[X.indices]
+        row_off += r
+        col_off += c
+    return row_off, col_off

@@ -200,3 +200,27 @@ def test_oracle_vs_compiled_reference(oracle, reference):
     assert rel_err(b.components_, a.components_) < 1e-4
     assert rel_err(b.code_, a.code_) < 1e-4
     np.testing.assert_array_equal(a.labels_, b.labels_)
+
+
+def test_golden_recsys(oracle, golden):
+    """OracleRecsysDictFact against whole fits of the unmodified reference (tests/golden/recsys.npz)."""
+    import json
+    from test_recsys import _data
+    g = golden("recsys.npz")
+    for ci, case in enumerate(json.loads(str(g["cases"]))):
+        X, X_te = _data(case["data"], case["dtype"])
+        kw = {k: v for k, v in case["kw"].items()}
+        if "crop" in kw:
+            kw["crop"] = tuple(kw["crop"])
+        est = oracle.OracleRecsysDictFact(random_state=0, **kw).fit(X)
+        tag = "fit_%d_" % ci
+        tol = 1e-10 if case["dtype"] == "float64" else 1e-4
+        assert est.n_iter_ == int(g[tag + "n_iter_"])
+        np.testing.assert_array_equal(est.feature_n_iter_, g[tag + "feature_n_iter_"])
+        for name in ("components_", "code_", "C_", "B_"):
+            assert rel_err(getattr(est, name), g[tag + name]) < tol, (ci, name)
+        if case["dtype"] == "float64":
+            assert rel_err(est.predict_data(X_te), g[tag + "pred_test"]) < tol
+    row, col = oracle.recsys_biases(_data("ratings", "float64")[0], beta=3.)
+    np.testing.assert_allclose(row, g["bias_row"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(col, g["bias_col"], rtol=1e-13, atol=1e-15)
