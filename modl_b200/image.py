@@ -85,8 +85,10 @@ class LazyCleanPatchExtractor(BaseEstimator):
         n_p, n_q = i_h - ph + 1, i_w - pw + 1
         missing = img == -1
         if not bool(missing.any()):
-            # fill(p, q, 1): every position, row-major [ref: image_fast.pyx:59-74]
-            pp, qq = np.divmod(np.arange(n_p * n_q, dtype=np.int64), n_q)
+            # fill(p, q, 1): every position, row-major [ref: image_fast.pyx:59-74].  Position j is (j // n_q, j % n_q),
+            # so only the selected ones are materialised (there are 16.6 M for a 4096 x 4096 image).
+            selection = self.random_state.permutation(n_p * n_q)[:self.max_patches]
+            pp, qq = np.divmod(selection.astype(np.int64), n_q)
         else:
             # clean_mask [ref: image_fast.pyx:12-57]: a patch is dropped when a missing value falls inside it.
             # The reference's channel loop bounds its window with the patch WIDTH (`rr - y + 1`, :45), so only
@@ -95,10 +97,9 @@ class LazyCleanPatchExtractor(BaseEstimator):
             dirty = torch.nn.functional.max_pool2d(bad, kernel_size=(ph, pw), stride=1)[0, 0] > 0
             keep = (~dirty).cpu().numpy()
             pp, qq = np.nonzero(keep)                       # row-major, like the nested loops
-        indices = np.stack([pp, qq, np.zeros_like(pp)], axis=1).astype(np.int64)
-        n_samples = indices.shape[0]
-        selection = self.random_state.permutation(n_samples)[:self.max_patches]
-        self.indices_3d = indices[selection]
+            selection = self.random_state.permutation(pp.shape[0])[:self.max_patches]
+            pp, qq = pp[selection], qq[selection]
+        self.indices_3d = np.stack([pp, qq, np.zeros_like(pp)], axis=1).astype(np.int64)
         ar_h = torch.arange(ph, device=dev)
         ar_w = torch.arange(pw, device=dev)
         self._offsets = (ar_h[None, :, None], ar_w[None, None, :])
