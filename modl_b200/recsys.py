@@ -115,7 +115,7 @@ class RecsysDictFact(BaseEstimator):
 
     def __init__(self, alpha=1.0, beta=.0, n_components=30, learning_rate=1., batch_size=1, dict_init=None,
                  l1_ratio=0, n_epochs=1, random_state=None, verbose=0, detrend=False, crop=None, callback=None,
-                 device=None):
+                 device=None, bookkeeping='batch'):
         self.callback = callback
         self.verbose = verbose
         self.random_state = random_state
@@ -130,6 +130,10 @@ class RecsysDictFact(BaseEstimator):
         self.detrend = detrend
         self.crop = crop
         self.device = device
+        # 'batch': the entry ordering of a minibatch is built when the minibatch is visited (one device sort and
+        # one host synchronisation per minibatch); 'epoch': built for many minibatches at once (one sort and one
+        # synchronisation per chunk of up to 2**26 entries), which takes the index work off the per-batch path
+        self.bookkeeping = bookkeeping
 
     # ---------------------------------------------------------------- state: device tensors, NumPy views
     def _state(self, name):
@@ -202,10 +206,16 @@ class RecsysDictFact(BaseEstimator):
             log_lim = log(n_samples * self.n_epochs / batch_size, 10)
             self.verbose_iter_ = ((np.logspace(0, log_lim, self.verbose, base=10) - 1) * batch_size).tolist()
 
+        if self.bookkeeping not in ('batch', 'epoch'):
+            raise ValueError("bookkeeping should be 'batch' or 'epoch'")
         for _ in range(self.n_epochs):
             permutation = self.random_state.permutation(n_samples)
-            for batch in gen_batches(n_samples, batch_size):
-                self._single_batch_fit(Xd, permutation[batch])
+            if self.bookkeeping == 'epoch':
+                for entries in self._epoch_entries(Xd, permutation, batch_size):
+                    self._batch_step(Xd, *entries)
+            else:
+                for batch in gen_batches(n_samples, batch_size):
+                    self._single_batch_fit(Xd, permutation[batch])
         self._refit(Xd)
         return self
 
@@ -244,8 +254,57 @@ class RecsysDictFact(BaseEstimator):
         src = src[by_col]
         return rows, subset, col_ptr, rows[pos[by_col]], Xd.data[src]
 
+    def _epoch_entries(self, Xd, permutation, batch_size, max_entries=1 << 26):
+        """`_batch_entries` for every minibatch of an epoch, the index work done for MANY minibatches at once:
+        the stored entries of a chunk of consecutive minibatches are ordered by (minibatch, column, position)
+        with one stable sort of the key `minibatch * n_features + column`; the distinct keys are the subsets
+        of all the minibatches back to back.  Yields the same tuples as `_batch_entries` (the entry arrays
+        are shared by the chunk, `col_ptr` holds offsets into them).  One host synchronisation per chunk."""
+        dev = self._device
+        n_features = Xd.shape[1]
+        permutation = np.ascontiguousarray(permutation, dtype=np.int64)
+        n = permutation.shape[0]
+        starts_all = Xd.indptr_host[permutation]
+        lens_all = Xd.indptr_host[permutation + 1] - starts_all
+        # chunks of whole minibatches holding at most max_entries stored entries (at least one minibatch)
+        per_batch = np.add.reduceat(lens_all, np.arange(0, n, batch_size))
+        chunks, lo, acc = [], 0, 0
+        for j, cnt in enumerate(per_batch):
+            if j > lo and acc + cnt > max_entries:
+                chunks.append((lo, j))
+                lo, acc = j, 0
+            acc += cnt
+        chunks.append((lo, per_batch.shape[0]))
+        for b0, b1 in chunks:
+            p0, p1 = b0 * batch_size, min(n, b1 * batch_size)
+            starts, lens = starts_all[p0:p1], lens_all[p0:p1]
+            total = int(lens.sum())
+            rows = torch.from_numpy(permutation[p0:p1]).to(dev)
+            lens_d = torch.from_numpy(lens).to(dev)
+            first = torch.from_numpy(starts - (np.cumsum(lens) - lens)).to(dev)
+            pos = torch.repeat_interleave(torch.arange(p1 - p0, device=dev), lens_d, output_size=total)
+            src = first[pos] + torch.arange(total, device=dev)
+            key = torch.div(pos, batch_size, rounding_mode='floor') * n_features + Xd.indices[src].to(torch.int64)
+            key, by_key = torch.sort(key, stable=True)
+            ukey, counts = torch.unique_consecutive(key, return_counts=True)
+            ubatch = torch.div(ukey, n_features, rounding_mode='floor')
+            subset_all = ukey - ubatch * n_features
+            col_ptr_all = torch.zeros((ukey.shape[0] + 1,), dtype=torch.int64, device=dev)
+            torch.cumsum(counts, dim=0, out=col_ptr_all[1:])
+            per = torch.bincount(ubatch, minlength=b1 - b0).cpu().numpy()        # the one synchronisation
+            offs = np.concatenate([[0], np.cumsum(per)])
+            src = src[by_key]
+            entry_row, entry_val = rows[pos[by_key]], Xd.data[src]
+            for j in range(b1 - b0):
+                r0, r1 = j * batch_size, min(p1 - p0, (j + 1) * batch_size)
+                yield (rows[r0:r1], subset_all[offs[j]:offs[j + 1]], col_ptr_all[offs[j]:offs[j + 1] + 1],
+                       entry_row, entry_val)
+
     def _single_batch_fit(self, Xd, batch):
         """One minibatch [ref: recsys.py:151-213]."""
+        self._batch_step(Xd, *self._batch_entries(Xd, batch))
+
+    def _batch_step(self, Xd, rows, subset, col_ptr, entry_row, entry_val):
         if self.verbose and self.verbose_iter_ and self.n_iter_ >= self.verbose_iter_[0]:
             print('Iteration %i' % self.n_iter_)
             self.verbose_iter_ = self.verbose_iter_[1:]
@@ -254,11 +313,10 @@ class RecsysDictFact(BaseEstimator):
         n_features = Xd.shape[1]
         code, D, Dt = self._d_code_, self._d_components_, self._d_Dt
         k = code.shape[1]
-        batch_size = batch.shape[0]
+        batch_size = rows.shape[0]
         self.n_iter_ += batch_size
         w = _batch_weight(self.n_iter_, batch_size, self.learning_rate, 0)
 
-        rows, subset, col_ptr, entry_row, entry_val = self._batch_entries(Xd, batch)
         # codes of the batch on the current dictionary (:169-178); independent across rows
         G = torch.empty((batch_size, k, k), dtype=code.dtype, device=code.device)
         Dx = torch.empty((batch_size, k), dtype=code.dtype, device=code.device)

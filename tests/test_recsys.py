@@ -115,12 +115,12 @@ class NumpyKernels(object):
                 o[e] = dot
 
 
-def _check_case(recsys, gold, ci, case, device, tol64, tol32):
+def _check_case(recsys, gold, ci, case, device, tol64, tol32, bookkeeping='batch'):
     X, X_te = _data(case["data"], case["dtype"])
     kw = dict(case["kw"])
     if "crop" in kw:
         kw["crop"] = tuple(kw["crop"])
-    est = recsys.RecsysDictFact(random_state=0, device=device, **kw).fit(X)
+    est = recsys.RecsysDictFact(random_state=0, device=device, bookkeeping=bookkeeping, **kw).fit(X)
     tag = "fit_%d_" % ci
     tol = tol64 if case["dtype"] == "float64" else tol32
     assert est.n_iter_ == int(gold[tag + "n_iter_"])
@@ -174,13 +174,38 @@ def test_no_cpu_fallback():
         recsys.RecsysDictFact(n_components=2, random_state=0, device="cpu").fit(X)
 
 
-def test_host_logic_cpu(gold, monkeypatch):
+@pytest.mark.parametrize("bookkeeping", ["batch", "epoch"])
+def test_host_logic_cpu(gold, monkeypatch, bookkeeping):
     """Whole fits with the NumPy stand-in for the kernels reproduce the reference: the host side (random
-    stream, batches, entry ordering, counters, detrend / crop) is right."""
+    stream, batches, entry ordering -- per minibatch or for a whole epoch at once --, counters, detrend / crop)
+    is right."""
     from modl_b200 import recsys
     monkeypatch.setattr(recsys, "_kernels_for", lambda device, tdt: NumpyKernels(device, tdt))
     for ci, case in enumerate(json.loads(str(gold["cases"]))):
-        _check_case(recsys, gold, ci, case, "cpu", 1e-9, 2e-3)
+        _check_case(recsys, gold, ci, case, "cpu", 1e-9, 2e-3, bookkeeping)
+
+
+@pytest.mark.parametrize("max_entries", [1 << 26, 700, 1])
+def test_epoch_entries_equal_batch_entries_cpu(max_entries):
+    """The epoch-level bookkeeping yields, minibatch by minibatch, exactly what the per-minibatch one builds --
+    also when the epoch is cut into several chunks (small `max_entries`; 1 = one minibatch per chunk)."""
+    from modl_b200 import recsys
+    X, _ = _data("ratings", "float64")
+    est = recsys.RecsysDictFact(n_components=2, random_state=0, device="cpu")
+    est.__dict__["_device"] = torch.device("cpu")
+    Xd = recsys._DeviceCSR(X, torch.float64, torch.device("cpu"))
+    perm = np.random.RandomState(3).permutation(X.shape[0])
+    bs = 7                                                              # 120 rows: 17 minibatches + a ragged one of 1
+    got = list(est._epoch_entries(Xd, perm, bs, max_entries=max_entries))
+    assert len(got) == -(-X.shape[0] // bs)
+    for j, (rows, subset, col_ptr, entry_row, entry_val) in enumerate(got):
+        w_rows, w_subset, w_ptr, w_erow, w_eval = est._batch_entries(Xd, perm[j * bs:(j + 1) * bs])
+        np.testing.assert_array_equal(rows.numpy(), w_rows.numpy())
+        np.testing.assert_array_equal(subset.numpy(), w_subset.numpy())
+        lo, hi = int(col_ptr[0]), int(col_ptr[-1])
+        np.testing.assert_array_equal((col_ptr - lo).numpy(), w_ptr.numpy())
+        np.testing.assert_array_equal(entry_row.numpy()[lo:hi], w_erow.numpy())
+        np.testing.assert_array_equal(entry_val.numpy()[lo:hi], w_eval.numpy())
 
 
 def test_batch_entries_ordering_cpu(monkeypatch):
@@ -300,6 +325,16 @@ def test_recsys_fits_match_the_reference(gold):
             Y = np.dot(est.code_, est.components_)
             np.testing.assert_array_almost_equal(Y, est.predict(X).toarray())
             assert abs(np.sqrt(np.mean((X.toarray() - Y) ** 2)) - est.score(X)) < 1e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="bookkeeping='epoch' was added after the round-1 GPU budget was spent: its host "
+                                        "logic is pinned on CPU, the device run is to be confirmed in round 2")
+def test_recsys_fits_epoch_bookkeeping(gold):
+    _gpu()
+    from modl_b200 import recsys
+    for ci, case in enumerate(json.loads(str(gold["cases"]))):
+        _check_case(recsys, gold, ci, case, None, 1e-8, 5e-3, bookkeeping='epoch')
 
 
 @pytest.mark.gpu
