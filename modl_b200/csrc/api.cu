@@ -97,6 +97,7 @@ int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "tc_gemm")) ctx->opt_tc_gemm = value;
     else if (!strcmp(name, "bcd_block")) ctx->opt_bcd_block = value;
     else if (!strcmp(name, "bcd_pilot")) ctx->opt_bcd_pilot = value;
+    else if (!strcmp(name, "bcd_coop_min_cols")) ctx->opt_bcd_coop_min_cols = value;
     else { set_error("unknown option %s", name); return MODL_EINVAL; }
     return MODL_OK;
 }

@@ -116,7 +116,9 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
     }
     // 2) cooperative launch over the SMs with a global barrier
     if (!nblk) {
-        int64_t want = ceil_div(s, 32);
+        // one CTA per >= 32 columns by default; "bcd_coop_min_cols" trades row-product parallelism (tiny: k x ncp FMAs
+        // per atom and CTA) for fewer participants at the per-atom grid barrier
+        int64_t want = ceil_div(s, ctx->opt_bcd_coop_min_cols > 32 ? ctx->opt_bcd_coop_min_cols : 32);
         if (want > ctx->sm_count) want = ctx->sm_count;
         if (want < 1) want = 1;
         cols = ceil_div(s, want);
