@@ -338,6 +338,29 @@ def test_recsys_fits_epoch_bookkeeping(gold):
 
 
 @pytest.mark.gpu
+def test_recsys_config5_width_against_the_oracle(oracle):
+    """BASELINE configs[4] width (10^5 items at Movielens-10M density, k = 50, alpha = 1, batch 10 as in the
+    reference's examples/predict_recsys.py:41-45) on a bounded number of rows: device fit against the CPU oracle
+    (itself pinned to the reference, tests/test_oracle.py::test_golden_recsys); rows hold ~1 340 ratings, i.e.
+    84 tiles of the Gram kernel, and a minibatch touches ~12 000 distinct columns."""
+    _gpu()
+    from modl_b200.recsys import RecsysDictFact
+    rng = np.random.RandomState(7)
+    n, p, k = 48, 100000, 50
+    seen = rng.rand(n, p) < 0.0134
+    U, V = rng.rand(n, 8), rng.rand(8, p)
+    X = sp.csr_matrix(np.where(seen, np.clip(np.round(1 + U.dot(V) + 0.3 * rng.randn(n, p)), 1, 5), 0.))
+    kw = dict(n_components=k, alpha=1., batch_size=10, n_epochs=1, random_state=0)
+    est = RecsysDictFact(**kw).fit(X)
+    orc = oracle.OracleRecsysDictFact(**kw).fit(X)
+    np.testing.assert_array_equal(est.feature_n_iter_, orc.feature_n_iter_)
+    for name in ("components_", "code_", "C_", "B_"):
+        err = rel_err(getattr(est, name), getattr(orc, name))
+        assert err < 1e-9, (name, err)
+    assert rel_err(est.predict(X).data, orc.predict_data(X)) < 1e-9
+
+
+@pytest.mark.gpu
 def test_recsys_completion_beats_centering():
     """[ref: tests/test_recsys.py:65-92] held-out error below that of the bias-only predictor."""
     _gpu()
