@@ -86,7 +86,8 @@ int64_t modl_ctx_launch_count(const modl_ctx *ctx);
  * "cd_warps" (warps per CTA of the CD kernel, 0 = auto), "force_global_gram" (debug),
  * "tc_gemm" (1 = float32 contractions on tcgen05 with the 3xTF32 split, 0 = CUDA-core FFMA GEMM),
  * "bcd_pilot" / "bcd_block" (dictionary-update kernel variants), "bcd_coop_min_cols" (fewest columns per CTA
- * of the grid-wide dictionary update, default 32), "bcd_timing" (debug stamps). */
+ * of the grid-wide dictionary update, default 32), "bcd_flag_barrier" (1 = per-CTA epoch flags instead of one atomic
+ * counter at its grid barrier; off until validated), "bcd_timing" (debug stamps). */
 int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value);
 /* Synchronises `stream`, then returns MODL_ENOTSPD if a Cholesky pivot was non-positive since
  * the last check (LAPACK posv info > 0, which the reference ignores:

@@ -98,6 +98,7 @@ int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "bcd_block")) ctx->opt_bcd_block = value;
     else if (!strcmp(name, "bcd_pilot")) ctx->opt_bcd_pilot = value;
     else if (!strcmp(name, "bcd_coop_min_cols")) ctx->opt_bcd_coop_min_cols = value;
+    else if (!strcmp(name, "bcd_flag_barrier")) ctx->opt_bcd_flag_barrier = value;
     else { set_error("unknown option %s", name); return MODL_EINVAL; }
     return MODL_OK;
 }

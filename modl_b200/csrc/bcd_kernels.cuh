@@ -68,6 +68,8 @@ struct BcdParams {
     int d_in_smem;       // keep the CTA's D slice in shared memory
     int use_cluster;     // 1: DSMEM exchange + hardware cluster barrier, 0: global memory + sense barrier
     unsigned *bar;       // global barrier counter (zero on entry)
+    unsigned *flags;     // [2][nblk] per-CTA epoch flags (zero on entry); used instead of `bar` when flag_barrier != 0
+    int flag_barrier;
     T *part;             // [2][nblk][BCD_NPART]       (global exchange, use_cluster == 0)
     T *vrow;             // [2][s]   candidate rows (elastic-net ball only)
     long long *timing;   // debug: [k][8] clock64 stamps of CTA 0 (NULL = off)
@@ -159,6 +161,37 @@ __device__ __forceinline__ void bcd_wait(bool use_cluster, unsigned *bar, unsign
         }
         __syncthreads();
     }
+}
+
+// Grid barrier without a shared counter ("bcd_flag_barrier"): every CTA owns one flag per atom parity; publishing is a
+// release store of the atom's serial number into the CTA's own flag (no atomics, no contention on one address), waiting
+// is warp 0 polling the nblk flags with ONE coalesced load per round.  The data the flag guards (this CTA's partial
+// sums, its slice of the candidate row) is written before the __syncthreads + fence that precede the store.
+__device__ __forceinline__ void bcd_flag_arrive(unsigned *flags, int par, int nblk, int g, unsigned serial)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(flags + par * nblk + g), "r"(serial) : "memory");
+    }
+}
+__device__ __forceinline__ void bcd_flag_wait(const unsigned *flags, int par, int nblk, unsigned serial)
+{
+    if (threadIdx.x < 32) {
+        const unsigned *f = flags + par * nblk;
+        while (true) {
+            bool ok = true;
+            for (int q = threadIdx.x; q < nblk; q += 32) {
+                unsigned cur;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(cur) : "l"(f + q) : "memory");
+                ok = ok && (cur >= serial);
+            }
+            if (__all_sync(kFullMask, ok)) break;
+            __nanosleep(20);
+        }
+        __threadfence();
+    }
+    __syncthreads();
 }
 
 // dotn[c] = sum_i crow[i] * D[i][c] over ALL rows, for the CTA's columns (all threads
@@ -358,7 +391,10 @@ bcd_update_kernel(BcdParams<T> P)
             }
         }
         BCD_STAMP(1);
-        if (!use_cluster) bcd_arrive(false, P.bar, epoch);
+        if (!use_cluster) {
+            if (P.flag_barrier) bcd_flag_arrive(P.flags, par, nblk, g, (unsigned)oi + 1u);
+            else bcd_arrive(false, P.bar, epoch);
+        }
         BCD_STAMP(2);
 
         // ---------------- S2 (overlaps the barrier): prefetch + next atom's row product ----------------
@@ -377,7 +413,8 @@ bcd_update_kernel(BcdParams<T> P)
             mbar_wait(xbar_addr + 8 * par, (unsigned)((oi >> 1) & 1));
             if (enet) __threadfence();
         } else {
-            bcd_wait(false, P.bar, (unsigned)nblk, epoch);
+            if (P.flag_barrier) bcd_flag_wait(P.flags, par, nblk, (unsigned)oi + 1u);
+            else bcd_wait(false, P.bar, (unsigned)nblk, epoch);
         }
         BCD_STAMP(4);
 

@@ -139,15 +139,18 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
     if (cw > 128) cw = 128;
     P.cols_per_cta = (int)cols; P.chunk = (int)cw; P.d_in_smem = d_in_smem; P.use_cluster = use_cluster;
 
-    // exchange workspace: [barrier 256 B][part 2*nblk*4][vrow 2*s]
+    // exchange workspace: [barrier 256 B][flags 2*nblk u32, padded][part 2*nblk*4][vrow 2*s]
     const size_t n_t = (size_t)(2 * nblk * BCD_NPART) + (size_t)nblk * k + 2 * (size_t)s;
+    const size_t sync_bytes = 256 + (size_t)round_up(2 * nblk * (int64_t)sizeof(unsigned), 256);
     unsigned char *base = nullptr;
-    MODL_TRY(ws<unsigned char>(ctx, WS_BCD_SYNC, 256 + n_t * sizeof(T), &base));
+    MODL_TRY(ws<unsigned char>(ctx, WS_BCD_SYNC, sync_bytes + n_t * sizeof(T), &base));
     P.bar = reinterpret_cast<unsigned *>(base);
-    T *tb = reinterpret_cast<T *>(base + 256);
+    P.flags = reinterpret_cast<unsigned *>(base + 256);
+    P.flag_barrier = ctx->opt_bcd_flag_barrier;
+    T *tb = reinterpret_cast<T *>(base + sync_bytes);
     P.part = tb; tb += 2 * nblk * BCD_NPART + (size_t)nblk * k;
     P.vrow = tb;
-    MODL_CUDA_TRY(cudaMemsetAsync(P.bar, 0, 256, st));
+    MODL_CUDA_TRY(cudaMemsetAsync(P.bar, 0, sync_bytes, st));
     P.timing = nullptr;
     if (ctx->opt_bcd_timing) {
         long long *tbuf = nullptr;

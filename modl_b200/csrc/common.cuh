@@ -91,6 +91,7 @@ struct modl_ctx {
     int opt_bcd_pilot = 1;        // use the warp-specialised look-ahead dictionary kernel when the panel fits a cluster
     int opt_tc_gemm = 1;          // float contractions on the tensor cores (tcgen05 3xTF32); 0 = CUDA-core FFMA GEMM
     int opt_bcd_block = 0;        // experimental: blocked dictionary update (deferred projection scalars, bcd_block.cuh)
+    int opt_bcd_flag_barrier = 0; // grid-wide dictionary update: per-CTA epoch flags instead of one atomic counter (to be validated)
     int opt_bcd_coop_min_cols = 32; // grid-wide dictionary update: fewest columns per CTA (more = fewer CTAs at the grid barrier)
     int opt_bcd_timing = 0;       // debug: record clock64 stamps inside the dictionary update
     int bcd_timing_k = 0;

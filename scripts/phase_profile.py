@@ -1,5 +1,5 @@
 """Per-phase device times of the minibatch step (in-library CUDA-event profiler, `modl_ctx_profile`) at the
-shapes of the "next" rows: python scripts/phase_profile.py [fmri] [image] [--out file.json] [--coop-min-cols N]"""
+shapes of the "next" rows: python scripts/phase_profile.py [fmri] [image] [--out file.json] [--coop-min-cols N] [--flag-barrier]"""
 import json
 import os
 import sys
@@ -38,6 +38,10 @@ def run(name):
     est.partial_fit(X[:3 * b])
     torch.cuda.synchronize()
     ctx = _lib.get_context(0)
+    if "--flag-barrier" in sys.argv:         # per-CTA epoch flags instead of the atomic counter (round-2 validation)
+        ctx.set_option("bcd_flag_barrier", 1)
+        est.partial_fit(X[:b])
+        torch.cuda.synchronize()
     if "--coop-min-cols" in sys.argv:        # sweep: fewer, wider CTAs at the grid barrier of the dictionary update
         ctx.set_option("bcd_coop_min_cols", int(sys.argv[sys.argv.index("--coop-min-cols") + 1]))
         est.partial_fit(X[:b])
