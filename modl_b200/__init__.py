@@ -1,7 +1,7 @@
 """modl_b200 -- B200-native implementation of MODL's per-minibatch inner loop
 (`DictFact._single_batch_fit` of arthurmensch/modl) behind the reference's estimator API.
 
-    from modl_b200 import DictFact, Coder
+    from modl_b200 import DictFact, Coder, ImageDictFact, fMRIDictFact, RecsysDictFact, ShardedDictFact
 
 Host code is Python; the hot path is hand-written CUDA for sm_100a in
 `modl_b200/csrc`, reached through the C ABI of `include/modl_b200.h`
@@ -25,6 +25,12 @@ def __getattr__(name):
     if name in ("fMRIDictFact", "fMRICoder", "RecordMasker", "rfMRIDictionaryScorer"):
         from . import fmri
         return getattr(fmri, name)
+    if name in ("RecsysDictFact", "compute_biases", "rmse"):
+        from . import recsys
+        return getattr(recsys, name)
+    if name in ("ShardedDictFact",):
+        from . import distributed
+        return getattr(distributed, name)
     if name in ("enet_norm", "enet_projection", "enet_scale"):
         from . import enet
         return getattr(enet, name)
