@@ -125,7 +125,8 @@ class RecordMasker(BaseEstimator):
         self._check_fitted()
         if isinstance(imgs, (list, tuple)):
             return [self.transform(img) for img in imgs]
-        data = _load_record(imgs)
+        # a `.npy` record is memory-mapped when no cleaning is asked for: under sharding a rank then reads only its rows
+        data = _load_record(imgs, mmap=not (self.detrend or self.standardize))
         mask = self.mask_img_.get_data()
         if data.ndim == 2 and data.shape[1] == self.n_voxels_:
             pass                                                   # already masked
