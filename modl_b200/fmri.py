@@ -21,6 +21,7 @@ are handed to `DictFact.partial_fit` as a CUDA tensor -- at the shape of BASELIN
 import itertools
 import os
 import time
+import warnings
 from math import sqrt
 
 import numpy as np
@@ -202,7 +203,9 @@ def _stage_record(masked_data, permutation, dtype, device):
         return torch.from_numpy(np.ascontiguousarray(masked_data[permutation], dtype=dtype)).to(device)
     else:
         host = np.ascontiguousarray(masked_data, dtype=dtype)
-        rows = torch.from_numpy(host).to(device)
+        with warnings.catch_warnings():                  # a memory-mapped record is read-only; it is only read here
+            warnings.simplefilter("ignore", UserWarning)
+            rows = torch.from_numpy(host).to(device)
     return rows.index_select(0, torch.from_numpy(permutation).to(device))
 
 
