@@ -3,19 +3,20 @@
 
 Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
     DictFact, synthetic dense planted-model X (float32), n_components=256, n_features=10000,
-    batch_size=512 per GPU, reduction=8, l1 coding (code_l1_ratio=1, code_alpha=1, tol=1e-2,
+    batch_size=512, reduction=8, l1 coding (code_l1_ratio=1, code_alpha=1, tol=1e-2,
     max_iter=100), state sized for n_samples=100000.
-A "step" is one pass of the hot path (`DictFact._single_batch_fit`) over one batch.
+A "step" is one pass of the hot path (`DictFact._single_batch_fit`) over one batch of 512 rows.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scaling weak|strong]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scaling strong|weak]
 
-N > 1 is launched by torchrun, one rank per GPU; the batch is sharded over samples, the
-per-batch statistics increments are summed with one NCCL all-reduce and every rank applies the
-(deterministic) dictionary update.  `--scaling weak` (default) keeps 512 samples per GPU per
-step; `--scaling strong` splits one 512-sample batch over the ranks.
+N > 1 is launched by torchrun, one rank per GPU.  The metric's batch is 512 rows, so the default is STRONG
+scaling: one 512-row batch split over the ranks by samples (the reference's own thread pool splits a batch the
+same way, dict_fact.py:584-586), the statistics increments summed with NCCL all-reduces issued from inside the
+library, the dictionary update replicated.  The weak-scaling number (512 rows per GPU) is measured in the same
+run and reported under "weak".  `--scaling weak` swaps the two.
 
-Rank 0 prints ONE JSON line (see the keys below).  `--impl reference` times the UNMODIFIED
-reference (oracle/_ref, its own Cython + NumPy path) on the host cores instead.
+Rank 0 prints ONE JSON line.  `--impl reference` times the UNMODIFIED reference (oracle/_ref, its own Cython +
+NumPy path) on the host cores instead.
 """
 import argparse
 import json
@@ -37,6 +38,11 @@ METRIC = "samples/sec per partial_fit (k=256, p=10k, batch=512)"
 EST_KW = dict(n_components=K, batch_size=B, reduction=R, code_l1_ratio=1., code_alpha=1., tol=1e-2,
               max_iter=100, Dx_agg='masked', G_agg='masked', rand_size=True, replacement=True,
               random_state=0)
+# identical in both arms (the driver compares them)
+CONFIG = {"workload": "DictFact k=256 p=10000 batch=512 reduction=8 l1 coding (BASELINE configs[1])",
+          "n_components": K, "n_features": P, "batch_size": B, "reduction": R, "code_alpha": 1.0, "tol": 1e-2,
+          "n_samples_state": N_SAMPLES_STATE}
+REPEATS = 5
 
 
 def make_data(n_rows, seed=0):
@@ -50,9 +56,14 @@ def make_data(n_rows, seed=0):
     return np.ascontiguousarray(X, dtype=np.float32)
 
 
+def rel_err(a, c):
+    a, c = np.asarray(a, dtype=np.float64), np.asarray(c, dtype=np.float64)
+    return float(np.linalg.norm(a - c) / max(np.linalg.norm(c), 1e-300))
+
+
 # --------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples nvidia-smi clocks / throttle reasons while the timed regions run."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -64,7 +75,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -107,7 +118,8 @@ class ClockSampler(object):
 def _reference_dictfact():
     ref = os.path.join(ROOT, "oracle", "_ref")
     if os.path.exists(os.path.join(ref, "modl", "decomposition", "dict_fact.py")):
-        sys.path.insert(0, ref)
+        if ref not in sys.path:
+            sys.path.insert(0, ref)
         from modl.decomposition.dict_fact import DictFact
         return DictFact, "reference"
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -115,8 +127,9 @@ def _reference_dictfact():
     return oracle.OracleDictFact, "port"
 
 
-def time_reference(X, steps, warmup, n_threads=1):
-    """samples/s of the reference's own partial_fit on the host cores; X holds (warmup+steps)*B rows."""
+def time_reference(X, steps, warmup, n_threads=1, keep=None):
+    """samples/s of the reference's own partial_fit on the host cores; X holds (warmup+steps)*B rows.
+    keep: dict that receives the estimator's code / dictionary after the first `keep['steps']` minibatches."""
     DictFact, kind = _reference_dictfact()
     kw = dict(EST_KW)
     if kind == "reference":
@@ -128,6 +141,9 @@ def time_reference(X, steps, warmup, n_threads=1):
     t0 = time.perf_counter()
     for i in range(warmup, warmup + steps):
         est.partial_fit(X[i * B:(i + 1) * B], np.arange(i * B, (i + 1) * B))
+        if keep is not None and i + 1 == keep["steps"]:
+            keep["code"] = np.array(est.code_[:keep["steps"] * B])
+            keep["D"] = np.array(est.components_)
     dt = time.perf_counter() - t0
     return steps * B / dt, dt / steps * 1e3, kind
 
@@ -140,30 +156,60 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def best_reference(X, steps, warmup, keep=None):
+    """The reference at its best on this box: BLAS threads in {1, all} x its own thread pool n_threads in {1, all}."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        threadpool_limits = None
+    cores = os.cpu_count() or 1
+    avail = blas_threads()
+    tried, best = [], None
+    for bt in sorted({1, avail}):
+        for nt in sorted({1, min(32, cores)}):
+            if threadpool_limits is not None:
+                with threadpool_limits(limits=bt):
+                    v, ms, kind = time_reference(X, steps, warmup, n_threads=nt, keep=keep if not tried else None)
+            else:
+                v, ms, kind = time_reference(X, steps, warmup, n_threads=nt, keep=keep if not tried else None)
+            tried.append({"blas_threads": bt, "n_threads": nt, "samples_per_s": v})
+            if best is None or v > best[0]:
+                best = (v, ms, bt, nt)
+            if kind != "reference":
+                break
+    v, ms, bt, nt = best
+    return {"value": v, "unit": "samples/s", "cores": max(bt, nt), "kind": kind, "ms_per_step": ms,
+            "sample": "%d timed minibatches of 512 rows (same data, same seeds as the GPU arm) after %d warm-up; reference "
+                      "DictFact.partial_fit; best of BLAS threads x n_threads = %s: BLAS %d, n_threads %d; %d host cores"
+                      % (steps, warmup, [(t["blas_threads"], t["n_threads"]) for t in tried], bt, nt, cores),
+            "tried": tried}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
+    if os.environ.get("OMP_NUM_THREADS") and not os.environ.get("MODL_BENCH_REEXEC"):
+        # torchrun pins OMP_NUM_THREADS=1, which would cap the reference's BLAS at one thread: run the arm in a clean
+        # environment so that it can use every host core
+        env = {k_: v for k_, v in os.environ.items()
+               if k_ not in ("OMP_NUM_THREADS", "RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT",
+                             "GROUP_RANK", "LOCAL_WORLD_SIZE", "ROLE_RANK", "ROLE_WORLD_SIZE", "TORCHELASTIC_RUN_ID")}
+        env["MODL_BENCH_REEXEC"] = "1"
+        out = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, stdout=subprocess.PIPE, text=True)
+        for line in out.stdout.splitlines():
+            if line.startswith("{"):
+                print_raw(line)
+        return
     steps, warmup = args.steps, args.warmup
     X = make_data((steps + warmup) * B)
-    best = None
-    for nt in (1, min(32, os.cpu_count() or 1)):
-        v_, ms_, kind = time_reference(X, steps, warmup, n_threads=nt)
-        if best is None or v_ > best[0]:
-            best = (v_, ms_, nt)
-        if kind != "reference":
-            break
-    val, ms, nt_best = best
-    cores = max(blas_threads(), nt_best)
+    cpu = best_reference(X, steps, warmup)
+    val, ms = cpu["value"], cpu["ms_per_step"]
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DictFact k=256 p=10000 batch=512 reduction=8 l1 coding (BASELINE configs[1])",
-                   "n_components": K, "n_features": P, "batch_size": B, "reduction": R},
-        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": kind,
-                         "sample": "%d timed minibatches of 512 rows after %d warm-up, reference DictFact.partial_fit, "
-                                   "best of n_threads in {1, 32} (n_threads=%d), BLAS threads=%d, %d host cores"
-                                   % (steps, warmup, nt_best, blas_threads(), os.cpu_count() or 1)},
+        "config": dict(CONFIG),
+        "cpu_baseline": cpu,
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -185,6 +231,96 @@ def algorithmic_work(s_mean, sweeps_mean, b=B):
     }
 
 
+STEP_BYTES = 45.6e6        # algorithmic bytes of one whole step at config 2 (each array touched once)
+STEP_FLOPS = 4.34e9
+REPLICATED = ("dict_prep", "dict_bcd", "dict_post")    # phases every rank repeats under sample sharding
+
+
+class Runner(object):
+    """One estimator on this rank's share of every 512 * (weak ? world : 1)-row batch."""
+
+    def __init__(self, torch, dist, dev, rank, world, b_local, kw_extra=None, est_cls=None):
+        self.torch, self.dist, self.dev, self.rank, self.world, self.b_local = torch, dist, dev, rank, world, b_local
+        self.b_global = b_local * world
+        kw = dict(EST_KW)
+        kw["batch_size"] = b_local
+        kw.update(kw_extra or {})
+        if est_cls is None:
+            if world > 1:
+                from modl_b200.distributed import ShardedDictFact as est_cls
+            else:
+                from modl_b200 import DictFact as est_cls
+        self.kw, self.est_cls = kw, est_cls
+
+    def new_est(self, X0, **over):
+        kw = dict(self.kw)
+        kw.update(over)
+        est = self.est_cls(device=self.dev, **kw)
+        est.prepare(n_samples=N_SAMPLES_STATE, X=X0[:K])
+        return est
+
+    def idx_of(self, i):
+        base = i * self.b_global + self.rank * self.b_local
+        return np.arange(base, base + self.b_local) % N_SAMPLES_STATE
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, ms):
+        if self.world > 1:
+            t = self.torch.tensor([ms], device=self.dev, dtype=self.torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def timed(self, est, rows, steps, warmup, repeats, ctx, code_out=None):
+        """`repeats` timed regions of EXACTLY `steps` steps each (barrier + synchronize on both sides, CUDA events on the
+        launching stream, max over ranks); rows[i] = this rank's rows of step i.  Returns per-region ms, host enqueue
+        ms per step, launches per region."""
+        torch, b = self.torch, self.b_local
+        nrows = rows.shape[0] // b
+        cursor = 0
+
+        def step(i):
+            j = i % nrows
+            if code_out is None:
+                est.partial_fit(rows[j * b:(j + 1) * b], self.idx_of(i))
+            else:
+                est.partial_fit(rows[j * b:(j + 1) * b], self.idx_of(i), code_out=code_out)
+
+        for _ in range(warmup):
+            step(cursor)
+            cursor += 1
+        regions, host, launches = [], [], 0
+        for _ in range(repeats):
+            self.barrier()
+            l0 = ctx.launch_count
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            h0 = time.perf_counter()
+            for _ in range(steps):
+                step(cursor)
+                cursor += 1
+            host.append((time.perf_counter() - h0) * 1e3 / steps)
+            e1.record()
+            self.barrier()
+            if hasattr(est, "synchronize"):
+                est.synchronize()
+            regions.append(self.max_over_ranks(e0.elapsed_time(e1)))
+            launches = ctx.launch_count - l0
+        return regions, float(np.median(host)), launches
+
+
+def summarize(regions, steps, rows_per_step):
+    med = float(np.median(regions))
+    return {"value": steps * rows_per_step / (med * 1e-3), "ms_per_step": med / steps,
+            "ms_per_step_min": float(np.min(regions)) / steps, "ms_per_step_max": float(np.max(regions)) / steps,
+            "regions": len(regions)}
+
+
 def run_b200(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -194,144 +330,135 @@ def run_b200(args, rank, world):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        from modl_b200.distributed import ShardedDictFact as Est
-    else:
-        from modl_b200 import DictFact as Est
     steps, warmup = args.steps, args.warmup
-    b_local = B if args.scaling == "weak" else B // world
-    b_global = b_local * world
-    total = steps + warmup
-    X = make_data(total * b_local, seed=rank if world > 1 else 0)
-    if world > 1:
-        # the dictionary initialisation must be identical on every rank
-        X0 = make_data(K, seed=0)
-    else:
-        X0 = X
-    kw = dict(EST_KW)
-    kw["batch_size"] = b_local if world > 1 else B
-
-    if world > 1 and os.environ.get("MODL_OVERLAP") is not None:
-        kw["overlap_exchange"] = bool(int(os.environ["MODL_OVERLAP"]))
-
-    def new_est():
-        est = Est(device=dev, **kw)
-        est.prepare(n_samples=N_SAMPLES_STATE, X=X0[:K])
-        return est
-
-    def idx_of(i):
-        # global row ids of this rank's shard of step i
-        base = i * b_global + rank * b_local
-        return np.arange(base, base + b_local) % N_SAMPLES_STATE
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
+    if B % world:
+        raise SystemExit("--gpus must divide the batch of %d rows" % B)
+    primary = args.scaling if world > 1 else "strong"
+    b_of = {"strong": B // world, "weak": B}
     ctx = _lib.get_context(local_rank)
+    X0 = make_data(K, seed=0)              # the dictionary initialisation, identical on every rank
+    n_data_steps = 24                      # distinct batches cycled through (24 x 20.5 MB at 512 rows: far larger than L2)
 
-    # ---- (1) device-resident pass: inputs in HBM before the timed region -----------------
-    est = new_est()
-    est.record_sweeps = True
-    Xd = torch.from_numpy(X).to(dev)          # (steps+warmup)*b rows: 20 MB per step, > L2 over the run
-    for i in range(warmup):
-        est.partial_fit(Xd[i * b_local:(i + 1) * b_local], idx_of(i))
-    barrier()
+    def data_for(b_local):
+        if world == 1:
+            return make_data(n_data_steps * B, seed=0)
+        # every rank draws the whole 512*steps matrix of its scaling mode from the same seed and keeps its rows, so that
+        # the union over ranks is the single-GPU data set
+        if b_local * world == B:
+            full = make_data(n_data_steps * B, seed=0).reshape(n_data_steps, B, P)
+            return np.ascontiguousarray(full[:, rank * b_local:(rank + 1) * b_local]).reshape(-1, P)
+        return make_data(n_data_steps * b_local, seed=1 + rank)
+
+    results = {}
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    launches0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    host0 = time.perf_counter()
-    for i in range(warmup, total):
-        est.partial_fit(Xd[i * b_local:(i + 1) * b_local], idx_of(i))
-    host_ms = (time.perf_counter() - host0) * 1e3 / steps      # host time to ENQUEUE a step (no synchronisation)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = ctx.launch_count - launches0
+
+    # ---- (0) multi-GPU parity: the sharded estimator against the single-GPU one on the concatenated batch ----
+    parity = None
+    if world > 1:
+        from modl_b200 import DictFact
+        from modl_b200.distributed import ShardedDictFact
+        bl = B // world
+        Xs = make_data(3 * B, seed=3)
+        sh = ShardedDictFact(device=dev, **dict(EST_KW, batch_size=bl))
+        sh.prepare(n_samples=3 * B, X=X0[:K])
+        for t in range(3):
+            lo = t * B + rank * bl
+            sh.partial_fit(Xs[lo:lo + bl], np.arange(lo, lo + bl))
+        spread = sh.check_replicas()
+        if rank == 0:
+            one = DictFact(device=dev, **EST_KW)
+            one.prepare(n_samples=3 * B, X=X0[:K])
+            one.partial_fit(Xs)
+            mine = np.concatenate([np.arange(t * B, t * B + bl) for t in range(3)])
+            parity = {"vs": "single-GPU DictFact on the concatenated 512-row batches, 3 steps from identical state",
+                      "code": rel_err(sh.code_[mine], one.code_[mine]), "D": rel_err(sh.components_, one.components_),
+                      "B": rel_err(sh.B_, one.B_), "replicas_spread": spread,
+                      "n_iter": [int(sh.n_iter_), int(one.n_iter_)]}
+        del sh
+
+    # ---- (1) device-resident passes: inputs in HBM before the timed regions ------------------------------------
+    diag = {}
+    for mode in ([primary] + (["weak" if primary == "strong" else "strong"] if world > 1 else [])):
+        b_local = b_of[mode]
+        run = Runner(torch, dist, dev, rank, world, b_local)
+        X = data_for(b_local)
+        Xd = torch.from_numpy(X).to(dev)
+        est = run.new_est(X0)
+        est.record_sweeps = True
+        reps = REPEATS if mode == primary else 3
+        regions, host_ms, launches = run.timed(est, Xd, steps, warmup, reps, ctx)
+        res = summarize(regions, steps, run.b_global)
+        res.update({"host_enqueue_ms_per_step": host_ms, "gpu_launches": int(launches), "batch_size_per_gpu": b_local,
+                    "global_batch": run.b_global})
+        results[mode] = res
+        if mode == primary:
+            sw = est.last_sweeps_
+            diag["mean_cd_sweeps"] = float(sw[:b_local].mean()) if sw is not None else float("nan")
+            diag["subset_len_last"] = float(est.last_subset_.shape[0])
+            last = run.idx_of(warmup + reps * steps - 1)
+            diag["code_density"] = float((est.code_dev[torch.as_tensor(last, device=dev)] != 0).float().mean().item())
+            keep = (run, est, X, Xd)
+        else:
+            del est, Xd
+    run, est, X, Xd = keep
+    b_local, b_global = run.b_local, run.b_global
+    main_res = results[primary]
+
+    # ---- (2) end-to-end: pinned host rows in, batch code out, both copies inside the timed regions -------------
+    e2e = None
+    if not args.no_e2e:
+        est2 = run.new_est(X0, async_host_copy=True)     # pinned rows stay untouched until the synchronisation that ends a region
+        Xp = torch.from_numpy(X).pin_memory()
+        code_host = torch.empty((b_local, K), dtype=torch.float32).pin_memory()
+        regions, host_ms2, _ = run.timed(est2, Xp, steps, warmup, REPEATS, ctx, code_out=code_host)
+        e2e = summarize(regions, steps, b_global)
+        e2e.update({"unit": "samples/s", "h2d_bytes_per_step": int(b_local * P * 4 + b_local * 8),
+                    "d2h_bytes_per_step": int(b_local * K * 4), "host_enqueue_ms_per_step": host_ms2,
+                    "api": "DictFact(async_host_copy=True).partial_fit(pinned host rows, sample_indices, code_out=pinned "
+                           "buffer): one 512-row batch per call; H2D of the rows and D2H of the batch code inside the region"})
+        if rank == 0:
+            buf_d = torch.empty((b_local, P), dtype=torch.float32, device=dev)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nfresh = min(n_data_steps, 16)
+            for i in range(2):
+                buf_d.copy_(Xp[i * b_local:(i + 1) * b_local], non_blocking=True)
+            ev0.record()
+            for i in range(nfresh):
+                buf_d.copy_(Xp[i * b_local:(i + 1) * b_local], non_blocking=True)
+            ev1.record()
+            torch.cuda.synchronize(dev)
+            e2e["pinned_h2d_GBps"] = nfresh * b_local * P * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+        del est2, Xp
+
+    # ---- (3) the survey's dense-code regime (code_alpha = 0.1): the CD kernel off its best case -----------------
+    dense = None
+    if not args.no_e2e and world == 1:
+        est3 = run.new_est(X0, code_alpha=0.1)
+        est3.record_sweeps = True
+        regions, _, _ = run.timed(est3, Xd, steps, warmup, 3, ctx)
+        dense = summarize(regions, steps, b_global)
+        sw = est3.last_sweeps_
+        last = run.idx_of(warmup + 3 * steps - 1)
+        dense.update({"code_alpha": 0.1, "mean_cd_sweeps": float(sw[:b_local].mean()),
+                      "code_density": float((est3.code_dev[torch.as_tensor(last, device=dev)] != 0).float().mean().item())})
+        del est3
     clk = clocks.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    value = steps * b_global / (ms_total * 1e-3)
-    sw = est.last_sweeps_
-    sweeps_mean = float(sw[:b_local].mean()) if sw is not None else float("nan")
-    last_idx = idx_of(total - 1)
-    density = float((est.code_dev[torch.as_tensor(last_idx, device=dev)] != 0).float().mean().item())
-    s_mean = float(est.last_subset_.shape[0])
 
-    # ---- (2) end-to-end pass: host (pinned) rows in, batch code out, copies timed ----------
-    if args.no_e2e:      # profiler runs only (ncu): skip the end-to-end and CPU legs
-        args.no_cpu = True
-    est2 = new_est()
-    est2.async_host_copy = True      # pinned rows stay untouched until the final synchronisation below
-    Xp = torch.from_numpy(X).pin_memory()
-    code_host = torch.empty((b_local, K), dtype=torch.float32).pin_memory()
-    for i in range(warmup):
-        est2.partial_fit(Xp[i * b_local:(i + 1) * b_local], idx_of(i))
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    wall0 = time.perf_counter()
-    for i in range(warmup, warmup + 1 if args.no_e2e else total):
-        ids = idx_of(i)
-        est2.partial_fit(Xp[i * b_local:(i + 1) * b_local], ids)
-        code_host.copy_(est2.code_dev[ids[0]:ids[0] + b_local] if ids[-1] - ids[0] == b_local - 1
-                        else est2.code_dev[torch.as_tensor(ids, device=dev)], non_blocking=True)
-    t1.record()
-    barrier()
-    e2e_ms = max(t0.elapsed_time(t1), 0.0)
-    wall_ms = (time.perf_counter() - wall0) * 1e3
-    e2e_ms = max(e2e_ms, wall_ms * 0.0)   # device time on the launching stream; wall kept for reference
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = steps * b_global / (e2e_ms * 1e-3)
-
-    # pinned host -> device bandwidth of this box (what bounds the end-to-end number once the kernels are fast)
-    h2d_gbps = h2d_fresh_gbps = None
-    if rank == 0:
-        buf_h = Xp[:b_local]
-        buf_d = torch.empty_like(buf_h, device=dev)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(2):
-            buf_d.copy_(buf_h, non_blocking=True)
-        ev0.record()
-        for _ in range(10):
-            buf_d.copy_(buf_h, non_blocking=True)
-        ev1.record()
-        torch.cuda.synchronize(dev)
-        h2d_gbps = 10 * buf_h.numel() * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
-        # the same copy over DISTINCT batches (what the end-to-end loop does: every step reads fresh host pages)
-        nfresh = min(total, 16)
-        ev0.record()
-        for i in range(nfresh):
-            buf_d.copy_(Xp[i * b_local:(i + 1) * b_local], non_blocking=True)
-        ev1.record()
-        torch.cuda.synchronize(dev)
-        h2d_fresh_gbps = nfresh * buf_h.numel() * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
-
-    # ---- (3) per-phase device times (separate profiled pass, CUDA events on the stream) ----
-    phases_ms, roof = None, None
-    # every rank runs the pass (the sharded step contains a collective); rank 0 reports
+    # ---- (4) per-phase device times (separate profiled pass on one stream, CUDA events inside the library) ------
     ctx.profile(True)
     nprof = min(steps, 10)
     for i in range(nprof):
-        j = warmup + i
-        est.partial_fit(Xd[j * b_local:(j + 1) * b_local], idx_of(j))
+        est.partial_fit(Xd[i * b_local:(i + 1) * b_local], run.idx_of(i))
     torch.cuda.synchronize(dev)
-    tot, nst = ctx.profile_read()
+    tot, _ = ctx.profile_read()
     ctx.profile(False)
-    barrier()
+    run.barrier()
+    roof = amdahl = None
     if rank == 0:
         phases_ms = {k_: v / max(nprof, 1) for k_, v in tot.items()}
-        work = algorithmic_work(s_mean, sweeps_mean, b_local)
+        work = algorithmic_work(diag["subset_len_last"], diag["mean_cd_sweeps"], b_local)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             pk = json.load(open(peaks_path))
@@ -345,58 +472,76 @@ def run_b200(args, rank, world):
         prof_json = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(prof_json):
             traffic = json.load(open(prof_json)).get(dom)
+        step_ms = main_res["ms_per_step"]
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": which,
-                "ms_per_launch": dom_ms,
-                "note": "the two dominant phases (code = warp-per-sample CD, dict_bcd = sequential atoms) are "
-                        "dependency-chain bound, not HBM or tensor bound (SURVEY H4); per-phase table in `phases`",
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": which, "ms_per_launch": dom_ms,
+                "note": "the two dominant phases (code = warp-per-sample CD, dict_bcd = sequential atoms) are dependency-chain "
+                        "bound, not HBM or tensor bound (SURVEY H4); per-phase table in `phases` (one stream, profiled pass); "
+                        "the timed step overlaps the full-width B_ product and the next batch's input preparation with "
+                        "dict_bcd on a second stream, so the step is shorter than the sum of its phases",
                 "phases": {p_: {"ms": phases_ms[p_],
                                 "GBps": work[p_]["bytes"] / (phases_ms[p_] * 1e-3) / 1e9 if phases_ms[p_] > 0 else None,
                                 "TFLOPs": work[p_]["flops"] / (phases_ms[p_] * 1e-3) / 1e12 if phases_ms[p_] > 0 else None,
                                 "alg_bytes": work[p_]["bytes"], "alg_flops": work[p_]["flops"]}
                            for p_ in phases_ms if p_ in work},
+                "step": {"ms": step_ms, "GBps": STEP_BYTES / (step_ms * 1e-3) / 1e9, "frac_hbm": STEP_BYTES / (step_ms * 1e-3) / 1e9 / hbm_peak,
+                         "TFLOPs": STEP_FLOPS / (step_ms * 1e-3) / 1e12, "frac_tensor": STEP_FLOPS / (step_ms * 1e-3) / 1e12 / tf_peak,
+                         "alg_bytes": STEP_BYTES, "alg_flops": STEP_FLOPS},
                 "tensor_peak_TFLOPs": tf_peak}
+        rep_ms = sum(phases_ms.get(p_, 0.0) for p_ in REPLICATED) + phases_ms.get("gram", 0.0)
+        shard_ms = sum(v for p_, v in phases_ms.items() if p_ not in REPLICATED and p_ != "gram")
+        amdahl = {"replicated_ms": rep_ms, "sharded_ms_at_this_N": shard_ms,
+                  "note": "per-phase device times at this rank's share of the batch; replicated = dictionary update (prep, "
+                          "sequential BCD, scatter) + the Gram product every rank repeats; sharded = gathers, Dx, code solve, "
+                          "statistics.  Strong-scaling speed-up is bounded by (rep + shard_1) / (rep + shard_1 / N): the "
+                          "sequential dictionary update does not shard over samples (SURVEY 8e)"}
 
-    # ---- (4) CPU baseline: the reference's own path on this box's host cores (rank 0, N=1) --
+    # ---- (5) CPU baseline: the reference's own path on this box's host cores (rank 0, N=1) ---------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         nb_cpu, warm_cpu = args.cpu_steps, 1
-        Xc = X[:(nb_cpu + warm_cpu) * B] if X.shape[0] >= (nb_cpu + warm_cpu) * B else make_data((nb_cpu + warm_cpu) * B)
-        best = None
-        for nt in (1, min(32, os.cpu_count() or 1)):
-            v_, ms_, kind = time_reference(Xc, nb_cpu, warm_cpu, n_threads=nt)
-            if best is None or v_ > best[0]:
-                best = (v_, ms_, nt)
-            if kind != "reference":
-                break
-        v, ms_c, nt_best = best
-        cpu = {"value": v, "unit": "samples/s", "cores": max(blas_threads(), nt_best), "kind": kind, "ms_per_step": ms_c,
-               "sample": "%d timed minibatches of 512 rows (same data, same seeds) after %d warm-up; reference "
-                         "DictFact.partial_fit, best of n_threads in {1, 32} (n_threads=%d), BLAS threads=%d, "
-                         "%d host cores" % (nb_cpu, warm_cpu, nt_best, blas_threads(), os.cpu_count() or 1)}
+        Xc = X[:(nb_cpu + warm_cpu) * B]
+        keepd = {"steps": 3}
+        cpu = best_reference(Xc, nb_cpu, warm_cpu, keep=keepd)
+        # the checker's other job: the first minibatches of the GPU path against the reference from identical state
+        from modl_b200 import DictFact
+        chk = DictFact(device=dev, **EST_KW)
+        chk.prepare(n_samples=N_SAMPLES_STATE, X=Xc[:K])
+        for i in range(3):
+            chk.partial_fit(Xd[i * B:(i + 1) * B], np.arange(i * B, (i + 1) * B))
+        if "code" in keepd:
+            parity = {"vs": "oracle/_ref (the unmodified reference), 3 minibatches from identical state, same seeds",
+                      "code": rel_err(chk.code_[:3 * B], keepd["code"]), "D": rel_err(chk.components_, keepd["D"])}
 
     if rank == 0:
+        cfg = dict(CONFIG)
         out = {
-            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms_total / steps, "host_enqueue_ms_per_step": host_ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "DictFact k=256 p=10000 batch=512 reduction=8 l1 coding (BASELINE configs[1])",
-                       "n_components": K, "n_features": P, "batch_size_per_gpu": b_local, "global_batch": b_global,
-                       "reduction": R, "code_alpha": 1.0, "tol": 1e-2, "n_samples_state": N_SAMPLES_STATE,
-                       "parallelism": "sample-sharded dp%d" % world,
-                       "l2": "inputs larger than L2: a fresh 20.5 MB batch per step, %d MB over the timed region"
-                             % int(steps * b_local * P * 4 / 1e6),
-                       "mean_cd_sweeps": sweeps_mean, "code_density": density, "subset_len_last": s_mean},
-            "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms / steps,
-                    "h2d_bytes_per_step": int(b_local * P * 4 + b_local * 8), "d2h_bytes_per_step": int(b_local * K * 4),
-                    "api": "DictFact(async_host_copy=True).partial_fit(pinned host rows, sample_indices), one batch per "
-                           "call, + read-back of the batch code into pinned memory every step",
-                    "pinned_h2d_GBps": h2d_gbps, "pinned_h2d_distinct_batches_GBps": h2d_fresh_gbps},
-            "gpu_launches": int(launches),
+            "metric": METRIC, "value": main_res["value"], "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": primary if world > 1 else args.scaling,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg,
+            "run": {"parallelism": "sample-sharded dp%d" % world, "batch_size_per_gpu": b_local, "global_batch": b_global,
+                    "timing": "median of %d timed regions of %d steps each (CUDA events, barrier + synchronize on both sides, "
+                              "max over ranks); min / max in ms_per_step_min / _max" % (main_res["regions"], steps),
+                    "ms_per_step_min": main_res["ms_per_step_min"], "ms_per_step_max": main_res["ms_per_step_max"],
+                    "l2": "inputs larger than L2: a fresh batch per step, cycling through %d distinct batches (%d MB)"
+                          % (n_data_steps, int(n_data_steps * b_local * P * 4 / 1e6)),
+                    "calls": "one partial_fit call per 512-row batch (one C call each: modl_partial_fit_f32)",
+                    **diag},
+            "host_enqueue_ms_per_step": main_res["host_enqueue_ms_per_step"],
+            "e2e": e2e,
+            "gpu_launches": main_res["gpu_launches"],
             "clocks": clk,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "parity": parity,
         }
+        if world > 1:
+            other = "weak" if primary == "strong" else "strong"
+            out[other] = dict(results[other], scaling=other, unit="samples/s")
+            out["amdahl"] = amdahl
+        if dense is not None:
+            out["extra"] = {"dense_codes": dense}
         print_json(out)
     if world > 1:
         dist.destroy_process_group()
@@ -407,21 +552,24 @@ def main():
     # goes to stderr instead
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
-    global print_json
+    global print_json, print_raw
+
+    def print_raw(line):
+        real_stdout.write(line + "\n")
+        real_stdout.flush()
 
     def print_json(obj):
-        real_stdout.write(json.dumps(obj) + "\n")
-        real_stdout.flush()
+        print_raw(json.dumps(obj))
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--cpu-steps", type=int, default=16)
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
+    ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true", help="profiler runs: shortest possible e2e leg")
+    ap.add_argument("--no-e2e", action="store_true", help="profiler runs: device-resident leg only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -85,9 +85,9 @@ int64_t modl_ctx_launch_count(const modl_ctx *ctx);
 /* tunables: "bcd_cluster" (largest thread-block cluster the dictionary update may use, 0 = none),
  * "cd_warps" (warps per CTA of the CD kernel, 0 = auto), "force_global_gram" (debug),
  * "tc_gemm" (1 = float32 contractions on tcgen05 with the 3xTF32 split, 0 = CUDA-core FFMA GEMM),
- * "bcd_pilot" / "bcd_block" (dictionary-update kernel variants), "bcd_coop_min_cols" (fewest columns per CTA
- * of the grid-wide dictionary update, default 32), "bcd_flag_barrier" (1 = per-CTA epoch flags instead of one atomic
- * counter at its grid barrier; off until validated), "bcd_timing" (debug stamps). */
+ * "bcd_pilot" (0 = plain per-atom cluster kernel instead of the look-ahead pilot kernel), "bcd_coop_min_cols" (fewest
+ * columns per CTA of the grid-wide dictionary update, default 128), "bcd_flag_barrier" (1 = per-CTA epoch flags instead
+ * of one atomic counter at its grid barrier; measured slower, off), "bcd_timing" (debug stamps). */
 int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value);
 /* Synchronises `stream`, then returns MODL_ENOTSPD if a Cholesky pivot was non-positive since
  * the last check (LAPACK posv info > 0, which the reference ignores:
@@ -297,6 +297,16 @@ typedef struct modl_step_params {
      * has been read", so that APPLY_SUB and DICT can share one call while another stream waits for exactly
      * that point before it rewrites B_. */
     void *ev_after_apply_sub;
+    /* Two-stream schedule of modl_partial_fit_* (below).  `slot` (0/1) selects one of two copies of the per-step
+     * device inputs (feature subset, atom order, B_[:, subset] panel) so that MODL_PHASE_PREFETCH of step t+1 may
+     * run while the dictionary update of step t still reads its own.  sm_avail (0 = all): SMs the full-width
+     * product may count on while the dictionary update's cluster is resident.  start_flag (device uint32, or
+     * NULL): the dictionary-update kernel stores start_serial there as soon as its CTAs are resident, which is
+     * what the second stream waits for before it launches anything that could take those SMs. */
+    int slot;
+    int sm_avail;
+    void *start_flag;
+    uint32_t start_serial;
 } modl_step_params;
 
 /* MODL_PHASE_STATS_SUB (same call as MODL_PHASE_CODE) computes ONLY what the dictionary update waits
@@ -308,10 +318,82 @@ typedef struct modl_step_params {
 enum { MODL_PHASE_CODE = 1, MODL_PHASE_STATS = 2, MODL_PHASE_APPLY = 4, MODL_PHASE_DICT = 8,
        MODL_PHASE_APPLY_SUB = 16, MODL_PHASE_APPLY_B = 32, MODL_PHASE_STATS_SUB = 64, MODL_PHASE_STATS_B = 128,
        /* the feature subset uploaded by the previous call of this context belongs to the same step: skip the upload */
-       MODL_PHASE_REUSE_SUBSET = 256 };
+       MODL_PHASE_REUSE_SUBSET = 256,
+       /* A call of its own, on any stream, ahead of the step: everything that depends on the batch, the subset and
+        * the atom order but not on the dictionary -- index uploads, the X side of the subset gather (packed rows, row
+        * norms), the packed X[:, subset]^T operand and (with FUSED_APPLY) the B_[:, subset] panel. */
+       MODL_PHASE_PREFETCH = 512,
+       /* flag: this step's MODL_PHASE_PREFETCH has completed (ordered by the caller's events) */
+       MODL_PHASE_INPUTS_READY = 1024,
+       /* flag, one GPU: STATS_SUB folds its product straight into C_ and into the B_[:, subset] panel
+        * ([panel | C_] = keep [panel | C_] + (w/b) code^T [X_sub | code], one tensor-core launch); no APPLY_SUB */
+       MODL_PHASE_FUSED_APPLY = 2048 };
 
 int modl_batch_fit_f32(modl_ctx *, const modl_step_params *prm, void *stream);
 int modl_batch_fit_f64(modl_ctx *, const modl_step_params *prm, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * The minibatch loop   [ref: DictFact.partial_fit, dict_fact.py:313-337, over _single_batch_fit :495-526]
+ *
+ * One call = every `batch_size` block of the rows passed to partial_fit: per block the host statements of the
+ * reference in their order (feature subset from the sampler :507, n_iter_ :509, sample_n_iter_ :510, batch
+ * weight :515, the atom order the caller drew :672) and the device phases of modl_batch_fit_* on two streams:
+ * the dictionary update (a 16-CTA cluster, sequential over atoms) only needs C_ and the SUBSET columns of B_
+ * (:532), so the full-width product B_ = (1-w) B_ + w/b code^T X (:559-566) and the next block's input
+ * preparation run on a second stream on the SMs the dictionary update leaves idle.  Results are those of
+ * calling modl_batch_fit_* block by block (B_[:, subset] panel and B_ agree to rounding of two equivalent
+ * products).  Rows may come from device memory or from host memory (staged through three device slots on a
+ * copy stream, so that the copy of block i+1 overlaps the kernels of block i, within a call and across calls).
+ * ---------------------------------------------------------------------------------- */
+typedef struct modl_fit modl_fit;     /* streams, events, staging slots and (optionally) NCCL communicators of one estimator */
+
+typedef struct modl_fit_params {       /* the estimator: state arrays (device, updated in place) and hyper-parameters */
+    int64_t n_samples, n_features, n_components, batch_size;
+    void *components, *code, *C, *B, *comp_norm, *G_full, *Dx_average, *G_average;
+    double reduction, learning_rate, code_alpha, code_l1_ratio, comp_l1_ratio, tol, step_size;
+    int max_iter, code_pos, comp_pos, Dx_agg, G_agg, optimizer_sgd;
+} modl_fit_params;
+
+typedef struct modl_fit_batches {      /* one partial_fit call */
+    const void *X;                     /* n_rows x n_features, leading dimension ldx */
+    int64_t ldx, n_rows;
+    int x_location;                    /* 0 = device, 1 = pinned host, 2 = pageable host */
+    const int64_t *h_sample_indices;   /* HOST int64[n_rows]: rows of code_ / the running averages (NULL = 0..n_rows-1) */
+    modl_sampler *sampler;             /* feature_sampler_ of the estimator */
+    int64_t *h_n_iter;                 /* HOST: n_iter_, updated */
+    int64_t *h_sample_n_iter;          /* HOST int64[n_samples]: sample_n_iter_, updated (may be NULL) */
+    int update_counters;               /* 0: the caller has already bumped both counters for these rows */
+    const int64_t *h_orders;           /* HOST int64[n_batches x k]: one atom permutation per block, drawn by the caller from
+                                          its NumPy RandomState in block order [ref: :672] */
+    const void *h_w_sample;            /* HOST real[n_rows]: sample_n_iter_ ** -sample_learning_rate [ref: :513]; 'average' modes */
+    int32_t *sweeps;                   /* device int32[batch_size] or NULL: CD sweeps per sample of the LAST block */
+    int64_t *h_last_subset;            /* HOST int64[n_features] or NULL: receives the last block's feature subset */
+    int64_t *h_last_subset_len;
+    void *h_code_out;                  /* HOST (pinned) real[n_rows x k] or NULL: every block's code, copied out on a stream
+                                          of its own as soon as the block's solve has finished */
+    int wait_host;                     /* 1: return once X has been consumed and h_code_out is complete; 0: fully asynchronous
+                                          (the caller keeps X untouched until modl_fit_synchronize) */
+} modl_fit_batches;
+
+int modl_fit_create(modl_ctx *ctx, modl_fit **out);
+void modl_fit_destroy(modl_fit *fit);
+/* "overlap" (1 = the two-stream schedule above, 0 = one fused call per block on the caller's stream),
+ * "gate" (1 = the second stream starts only once the dictionary-update kernel is resident). */
+int modl_fit_set_option(modl_fit *fit, const char *name, int value);
+/* Blocks until the loop's own streams (copies, second stream, code read-back) are idle. */
+int modl_fit_synchronize(modl_fit *fit);
+int modl_partial_fit_f32(modl_fit *fit, const modl_fit_params *est, const modl_fit_batches *io, void *stream);
+int modl_partial_fit_f64(modl_fit *fit, const modl_fit_params *est, const modl_fit_batches *io, void *stream);
+
+/* Sample-sharded data parallelism, one process per GPU (the reference's analogue is its thread pool over
+ * slices of a batch, dict_fact.py:584-586, 621-635).  Every rank passes ITS rows of each block (the same count on
+ * every rank); the loop sums the statistics increments over ranks with ncclAllReduce -- the k x (k + s) part the
+ * dictionary update waits for on the caller's stream, the k x p part of B_ on the second stream behind the
+ * dictionary update -- and every rank applies the same deterministic dictionary update to bit-identical inputs.
+ * modl_nccl_unique_id: rank 0 draws two ids (128 bytes each) and ships them to the other ranks by any means
+ * (torch.distributed broadcast); modl_fit_set_comm is collective. */
+int modl_nccl_unique_id(void *h_out, int64_t capacity);
+int modl_fit_set_comm(modl_fit *fit, int world, int rank, const void *h_id_main, const void *h_id_side);
 
 /* ------------------------------------------------------------------------------------
  * Recsys: the missing-value path   [ref: RecsysDictFact, modl/decomposition/recsys.py:147-213,

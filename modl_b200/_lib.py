@@ -30,10 +30,34 @@ class StepParams(C.Structure):
         ("optimizer_sgd", ci),
         ("sweeps", vp),
         ("phases", ci), ("global_batch", i64), ("stats_inc", vp), ("inc_sub", vp), ("ev_after_apply_sub", vp),
+        ("slot", ci), ("sm_avail", ci), ("start_flag", vp), ("start_serial", C.c_uint32),
     ]
+
+class FitParams(C.Structure):
+    """struct modl_fit_params (include/modl_b200.h)."""
+    _fields_ = [
+        ("n_samples", i64), ("n_features", i64), ("n_components", i64), ("batch_size", i64),
+        ("components", vp), ("code", vp), ("C", vp), ("B", vp), ("comp_norm", vp),
+        ("G_full", vp), ("Dx_average", vp), ("G_average", vp),
+        ("reduction", f64), ("learning_rate", f64), ("code_alpha", f64), ("code_l1_ratio", f64),
+        ("comp_l1_ratio", f64), ("tol", f64), ("step_size", f64),
+        ("max_iter", ci), ("code_pos", ci), ("comp_pos", ci), ("Dx_agg", ci), ("G_agg", ci), ("optimizer_sgd", ci),
+    ]
+
+
+class FitBatches(C.Structure):
+    """struct modl_fit_batches (include/modl_b200.h)."""
+    _fields_ = [
+        ("X", vp), ("ldx", i64), ("n_rows", i64), ("x_location", ci),
+        ("h_sample_indices", vp), ("sampler", vp), ("h_n_iter", vp), ("h_sample_n_iter", vp),
+        ("update_counters", ci), ("h_orders", vp), ("h_w_sample", vp), ("sweeps", vp),
+        ("h_last_subset", vp), ("h_last_subset_len", vp), ("h_code_out", vp), ("wait_host", ci),
+    ]
+
 
 PHASE_CODE, PHASE_STATS, PHASE_APPLY, PHASE_DICT, PHASE_APPLY_SUB, PHASE_APPLY_B = 1, 2, 4, 8, 16, 32
 PHASE_STATS_SUB, PHASE_STATS_B, PHASE_REUSE_SUBSET = 64, 128, 256
+PHASE_PREFETCH, PHASE_INPUTS_READY, PHASE_FUSED_APPLY = 512, 1024, 2048
 
 
 class ModlError(RuntimeError):
@@ -71,7 +95,14 @@ def _declare(L):
     fn("modl_ctx_check_info", ci, [vp, vp])
     fn("modl_ctx_profile", ci, [vp, ci])
     fn("modl_ctx_profile_read", ci, [vp, vp, vp])
+    fn("modl_fit_create", ci, [vp, C.POINTER(vp)])
+    fn("modl_fit_destroy", None, [vp])
+    fn("modl_fit_set_option", ci, [vp, C.c_char_p, ci])
+    fn("modl_fit_synchronize", ci, [vp])
+    fn("modl_nccl_unique_id", ci, [vp, i64])
+    fn("modl_fit_set_comm", ci, [vp, ci, ci, vp, vp])
     for sfx, real in (("f32", f32), ("f64", f64)):
+        fn("modl_partial_fit_" + sfx, ci, [vp, C.POINTER(FitParams), C.POINTER(FitBatches), vp])
         fn("modl_enet_norm_" + sfx, ci, [vp, vp, i64, i64, i64, real, vp, vp])
         fn("modl_enet_projection_" + sfx, ci, [vp, vp, vp, i64, i64, i64, vp, real, vp])
         fn("modl_enet_scale_" + sfx, ci, [vp, vp, i64, i64, i64, real, real, vp])
@@ -98,12 +129,13 @@ EXPORTED = (
      "modl_rs_shuffle_with_trace", "modl_sampler_create", "modl_sampler_destroy",
      "modl_sampler_yield_subset", "modl_batch_weight", "modl_ctx_create", "modl_ctx_destroy",
      "modl_ctx_sm_count", "modl_ctx_launch_count", "modl_ctx_set_option", "modl_ctx_check_info",
-     "modl_ctx_profile", "modl_ctx_profile_read"]
+     "modl_ctx_profile", "modl_ctx_profile_read", "modl_fit_create", "modl_fit_destroy", "modl_fit_set_option",
+     "modl_fit_synchronize", "modl_nccl_unique_id", "modl_fit_set_comm"]
     + [n + s for s in ("f32", "f64") for n in (
         "modl_enet_norm_", "modl_enet_projection_", "modl_enet_scale_", "modl_gram_dx_",
         "modl_enet_regression_single_gram_", "modl_enet_regression_multi_gram_",
         "modl_update_G_average_", "modl_update_Dx_average_", "modl_update_stats_",
-        "modl_update_dict_", "modl_batch_fit_", "modl_recsys_gram_dx_", "modl_recsys_update_B_",
+        "modl_update_dict_", "modl_batch_fit_", "modl_partial_fit_", "modl_recsys_gram_dx_", "modl_recsys_update_B_",
         "modl_recsys_update_C_", "modl_recsys_sync_transposed_", "modl_recsys_predict_")])
 
 _lib = None
@@ -165,6 +197,43 @@ class Context(object):
 
     def check_info(self, stream):
         check(lib().modl_ctx_check_info(self.handle, vp(stream)))
+
+
+class FitLoop(object):
+    """One modl_fit per estimator: the streams, events, staging slots and (sharded) NCCL communicators of its
+    minibatch loop (modl_partial_fit_*)."""
+
+    def __init__(self, ctx):
+        h = vp()
+        check(lib().modl_fit_create(ctx.handle, C.byref(h)))
+        self.handle = h
+        self.ctx = ctx
+        self.world = 1
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                lib().modl_fit_destroy(h)
+            except Exception:
+                pass
+
+    def set_option(self, name, value):
+        check(lib().modl_fit_set_option(self.handle, name.encode(), int(value)))
+
+    def synchronize(self):
+        check(lib().modl_fit_synchronize(self.handle))
+
+    def set_comm(self, world, rank, id_main, id_side):
+        check(lib().modl_fit_set_comm(self.handle, int(world), int(rank), id_main, id_side))
+        self.world = int(world)
+
+
+def nccl_unique_id():
+    """128 bytes identifying a new NCCL communicator (drawn on one rank, shipped to the others)."""
+    buf = C.create_string_buffer(128)
+    check(lib().modl_nccl_unique_id(buf, 128))
+    return buf.raw
 
 
 def get_context(device_index):

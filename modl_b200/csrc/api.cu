@@ -49,17 +49,9 @@ extern "C" {
 int modl_version(void) { return 100; }
 const char *modl_last_error(void) { return modl::g_err; }
 
-int modl_ctx_create(int device, modl_ctx **out)
+static int ctx_init(modl_ctx *c, int device)
 {
-    MODL_REQUIRE(out != nullptr, "out is NULL");
-    *out = nullptr;
-    int count = 0;
-    MODL_CUDA_TRY(cudaGetDeviceCount(&count));
-    MODL_REQUIRE(device >= 0 && device < count, "no such CUDA device");
-    MODL_CUDA_TRY(cudaSetDevice(device));
-    modl_ctx *c = new (std::nothrow) modl_ctx();
-    if (!c) return MODL_ENOMEM;
-    c->device = device;
+    CtxGuard g_(c);                      // makes `device` current; the caller's device is restored on return
     MODL_CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     MODL_CUDA_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     MODL_CUDA_TRY(cudaDeviceGetAttribute(&c->cluster_ok, cudaDevAttrClusterLaunch, device));
@@ -67,10 +59,27 @@ int modl_ctx_create(int device, modl_ctx **out)
     if (const char *e = getenv("MODL_CD_WARPS")) c->opt_cd_warps = atoi(e);
     if (const char *e = getenv("MODL_FORCE_GLOBAL_GRAM")) c->opt_force_global_gram = atoi(e);
     if (const char *e = getenv("MODL_TC_GEMM")) c->opt_tc_gemm = atoi(e);
-    if (const char *e = getenv("MODL_BCD_BLOCK")) c->opt_bcd_block = atoi(e);
     int *info = nullptr;
-    if (ws<int>(c, WS_INFO, 4, &info) != MODL_OK) { delete c; return MODL_ECUDA; }
+    MODL_TRY(ws<int>(c, WS_INFO, 4, &info));
     MODL_CUDA_TRY(cudaMemset(info, 0, 4 * sizeof(int)));
+    return MODL_OK;
+}
+
+int modl_ctx_create(int device, modl_ctx **out)
+{
+    MODL_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    MODL_CUDA_TRY(cudaGetDeviceCount(&count));
+    MODL_REQUIRE(device >= 0 && device < count, "no such CUDA device");
+    modl_ctx *c = new (std::nothrow) modl_ctx();
+    if (!c) return MODL_ENOMEM;
+    c->device = device;
+    const int status = ctx_init(c, device);
+    if (status != MODL_OK) {
+        modl_ctx_destroy(c);
+        return status;
+    }
     *out = c;
     return MODL_OK;
 }
@@ -78,9 +87,11 @@ int modl_ctx_create(int device, modl_ctx **out)
 void modl_ctx_destroy(modl_ctx *ctx)
 {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    for (int i = 0; i < WS_COUNT; ++i)
-        if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
+    {
+        CtxGuard g_(ctx);
+        for (int i = 0; i < WS_COUNT; ++i)
+            if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
+    }
     delete ctx;
 }
 
@@ -90,13 +101,14 @@ int64_t modl_ctx_launch_count(const modl_ctx *ctx) { return ctx ? ctx->launches 
 int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value)
 {
     MODL_REQUIRE(ctx && name, "null");
+    CtxGuard g_(ctx);
     if (!strcmp(name, "bcd_cluster")) ctx->opt_bcd_cluster = value;
     else if (!strcmp(name, "cd_warps")) ctx->opt_cd_warps = value;
     else if (!strcmp(name, "force_global_gram")) ctx->opt_force_global_gram = value;
     else if (!strcmp(name, "bcd_timing")) ctx->opt_bcd_timing = value;
     else if (!strcmp(name, "tc_gemm")) ctx->opt_tc_gemm = value;
-    else if (!strcmp(name, "bcd_block")) ctx->opt_bcd_block = value;
     else if (!strcmp(name, "bcd_pilot")) ctx->opt_bcd_pilot = value;
+    else if (!strcmp(name, "bcd_pipeline")) ctx->opt_bcd_pipeline = value;
     else if (!strcmp(name, "bcd_coop_min_cols")) ctx->opt_bcd_coop_min_cols = value;
     else if (!strcmp(name, "bcd_flag_barrier")) ctx->opt_bcd_flag_barrier = value;
     else { set_error("unknown option %s", name); return MODL_EINVAL; }
@@ -106,6 +118,7 @@ int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value)
 int modl_ctx_profile(modl_ctx *ctx, int enable)
 {
     MODL_REQUIRE(ctx, "null ctx");
+    CtxGuard g_(ctx);
     if (enable && !ctx->prof_ev[0]) {
         for (int i = 0; i < 33; ++i) MODL_CUDA_TRY(cudaEventCreate(&ctx->prof_ev[i]));
     }
@@ -130,6 +143,7 @@ int modl_ctx_profile_read(modl_ctx *ctx, double *h_ms, int64_t *h_steps)
 int modl_debug_bcd_timing(modl_ctx *ctx, double *h_gaps7)
 {
     MODL_REQUIRE(ctx && h_gaps7 && ctx->bcd_timing_k > 0 && ctx->slot_ptr[WS_MISC], "no timing recorded");
+    CtxGuard g_(ctx);
     const int k = ctx->bcd_timing_k;
     std::vector<long long> t((size_t)8 * k);
     MODL_CUDA_TRY(cudaDeviceSynchronize());
@@ -158,6 +172,7 @@ int modl_debug_bcd_timing(modl_ctx *ctx, double *h_gaps7)
 int modl_debug_bcd_stamps(modl_ctx *ctx, long long *h_out, int n)
 {
     MODL_REQUIRE(ctx && h_out && n > 0 && ctx->slot_ptr[WS_MISC], "no timing recorded");
+    CtxGuard g_(ctx);
     MODL_CUDA_TRY(cudaDeviceSynchronize());
     MODL_CUDA_TRY(cudaMemcpy(h_out, ctx->slot_ptr[WS_MISC], sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost));
     return MODL_OK;
@@ -168,6 +183,7 @@ int modl_debug_bcd_stamps(modl_ctx *ctx, long long *h_out, int n)
 int modl_ctx_check_info(modl_ctx *ctx, void *stream)
 {
     MODL_REQUIRE(ctx, "null ctx");
+    CtxGuard g_(ctx);
     int h[4] = {0, 0, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
     MODL_CUDA_TRY(cudaMemcpyAsync(h, ctx->slot_ptr[WS_INFO], sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -223,10 +239,12 @@ static int regression(modl_ctx *ctx, const T *G, int64_t g_stride, T *Dx, const 
                         alpha * (T(1) - l1_ratio), tol, max_iter, positive, sweeps, st);
 }
 
-// upload the atom order as int32
-static int upload_order(modl_ctx *ctx, const int64_t *h_order, int64_t k, int32_t **d_order, cudaStream_t st)
+// upload the atom order as int32 (two buffers: the step in flight and the one being prefetched)
+static int upload_order(modl_ctx *ctx, const int64_t *h_order, int64_t k, int32_t **d_order, cudaStream_t st, int slot = 0,
+                        bool ready = false)
 {
-    MODL_TRY(ws<int32_t>(ctx, WS_ORDER, (size_t)k, d_order));
+    MODL_TRY(ws<int32_t>(ctx, slot ? WS_ORDER2 : WS_ORDER, (size_t)k, d_order));
+    if (ready) return MODL_OK;          // uploaded by this step's MODL_PHASE_PREFETCH
     std::vector<int32_t> tmp((size_t)k);
     for (int64_t i = 0; i < k; ++i) {
         MODL_REQUIRE(h_order[i] >= 0 && h_order[i] < k, "order is not a permutation of range(k)");
@@ -243,14 +261,15 @@ template <typename T>
 static int update_dict_impl(modl_ctx *ctx, T *components, int64_t ldd, const T *B, int64_t ldb, const T *C,
                             T *comp_norm, T *G_full, const int64_t *subset, int64_t s, const int64_t *h_order,
                             int64_t k, int64_t p, T comp_l1_ratio, int comp_pos, int mode, double w,
-                            double step_size, T *Dpanel, bool panel_ready, cudaStream_t st, bool bpanel_ready = false)
+                            double step_size, T *Dpanel, bool panel_ready, cudaStream_t st, bool bpanel_ready = false,
+                            int slot = 0, bool order_ready = false, unsigned *start_flag = nullptr, unsigned start_serial = 0)
 {
     MODL_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (variational) or 1 (sgd)");
     if (k <= 0) return MODL_OK;
     const int64_t lds = panel_ld(s);
     T *Bp = nullptr;
     prof_mark(ctx, st, MODL_PROF_DICT_PREP);
-    MODL_TRY(ws<T>(ctx, WS_PANEL_B, (size_t)(k * lds), &Bp));
+    MODL_TRY(ws<T>(ctx, slot ? WS_PANEL_B2 : WS_PANEL_B, (size_t)(k * lds), &Bp));
     if (!panel_ready) MODL_TRY(gather_cols<T>(ctx, components, ldd, k, p, subset, s, Dpanel, lds, nullptr, st));
     if (!bpanel_ready)
         MODL_TRY(gather_cols<T>(ctx, B, ldb, k, p, subset, s, Bp, lds, nullptr, st));   // gradient_[:, subset] = B_[:, subset]
@@ -259,10 +278,11 @@ static int update_dict_impl(modl_ctx *ctx, T *components, int64_t ldd, const T *
         MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, k, k, s, T(-1), Dpanel, lds, Dpanel, lds, T(1), G_full, k, st));
 
     int32_t *d_order = nullptr;
-    MODL_TRY(upload_order(ctx, h_order, k, &d_order, st));
+    MODL_TRY(upload_order(ctx, h_order, k, &d_order, st, slot, order_ready));
     prof_mark(ctx, st, MODL_PROF_DICT_BCD);
     if (mode == 0) {
-        MODL_TRY(bcd_update<T>(ctx, Dpanel, Bp, lds, C, comp_norm, d_order, k, s, comp_l1_ratio, comp_pos, st));
+        MODL_TRY(bcd_update<T>(ctx, Dpanel, Bp, lds, C, comp_norm, d_order, k, s, comp_l1_ratio, comp_pos, st, start_flag,
+                               start_serial));
     } else if (s > 0) {
         // 'sgd' branch [ref: :695-708]: no sequential dependency between atoms
         enet_norm_rows_kernel<T><<<grid_for(ctx, k, 16), 256, 0, st>>>(Dpanel, (int)k, (int)s, lds, comp_l1_ratio,
@@ -335,18 +355,25 @@ static int enet_scale_impl(modl_ctx *ctx, T *X, int64_t rows, int64_t n, int64_t
 // dictionary update works on.
 static int gram_dx_tc(modl_ctx *ctx, const float *D, int64_t ldd, const float *X, int64_t ldx, const int64_t *subset,
                       int64_t kd, int64_t k, int64_t b, int64_t p, float scale, float *G, float *Dx, float *xnorm2,
-                      float *plain_D, int64_t lds, cudaStream_t st, float *plain_X = nullptr)
+                      float *plain_D, int64_t lds, cudaStream_t st, float *plain_X = nullptr, int x_mode = 0)
 {
+    // x_mode 0: everything; 1: only the X rows of the packed panel (+ plain X panel, row norms) -- the part of
+    // the step that does not depend on the dictionary, which MODL_PHASE_PREFETCH runs ahead of time on another
+    // stream; 2: the X rows are already there (the rest of the work).
     const bool want_dx = Dx != nullptr && b > 0;
     const int64_t rows = k + (want_dx ? b : 0);
     float *packed = nullptr;
     MODL_TRY(ws<float>(ctx, WS_TC_A, tc_packed_elems(rows, kd), &packed));
     prof_mark(ctx, st, MODL_PROF_GATHER);
-    MODL_TRY(tc_pack_rows(ctx, D, ldd, k, p, subset, kd, packed, 0, want_dx ? k : tc_rows_padded(k), plain_D, lds, nullptr, st));
-    if (want_dx)
-        MODL_TRY(tc_pack_rows(ctx, X, ldx, b, p, subset, kd, packed, k, tc_rows_padded(k + b), plain_X, lds, xnorm2, st));
-    else if (xnorm2 && b > 0)
-        MODL_TRY(gather_cols<float>(ctx, X, ldx, b, p, nullptr, 0, (float *)nullptr, 0, xnorm2, st));
+    if (x_mode != 1)
+        MODL_TRY(tc_pack_rows(ctx, D, ldd, k, p, subset, kd, packed, 0, want_dx ? k : tc_rows_padded(k), plain_D, lds, nullptr, st));
+    if (x_mode != 2) {
+        if (want_dx)
+            MODL_TRY(tc_pack_rows(ctx, X, ldx, b, p, subset, kd, packed, k, tc_rows_padded(k + b), plain_X, lds, xnorm2, st));
+        else if (xnorm2 && b > 0)
+            MODL_TRY(gather_cols<float>(ctx, X, ldx, b, p, nullptr, 0, (float *)nullptr, 0, xnorm2, st));
+    }
+    if (x_mode == 1) return MODL_OK;
     prof_mark(ctx, st, MODL_PROF_GRAM);
     if (G != nullptr && (!want_dx || Dx == G + k * k)) {
         MODL_TRY(tc_gemm(ctx, packed, packed, rows, k, kd, scale, 0.f, G, k, 128, st)); // G and Dx are one (k + b) x k matrix
@@ -367,9 +394,11 @@ static inline bool use_tc(const modl_ctx *ctx) { return std::is_same<T, float>::
 // G / Dx / xnorm2 products; panel (optional out): where D_sub (k x s) was left
 template <typename T>
 static int gram_dx_impl(modl_ctx *ctx, const T *D, int64_t ldd, const T *X, int64_t ldx, const int64_t *subset, int64_t s,
-                        int64_t k, int64_t b, int64_t p, T scale, T *G, T *Dx, T *xnorm2, T **panel_out, cudaStream_t st)
+                        int64_t k, int64_t b, int64_t p, T scale, T *G, T *Dx, T *xnorm2, T **panel_out, cudaStream_t st,
+                        int x_mode = 0)
 {
     MODL_REQUIRE(ctx && D && k >= 1 && p >= 1 && b >= 0, "gram_dx arguments");
+    MODL_REQUIRE(x_mode == 0 || subset != nullptr, "the split X / D gather needs a feature subset");
     MODL_REQUIRE(X != nullptr || (Dx == nullptr && xnorm2 == nullptr), "X required for Dx / xnorm2");
     if (subset == nullptr) {
         if constexpr (std::is_same<T, float>::value) {
@@ -389,18 +418,23 @@ static int gram_dx_impl(modl_ctx *ctx, const T *D, int64_t ldd, const T *X, int6
     MODL_REQUIRE(s >= 0 && s <= p, "subset length");
     const int64_t lds = panel_ld(s);
     T *panel = nullptr;
-    MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)((k + b) * lds), &panel));
-    T *Dsub = panel, *Xsub = panel + k * lds;
+    // D_sub and X_sub panels live in separate slots: the prefetch of step t+1 rewrites X_sub (whose row pitch changes
+    // with the subset length) while the dictionary update of step t still works on D_sub
+    T *Xsub = nullptr;
+    MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)(k * lds), &panel));
+    MODL_TRY(ws<T>(ctx, WS_PANEL_X, (size_t)((b > 0 ? b : 1) * lds), &Xsub));
+    T *Dsub = panel;
     if constexpr (std::is_same<T, float>::value) {
         if (use_tc<T>(ctx) && s > 0 && (G || (Dx && b > 0))) {
             if (panel_out) *panel_out = Dsub;
-            return gram_dx_tc(ctx, D, ldd, X, ldx, subset, s, k, b, p, scale, G, Dx, xnorm2, Dsub, lds, st, Xsub);
+            return gram_dx_tc(ctx, D, ldd, X, ldx, subset, s, k, b, p, scale, G, Dx, xnorm2, Dsub, lds, st, Xsub, x_mode);
         }
     }
     prof_mark(ctx, st, MODL_PROF_GATHER);
-    MODL_TRY(gather_cols<T>(ctx, D, ldd, k, p, subset, s, Dsub, lds, nullptr, st));
-    if (b > 0 && (Dx || xnorm2))
+    if (x_mode != 1) MODL_TRY(gather_cols<T>(ctx, D, ldd, k, p, subset, s, Dsub, lds, nullptr, st));
+    if (x_mode != 2 && b > 0 && (Dx || xnorm2))
         MODL_TRY(gather_cols<T>(ctx, X, ldx, b, p, subset, s, Dx ? Xsub : (T *)nullptr, lds, xnorm2, st));
+    if (x_mode == 1) return MODL_OK;
     prof_mark(ctx, st, MODL_PROF_GRAM);
     if (G) MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, k, k, s, scale, Dsub, lds, Dsub, lds, T(0), G, k, st));
     if (Dx && b > 0) MODL_TRY(gemm_simt<T>(ctx, A_KMAJOR, B_KMAJOR, b, k, s, scale, Xsub, lds, Dsub, lds, T(0), Dx, k, st));
@@ -476,43 +510,63 @@ static int update_stats_impl(modl_ctx *ctx, const T *code, const int64_t *indice
     return MODL_OK;
 }
 
-// What the dictionary update waits for, and nothing else: inc_sub = a [code^T code | code^T X[:, subset]]
-// (k x k, then k x lds).  Xsub is the plain b x lds panel of X[:, subset].
-template <typename T>
-static int stats_sub_impl(modl_ctx *ctx, const T *cb, const T *Xsub, int64_t lds, int64_t s, T *inc_sub, T a, int64_t b,
-                          int64_t k, cudaStream_t st)
+// Packed X[:, subset]^T (the B operand of the subset statistics product) -- depends on the batch and the subset
+// only, so MODL_PHASE_PREFETCH builds it ahead of time.  The packed code^T is appended at the next tile boundary.
+static inline int64_t xs_split(int64_t s) { return s > 0 ? round_up(s, 128) : 0; }
+static int pack_xsub(modl_ctx *ctx, const float *Xsub, int64_t lds, int64_t s, int64_t b, int64_t k, float **XsP, cudaStream_t st,
+                     bool do_pack)
 {
-    if constexpr (std::is_same<T, float>::value) {
-        if (use_tc<T>(ctx)) {
-            float *codeP = nullptr, *XsP = nullptr;
-            MODL_TRY(ws<float>(ctx, WS_TC_CODE, tc_packed_elems(k, b), &codeP));
-            MODL_TRY(tc_pack_cols(ctx, cb, k, b, k, codeP, 128, st));
-            ctx->code_packed = 1;
-            MODL_TRY(tc_gemm(ctx, codeP, codeP, k, k, b, a, 0.f, inc_sub, k, 128, st));
-            if (s > 0) {
-                MODL_TRY(ws<float>(ctx, WS_TC_XS, tc_packed_elems(s, b), &XsP));
-                MODL_TRY(tc_pack_cols(ctx, Xsub, lds, b, s, XsP, 128, st));
-                MODL_TRY(tc_gemm(ctx, codeP, XsP, k, s, b, a, 0.f, inc_sub + k * k, lds, 128, st));
-            }
-            return MODL_OK;
-        }
-    }
-    MODL_TRY(gemm_simt<T>(ctx, A_MMAJOR, B_NMAJOR, k, k, b, a, cb, k, cb, k, T(0), inc_sub, k, st));
-    if (s > 0) MODL_TRY(gemm_simt<T>(ctx, A_MMAJOR, B_NMAJOR, k, s, b, a, cb, k, Xsub, lds, T(0), inc_sub + k * k, lds, st));
+    MODL_TRY(ws<float>(ctx, WS_TC_XS, tc_packed_elems(xs_split(s) + k, b), XsP));
+    if (do_pack && s > 0) MODL_TRY(tc_pack_cols(ctx, Xsub, lds, b, s, *XsP, 128, st));
     return MODL_OK;
 }
 
-// The full-width statistic on whatever stream the caller chose: out = be * out + a * code^T X  (k x p)
+// What the dictionary update waits for, and nothing else:
+//   raw (sharded) form: inc_sub = a [code^T code | code^T X[:, subset]]   (k x k, then k x lds), summed over ranks by the caller;
+//   fused (one GPU) form, inc_sub == NULL:  C_ = keep C_ + a code^T code  and  Bp = keep Bp + a code^T X[:, subset], where Bp
+//   already holds B_[:, subset] -- ONE tensor-core launch, [Bp | C_] = code^T [X_sub | code] with the decay in the epilogue.
+// Xsub is the plain b x lds panel of X[:, subset]; xs_packed says its packed transpose is already in WS_TC_XS.
+template <typename T>
+static int stats_sub_impl(modl_ctx *ctx, const T *cb, const T *Xsub, int64_t lds, int64_t s, T *inc_sub, T *Cmat, T *Bp, T a,
+                          T keep, int64_t b, int64_t k, cudaStream_t st, bool xs_packed)
+{
+    T *outC = inc_sub ? inc_sub : Cmat, *outB = inc_sub ? inc_sub + k * k : Bp;
+    const T be = inc_sub ? T(0) : keep;
+    if constexpr (std::is_same<T, float>::value) {
+        if (use_tc<T>(ctx)) {
+            float *XsP = nullptr;
+            MODL_TRY(pack_xsub(ctx, Xsub, lds, s, b, k, &XsP, st, !xs_packed));
+            const int64_t nkb = ceil_div(b, 32);
+            float *codeP = XsP + (size_t)(xs_split(s) / 128) * nkb * (2 * 128 * 32);
+            MODL_TRY(tc_pack_cols(ctx, cb, k, b, k, codeP, 128, st));
+            ctx->code_packed = codeP;
+            if (s > 0)
+                return tc_gemm(ctx, codeP, XsP, k, xs_split(s) + k, b, a, be, outB, lds, 128, st, WS_GEMM_PART, outC, k, xs_split(s), s);
+            return tc_gemm(ctx, codeP, codeP, k, k, b, a, be, outC, k, 128, st);
+        }
+    }
+    MODL_TRY(gemm_simt<T>(ctx, A_MMAJOR, B_NMAJOR, k, k, b, a, cb, k, cb, k, be, outC, k, st));
+    if (s > 0) MODL_TRY(gemm_simt<T>(ctx, A_MMAJOR, B_NMAJOR, k, s, b, a, cb, k, Xsub, lds, be, outB, lds, st));
+    return MODL_OK;
+}
+
+// The full-width statistic on whatever stream the caller chose: out = be * out + a * code^T X  (k x p).
+// sm_avail: SMs the product may count on (the dictionary update's cluster holds the others while it runs).
 template <typename T>
 static int stats_b_impl(modl_ctx *ctx, const T *cb, const T *X, int64_t ldx, T *out, int64_t ldo, T a, T be, int64_t b,
-                        int64_t k, int64_t p, cudaStream_t st)
+                        int64_t k, int64_t p, cudaStream_t st, int sm_avail)
 {
     if constexpr (std::is_same<T, float>::value) {
         if (use_tc<T>(ctx)) {
-            float *codeP = nullptr, *XP = nullptr;
-            MODL_TRY(ws<float>(ctx, WS_TC_CODE, tc_packed_elems(k, b), &codeP));
-            if (!ctx->code_packed) MODL_TRY(tc_pack_cols(ctx, cb, k, b, k, codeP, 128, st));
-            const int bn = tc_pick_bn(ctx, p, ceil_div(k, 128));
+            const float *codeP = ctx->code_packed;
+            float *XP = nullptr;
+            if (!codeP) {
+                float *cp = nullptr;
+                MODL_TRY(ws<float>(ctx, WS_TC_CODE, tc_packed_elems(k, b), &cp));
+                MODL_TRY(tc_pack_cols(ctx, cb, k, b, k, cp, 128, st));
+                codeP = cp;
+            }
+            const int bn = tc_pick_bn(ctx, p, ceil_div(k, 128), sm_avail);
             MODL_TRY(ws<float>(ctx, WS_TC_X, tc_packed_elems(p, b, bn), &XP));
             MODL_TRY(tc_pack_cols(ctx, X, ldx, b, p, XP, bn, st));
             return tc_gemm(ctx, codeP, XP, k, p, b, a, be, out, ldo, bn, st, WS_GEMM_PART2);
@@ -538,7 +592,7 @@ static int update_dict_entry(modl_ctx *ctx, T *components, int64_t ldd, const T 
 // the fused step  [ref: dict_fact.py:507-533, 577-648]
 // ---------------------------------------------------------------------------------------
 template <typename T>
-static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream)
+int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream)
 {
     MODL_REQUIRE(ctx && q, "null arguments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -550,21 +604,35 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     MODL_REQUIRE(q->G_agg != MODL_AGG_FULL || q->G_full, "G_agg='full' needs G_full");
     MODL_REQUIRE(q->G_agg != MODL_AGG_AVERAGE || (q->G_average && q->w_sample), "G_agg='average' needs G_average, w_sample");
     MODL_REQUIRE(q->Dx_agg != MODL_AGG_AVERAGE || (q->Dx_average && q->w_sample), "Dx_agg='average' needs Dx_average, w_sample");
+    MODL_REQUIRE(q->slot == 0 || q->slot == 1, "slot");
     ctx->prof_n = 0;
     prof_mark(ctx, st, MODL_PROF_GATHER);
     const T *X = static_cast<const T *>(q->X);
     T *D = static_cast<T *>(q->components);
     T *code = static_cast<T *>(q->code);
     const T r = (T)q->reduction;
-    const bool reuse_subset = (q->phases & MODL_PHASE_REUSE_SUBSET) != 0;
-    const int phases = (q->phases & ~MODL_PHASE_REUSE_SUBSET) ? (q->phases & ~MODL_PHASE_REUSE_SUBSET)
-                                                              : (MODL_PHASE_CODE | MODL_PHASE_STATS | MODL_PHASE_APPLY | MODL_PHASE_DICT);
+    const int flag_bits = MODL_PHASE_REUSE_SUBSET | MODL_PHASE_INPUTS_READY | MODL_PHASE_FUSED_APPLY;
+    const bool inputs_ready = (q->phases & MODL_PHASE_INPUTS_READY) != 0;     // this step's MODL_PHASE_PREFETCH has run
+    const bool reuse_subset = (q->phases & MODL_PHASE_REUSE_SUBSET) != 0 || inputs_ready;
+    const bool fused_apply = (q->phases & MODL_PHASE_FUSED_APPLY) != 0;
+    const int phases = (q->phases & ~flag_bits) ? (q->phases & ~flag_bits)
+                                                : (MODL_PHASE_CODE | MODL_PHASE_STATS | MODL_PHASE_APPLY | MODL_PHASE_DICT);
+    const int slot = q->slot;
     T *inc = static_cast<T *>(q->stats_inc);
     T *inc_sub = static_cast<T *>(q->inc_sub);
+    const double bt = (double)(q->global_batch > 0 ? q->global_batch : b);
+    const T av = q->optimizer_sgd ? (T)(1.0 / bt) : (T)(q->w / bt);
+    const T keep = q->optimizer_sgd ? T(0) : (T)(1.0 - q->w);
+    const int64_t lds = panel_ld(s);
+    // which parts of the code phase work on the feature subset [ref: :589-604]
+    const bool need_sub = q->Dx_agg != MODL_AGG_FULL || q->G_agg != MODL_AGG_FULL;
+    const bool dx_sub = q->Dx_agg != MODL_AGG_FULL;
+    const bool g_sub = q->G_agg != MODL_AGG_FULL;
+    const bool x_ahead = need_sub && dx_sub && s > 0;     // the X side of the gather can run ahead of the dictionary
+
     if (phases == MODL_PHASE_APPLY_B) {
         // B_ = (1-w) B_ + all-reduced increments; touches no workspace, so it may run on a side stream
         MODL_REQUIRE(inc != nullptr, "APPLY_B without stats_inc");
-        const T keep = q->optimizer_sgd ? T(0) : (T)(1.0 - q->w);
         xpby_kernel<T><<<grid_for(ctx, ceil_div(k * p, 256), 8), 256, 0, st>>>(static_cast<T *>(q->B), inc + k * k, k * p, keep);
         MODL_LAUNCH_CHECK(ctx);
         ctx->prof_n = 0;
@@ -573,25 +641,23 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     if (phases == MODL_PHASE_STATS_B) {
         // full-width B statistic from the batch code left in the workspace by this step's CODE phase
         MODL_REQUIRE(ctx->slot_ptr[WS_CODE_BATCH] != nullptr, "STATS_B before any CODE phase");
-        const double bt = (double)(q->global_batch > 0 ? q->global_batch : b);
-        const T av = q->optimizer_sgd ? (T)(1.0 / bt) : (T)(q->w / bt);
         const T *cbp = static_cast<const T *>(ctx->slot_ptr[WS_CODE_BATCH]);
         ctx->prof_n = 0;
-        if (inc) return stats_b_impl<T>(ctx, cbp, X, q->ldx, inc + k * k, p, av, T(0), b, k, p, st);
-        const T keep = q->optimizer_sgd ? T(0) : (T)(1.0 - q->w);
-        return stats_b_impl<T>(ctx, cbp, X, q->ldx, static_cast<T *>(q->B), p, av, keep, b, k, p, st);
+        if (inc) return stats_b_impl<T>(ctx, cbp, X, q->ldx, inc + k * k, p, av, T(0), b, k, p, st, q->sm_avail);
+        return stats_b_impl<T>(ctx, cbp, X, q->ldx, static_cast<T *>(q->B), p, av, keep, b, k, p, st, q->sm_avail);
     }
     MODL_REQUIRE(!(phases & (MODL_PHASE_APPLY_B | MODL_PHASE_STATS_B)), "APPLY_B / STATS_B run in calls of their own");
-    MODL_REQUIRE(!(phases & MODL_PHASE_STATS_SUB) || ((phases & MODL_PHASE_CODE) && inc_sub && !(phases & MODL_PHASE_STATS)),
-                 "STATS_SUB needs CODE in the same call, inc_sub, and excludes STATS");
+    MODL_REQUIRE(!(phases & MODL_PHASE_STATS_SUB) || ((phases & MODL_PHASE_CODE) && (inc_sub || fused_apply) && !(phases & MODL_PHASE_STATS)),
+                 "STATS_SUB needs CODE in the same call, inc_sub (or FUSED_APPLY), and excludes STATS");
     MODL_REQUIRE(!(phases & MODL_PHASE_APPLY_SUB) || inc_sub, "APPLY_SUB without inc_sub");
     MODL_REQUIRE(!(phases & MODL_PHASE_STATS) || (phases & MODL_PHASE_CODE), "STATS phase needs CODE in the same call");
     MODL_REQUIRE(inc != nullptr || q->phases == 0 || !(phases & MODL_PHASE_APPLY) || (phases & MODL_PHASE_STATS),
                  "APPLY without stats_inc");
+    MODL_REQUIRE(!(phases & MODL_PHASE_PREFETCH) || phases == MODL_PHASE_PREFETCH, "PREFETCH runs in a call of its own");
 
     // subset -> device
     int64_t *d_subset = nullptr;
-    MODL_TRY(ws<int64_t>(ctx, WS_SUBSET, (size_t)(s > 0 ? s : 1), &d_subset));
+    MODL_TRY(ws<int64_t>(ctx, slot ? WS_SUBSET2 : WS_SUBSET, (size_t)(s > 0 ? s : 1), &d_subset));
     if (s > 0 && !reuse_subset)
         MODL_CUDA_TRY(cudaMemcpyAsync(d_subset, q->h_subset, sizeof(int64_t) * (size_t)s, cudaMemcpyHostToDevice, st));
 
@@ -601,15 +667,41 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     Dxw = Gw + k * k;
     MODL_TRY(ws<T>(ctx, WS_CODE_BATCH, (size_t)(b * k), &cb));
 
+    if (phases == MODL_PHASE_PREFETCH) {
+        // Everything of the step that depends on the batch, the subset and the atom order but NOT on the
+        // dictionary or on this step's codes: index uploads, the X side of the subset gather (packed rows,
+        // row norms), the packed X[:, subset]^T operand of the subset statistics and, on one GPU, the
+        // B_[:, subset] panel the fused statistics product accumulates into.  Runs on another stream while
+        // the previous step's dictionary update holds its 16 SMs.
+        int32_t *d_order = nullptr;
+        MODL_TRY(upload_order(ctx, q->h_order, k, &d_order, st, slot));
+        if (x_ahead) {
+            MODL_TRY(gram_dx_impl<T>(ctx, D, p, X, q->ldx, d_subset, s, k, b, p, r, g_sub ? Gw : (T *)nullptr, Dxw, xnorm2, &panel, st, 1));
+            if constexpr (std::is_same<T, float>::value) {
+                if (use_tc<T>(ctx)) {
+                    float *XsP = nullptr;
+                    float *Xs = nullptr;
+                    MODL_TRY(ws<float>(ctx, WS_PANEL_X, (size_t)(b * lds), &Xs));
+                    MODL_TRY(pack_xsub(ctx, Xs, lds, s, b, k, &XsP, st, true));
+                }
+            }
+        }
+        if (fused_apply && s > 0) {
+            T *Bp = nullptr;
+            MODL_TRY(ws<T>(ctx, slot ? WS_PANEL_B2 : WS_PANEL_B, (size_t)(k * lds), &Bp));
+            MODL_TRY(gather_cols<T>(ctx, static_cast<const T *>(q->B), p, k, p, d_subset, s, Bp, lds, nullptr, st));
+        }
+        ctx->prof_n = 0;
+        return MODL_OK;
+    }
+
     T *panel_keep = nullptr;
     if (phases & MODL_PHASE_CODE) {
     // ---- _compute_code [ref: :577-648] ----
-    const bool need_sub = q->Dx_agg != MODL_AGG_FULL || q->G_agg != MODL_AGG_FULL;
-    const bool dx_sub = q->Dx_agg != MODL_AGG_FULL;
-    const bool g_sub = q->G_agg != MODL_AGG_FULL;
+    const int x_mode = (inputs_ready && x_ahead) ? 2 : 0;
     if (need_sub) {
         MODL_TRY(gram_dx_impl<T>(ctx, D, p, X, q->ldx, d_subset, s, k, b, p, r, g_sub ? Gw : (T *)nullptr,
-                                 dx_sub ? Dxw : (T *)nullptr, xnorm2, &panel, st));
+                                 dx_sub ? Dxw : (T *)nullptr, xnorm2, &panel, st, x_mode));
     }
     if (!dx_sub) {   // Dx = X . D^T over all features [ref: :592]
         MODL_TRY(gram_dx_impl<T>(ctx, D, p, X, q->ldx, nullptr, 0, k, b, p, T(1), (T *)nullptr, Dxw,
@@ -646,18 +738,26 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
                            (T)q->code_alpha, q->code_pos, (T)q->tol, q->max_iter, q->sweeps, st));
 
     panel_keep = panel;
-    ctx->code_packed = 0;
+    ctx->code_packed = nullptr;
     if (phases & MODL_PHASE_STATS_SUB) {
         prof_mark(ctx, st, MODL_PROF_STATS);
-        const int64_t lds = panel_ld(s);
-        T *pn = nullptr;
-        MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)((k + b) * lds), &pn));
-        T *Xsub = pn + k * lds;
-        if (!(need_sub && dx_sub && s > 0))       // X[:, subset] was not gathered by the code phase (Dx_agg == 'full')
+        T *Xsub = nullptr;
+        MODL_TRY(ws<T>(ctx, WS_PANEL_X, (size_t)(b * lds), &Xsub));
+        const bool x_there = need_sub && dx_sub && s > 0;   // X[:, subset] was gathered by the code phase (or its prefetch)
+        if (!x_there)                                       // Dx_agg == 'full'
             MODL_TRY(gather_cols<T>(ctx, X, q->ldx, b, p, d_subset, s, Xsub, lds, nullptr, st));
-        const double bt = (double)(q->global_batch > 0 ? q->global_batch : b);
-        const T av = q->optimizer_sgd ? (T)(1.0 / bt) : (T)(q->w / bt);
-        MODL_TRY(stats_sub_impl<T>(ctx, cb, Xsub, lds, s, inc_sub, av, b, k, st));
+        T *Bp = nullptr;
+        if (fused_apply) {
+            MODL_TRY(ws<T>(ctx, slot ? WS_PANEL_B2 : WS_PANEL_B, (size_t)(k * lds), &Bp));
+            if (!inputs_ready && s > 0)
+                MODL_TRY(gather_cols<T>(ctx, static_cast<const T *>(q->B), p, k, p, d_subset, s, Bp, lds, nullptr, st));
+        }
+        MODL_TRY(stats_sub_impl<T>(ctx, cb, Xsub, lds, s, fused_apply ? (T *)nullptr : inc_sub, static_cast<T *>(q->C), Bp, av,
+                                   keep, b, k, st, inputs_ready && x_there));
+        if (fused_apply) {
+            ctx->panel_b_ready = 1;
+            if (q->ev_after_apply_sub) MODL_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(q->ev_after_apply_sub), st));
+        }
     }
     // ---- _update_C / _update_B [ref: :559-575] ----
     if (phases & MODL_PHASE_STATS) {
@@ -668,7 +768,7 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
                                           st, q->global_batch, true));
             if (inc_sub) {   // compact copy of what the dictionary update needs first: [C inc | B inc[:, subset]]
                 MODL_CUDA_TRY(cudaMemcpyAsync(inc_sub, inc, sizeof(T) * (size_t)(k * k), cudaMemcpyDeviceToDevice, st));
-                MODL_TRY(gather_cols<T>(ctx, inc + k * k, p, k, p, d_subset, s, inc_sub + k * k, panel_ld(s), nullptr, st));
+                MODL_TRY(gather_cols<T>(ctx, inc + k * k, p, k, p, d_subset, s, inc_sub + k * k, lds, nullptr, st));
             }
         }
         else
@@ -678,7 +778,6 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     }   // MODL_PHASE_CODE
     if ((phases & MODL_PHASE_APPLY) && inc) {
         prof_mark(ctx, st, MODL_PROF_STATS);
-        const T keep = q->optimizer_sgd ? T(0) : (T)(1.0 - q->w);
         xpby_kernel<T><<<grid_for(ctx, ceil_div(k * k, 256), 4), 256, 0, st>>>(static_cast<T *>(q->C), inc, k * k, keep);
         MODL_LAUNCH_CHECK(ctx);
         xpby_kernel<T><<<grid_for(ctx, ceil_div(k * p, 256), 8), 256, 0, st>>>(static_cast<T *>(q->B), inc + k * k, k * p, keep);
@@ -686,12 +785,10 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     }
     if (phases & MODL_PHASE_APPLY_SUB) {
         prof_mark(ctx, st, MODL_PROF_STATS);
-        const T keep = q->optimizer_sgd ? T(0) : (T)(1.0 - q->w);
-        const int64_t lds = panel_ld(s);
         xpby_kernel<T><<<grid_for(ctx, ceil_div(k * k, 256), 4), 256, 0, st>>>(static_cast<T *>(q->C), inc_sub, k * k, keep);
         MODL_LAUNCH_CHECK(ctx);
         T *Bp = nullptr;
-        MODL_TRY(ws<T>(ctx, WS_PANEL_B, (size_t)(k * lds), &Bp));
+        MODL_TRY(ws<T>(ctx, slot ? WS_PANEL_B2 : WS_PANEL_B, (size_t)(k * lds), &Bp));
         if (s > 0) {
             gather_axpby_kernel<T><<<grid_for(ctx, k, 16), 256, 0, st>>>(static_cast<const T *>(q->B), p, (int)k, d_subset, (int)s,
                                                                           keep, inc_sub + k * k, lds, Bp, lds);
@@ -704,11 +801,12 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     // ---- _update_dict [ref: :650-715] ----
     T *Dpanel = panel_keep;
     bool ready = panel_keep != nullptr;
-    if (!ready) MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)(k * panel_ld(s)), &Dpanel));
+    if (!ready) MODL_TRY(ws<T>(ctx, WS_PANEL_DX, (size_t)(k * lds), &Dpanel));
     MODL_TRY(update_dict_impl<T>(ctx, D, p, static_cast<const T *>(q->B), p, static_cast<const T *>(q->C),
                                  static_cast<T *>(q->comp_norm), q->G_agg == MODL_AGG_FULL ? static_cast<T *>(q->G_full) : (T *)nullptr,
                                  d_subset, s, q->h_order, k, p, (T)q->comp_l1_ratio, q->comp_pos, q->optimizer_sgd ? 1 : 0, q->w,
-                                 q->step_size, Dpanel, ready, st, ctx->panel_b_ready != 0));
+                                 q->step_size, Dpanel, ready, st, ctx->panel_b_ready != 0, slot, inputs_ready,
+                                 static_cast<unsigned *>(q->start_flag), q->start_serial));
     ctx->panel_b_ready = 0;
     }   // MODL_PHASE_DICT
     if (ctx->prof_on && ctx->prof_n > 0) {
@@ -725,6 +823,9 @@ static int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream
     return MODL_OK;
 }
 
+template int batch_fit_impl<float>(modl_ctx *, const modl_step_params *, void *);
+template int batch_fit_impl<double>(modl_ctx *, const modl_step_params *, void *);
+
 }  // namespace modl
 
 // ---------------------------------------------------------------------------------------
@@ -734,29 +835,30 @@ extern "C" {
 
 #define MODL_DEFINE_TYPED(SFX, T)                                                                                           \
     int modl_enet_norm_##SFX(modl_ctx *c, const T *v, int64_t rows, int64_t n, int64_t ld, T l1, T *out, void *st)          \
-    { return enet_norm_impl<T>(c, v, rows, n, ld, l1, out, st); }                                                           \
+    { CtxGuard g_(c); return enet_norm_impl<T>(c, v, rows, n, ld, l1, out, st); }                                                           \
     int modl_enet_projection_##SFX(modl_ctx *c, const T *v, T *out, int64_t rows, int64_t n, int64_t ld, const T *radius,   \
                                    T l1, void *st)                                                                          \
-    { return enet_projection_impl<T>(c, v, out, rows, n, ld, radius, l1, st); }                                             \
+    { CtxGuard g_(c); return enet_projection_impl<T>(c, v, out, rows, n, ld, radius, l1, st); }                                             \
     int modl_enet_scale_##SFX(modl_ctx *c, T *X, int64_t rows, int64_t n, int64_t ld, T l1, T radius, void *st)             \
-    { return enet_scale_impl<T>(c, X, rows, n, ld, l1, radius, st); }                                                       \
+    { CtxGuard g_(c); return enet_scale_impl<T>(c, X, rows, n, ld, l1, radius, st); }                                                       \
     int modl_gram_dx_##SFX(modl_ctx *c, const T *D, int64_t ldd, const T *X, int64_t ldx, const int64_t *subset, int64_t s, \
                            int64_t k, int64_t b, int64_t p, T scale, T *G, T *Dx, T *xnorm2, void *st)                      \
-    { return gram_dx_impl<T>(c, D, ldd, X, ldx, subset, s, k, b, p, scale, G, Dx, xnorm2, nullptr, (cudaStream_t)st); }     \
+    { CtxGuard g_(c); return gram_dx_impl<T>(c, D, ldd, X, ldx, subset, s, k, b, p, scale, G, Dx, xnorm2, nullptr, (cudaStream_t)st); }     \
     int modl_enet_regression_single_gram_##SFX(modl_ctx *c, const T *G, T *Dx, const T *X, int64_t ldx, int64_t p,          \
                                                const T *xnorm2, T *code, const int64_t *indices, int64_t b, int64_t k,      \
                                                T l1, T alpha, int positive, T tol, int max_iter, int32_t *sweeps, void *st) \
-    { return regression_entry<T>(c, G, 0, Dx, X, ldx, p, xnorm2, code, indices, b, k, l1, alpha, positive, tol, max_iter,   \
+    { CtxGuard g_(c); return regression_entry<T>(c, G, 0, Dx, X, ldx, p, xnorm2, code, indices, b, k, l1, alpha, positive, tol, max_iter,   \
                                  sweeps, st); }                                                                             \
     int modl_enet_regression_multi_gram_##SFX(modl_ctx *c, const T *G, T *Dx, const T *X, int64_t ldx, int64_t p,           \
                                               const T *xnorm2, T *code, const int64_t *indices, int64_t b, int64_t k,       \
                                               T l1, T alpha, int positive, T tol, int max_iter, int32_t *sweeps, void *st)  \
-    { return regression_entry<T>(c, G, k * k, Dx, X, ldx, p, xnorm2, code, indices, b, k, l1, alpha, positive, tol,         \
+    { CtxGuard g_(c); return regression_entry<T>(c, G, k * k, Dx, X, ldx, p, xnorm2, code, indices, b, k, l1, alpha, positive, tol,         \
                                  max_iter, sweeps, st); }                                                                   \
     int modl_update_G_average_##SFX(modl_ctx *c, T *Gav, const T *G, const T *w, const int64_t *indices, int64_t b,         \
                                     int64_t k, void *st)                                                                    \
     {                                                                                                                       \
         MODL_REQUIRE(c && Gav && G && w && b >= 0 && k >= 1, "update_G_average arguments");                                 \
+        CtxGuard g_(c);                                                                                                     \
         if (b == 0) return MODL_OK;                                                                                         \
         dim3 grid((unsigned)grid_for(c, ceil_div(k * k, 256), 2), (unsigned)(b < 65535 ? b : 65535));                       \
         update_g_average_kernel<T><<<grid, 256, 0, (cudaStream_t)st>>>(Gav, G, w, indices, (int)b, k * k);                  \
@@ -767,6 +869,7 @@ extern "C" {
                                      void *st)                                                                              \
     {                                                                                                                       \
         MODL_REQUIRE(c && Dav && Dx && w && b >= 0 && k >= 1, "update_Dx_average arguments");                               \
+        CtxGuard g_(c);                                                                                                     \
         if (b == 0) return MODL_OK;                                                                                         \
         update_dx_average_kernel<T><<<grid_for(c, b, 16), 128, 0, (cudaStream_t)st>>>(Dav, Dx, w, indices, (int)b, (int)k); \
         MODL_LAUNCH_CHECK(c);                                                                                               \
@@ -774,13 +877,14 @@ extern "C" {
     }                                                                                                                       \
     int modl_update_stats_##SFX(modl_ctx *c, const T *code, const int64_t *indices, const T *X, int64_t ldx, T *C, T *B,    \
                                 int64_t ldb, double w, int64_t b, int64_t k, int64_t p, int overwrite, void *st)            \
-    { return update_stats_impl<T>(c, code, indices, X, ldx, C, B, ldb, w, b, k, p, overwrite, (cudaStream_t)st); }          \
+    { CtxGuard g_(c); return update_stats_impl<T>(c, code, indices, X, ldx, C, B, ldb, w, b, k, p, overwrite, (cudaStream_t)st); }          \
     int modl_update_dict_##SFX(modl_ctx *c, T *comp, int64_t ldd, const T *B, int64_t ldb, const T *C, T *comp_norm,        \
                                T *G_full, const int64_t *subset, int64_t s, const int64_t *h_order, int64_t k, int64_t p,   \
                                T l1, int pos, int mode, double w, double step, void *st)                                    \
-    { return update_dict_entry<T>(c, comp, ldd, B, ldb, C, comp_norm, G_full, subset, s, h_order, k, p, l1, pos, mode, w,   \
+    { CtxGuard g_(c); return update_dict_entry<T>(c, comp, ldd, B, ldb, C, comp_norm, G_full, subset, s, h_order, k, p, l1, pos, mode, w,   \
                                   step, st); }                                                                              \
-    int modl_batch_fit_##SFX(modl_ctx *c, const modl_step_params *prm, void *st) { return batch_fit_impl<T>(c, prm, st); }
+    int modl_batch_fit_##SFX(modl_ctx *c, const modl_step_params *prm, void *st)                                            \
+    { CtxGuard g_(c); return batch_fit_impl<T>(c, prm, st); }
 
 MODL_DEFINE_TYPED(f32, float)
 MODL_DEFINE_TYPED(f64, double)

@@ -73,7 +73,20 @@ struct BcdParams {
     T *part;             // [2][nblk][BCD_NPART]       (global exchange, use_cluster == 0)
     T *vrow;             // [2][s]   candidate rows (elastic-net ball only)
     long long *timing;   // debug: [k][8] clock64 stamps of CTA 0 (NULL = off)
+    unsigned *start_flag;    // optional: *start_flag = start_serial as soon as every CTA of the launch is resident
+    unsigned start_serial;   //   (the second stream of modl_partial_fit_* waits for it, so that its kernels cannot
+                             //   take the SMs this launch needs to be placed)
 };
+
+// "the whole launch is resident": called by one thread after the first cluster / grid-wide barrier
+template <typename T>
+__device__ __forceinline__ void bcd_signal_start(const BcdParams<T> &P)
+{
+    if (P.start_flag != nullptr) {
+        *reinterpret_cast<volatile unsigned *>(P.start_flag) = P.start_serial;
+        __threadfence_system();
+    }
+}
 
 // 1 / sqrt(x): the hardware approximation plus one Newton step (float), exact division (double)
 __device__ __forceinline__ float bcd_rsqrt(float x)
@@ -121,12 +134,14 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Bounded spin: a protocol error becomes a trap (launch failure), never a hung GPU.
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
     unsigned done = 0;
-    while (!done) {
+    for (unsigned spin = 0; !done; ++spin) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && spin > (1u << 22)) __trap();
     }
 }
 
@@ -335,6 +350,7 @@ bcd_update_kernel(BcdParams<T> P)
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     }
+    if (g == 0 && tid == 0) bcd_signal_start(P);   // cluster and cooperative launches are co-scheduled: all CTAs are resident
     unsigned epoch = 0;
     T na_carry = T(0);           // enet_norm partial of the previous atom held by this thread
     T radius_prev = T(0);

@@ -1,6 +1,5 @@
 // bcd_launch.cu -- launch geometry of the dictionary-update kernels (bcd_kernels.cuh, bcd_pilot.cuh).
 #include "bcd_kernels.cuh"
-#include "bcd_block.cuh"
 #include "bcd_pilot.cuh"
 #include "launch.h"
 
@@ -32,7 +31,8 @@ static const void *pilot_kernel_for(int ncl, bool enet)
 
 template <typename T>
 int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *comp_norm,
-                      const int32_t *d_order, int64_t k, int64_t s, T l1_ratio, int positive, cudaStream_t st)
+                      const int32_t *d_order, int64_t k, int64_t s, T l1_ratio, int positive, cudaStream_t st,
+                      unsigned *start_flag, unsigned start_serial)
 {
     if (s <= 0 || k <= 0) return MODL_OK;
     auto kern = bcd_update_kernel<T>;
@@ -44,6 +44,7 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
     BcdParams<T> P;
     P.Dp = Dp; P.Bp = Bp; P.C = C; P.comp_norm = comp_norm; P.order = d_order;
     P.k = (int)k; P.s = (int)s; P.lds = (int)lds; P.l1_ratio = l1_ratio; P.positive = positive;
+    P.start_flag = start_flag; P.start_serial = start_serial;
 
     int nblk = 0, use_cluster = 0, d_in_smem = 0, use_pilot = 0;
     int64_t cols = 0;
@@ -53,16 +54,10 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
         for (int cs = 16; cs >= 2 && !nblk; cs >>= 1) {
             if (cs > ctx->opt_bcd_cluster) continue;
             const int64_t c = round_up(ceil_div(s, cs), 4), ncp = round_up(c, 32);
-            // variant 2 = blocked update with deferred projection scalars (L2 ball, no positivity clamp),
-            // 1 = per-atom look-ahead pilot, 0 = plain per-atom kernel
-            const bool block_ok = ctx->opt_bcd_block && l1_ratio == T(0) && !positive;
-            for (int pilot = block_ok ? 2 : (ctx->opt_bcd_pilot ? 1 : 0); pilot >= 0 && !nblk; --pilot) {
-                if (pilot == 1 && !ctx->opt_bcd_pilot) continue;
+            // variant 1 = per-atom look-ahead pilot, 0 = plain per-atom kernel
+            for (int pilot = ctx->opt_bcd_pilot ? 1 : 0; pilot >= 0 && !nblk; --pilot) {
                 size_t need;
-                if (pilot == 2) {
-                    if (ncp > BB_THREADS) continue;
-                    need = bcd_block_smem_bytes<T>(k, ncp);
-                } else if (pilot) {
+                if (pilot) {
                     if (ncp > 192) continue;
                     need = bcd_pilot_smem_bytes<T>(k, ncp);
                 } else {
@@ -70,8 +65,7 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
                     if (ncp > 2 * BCD_THREADS) continue;
                 }
                 if (need > budget) continue;
-                const void *fn = pilot == 2 ? (const void *)bcd_block_kernel<T>
-                                 : pilot ? pilot_kernel_for<T>((int)(ncp / 32), l1_ratio != T(0)) : (const void *)kern;
+                const void *fn = pilot ? pilot_kernel_for<T>((int)(ncp / 32), l1_ratio != T(0)) : (const void *)kern;
                 // (kernel, cluster size, shared memory) combinations already validated on this device: skip the
                 // attribute and occupancy queries (tens of microseconds of host time per step)
                 struct Seen { const void *fn; int cs; size_t need; int device; };
@@ -95,7 +89,7 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
                     continue;
                 }
                 cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(cs); cfg.blockDim = dim3(pilot == 2 ? BB_THREADS : pilot ? BP_THREADS : BCD_THREADS);
+                cfg.gridDim = dim3(cs); cfg.blockDim = dim3(pilot ? BP_THREADS : BCD_THREADS);
                 cfg.dynamicSmemBytes = need; cfg.stream = st;
                 cudaLaunchAttribute at[1];
                 at[0].id = cudaLaunchAttributeClusterDimension;
@@ -160,7 +154,7 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
     }
 
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(use_pilot == 2 ? BB_THREADS : use_pilot ? BP_THREADS : BCD_THREADS);
+    cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(use_pilot ? BP_THREADS : BCD_THREADS);
     cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     if (use_cluster) {
@@ -171,10 +165,7 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
         at[0].val.cooperative = 1;
     }
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (use_pilot == 2) {
-        void *args[] = {&P};
-        MODL_CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void *)bcd_block_kernel<T>, args));
-    } else if (use_pilot) {
+    if (use_pilot) {
         void *args[] = {&P};
         MODL_CUDA_TRY(cudaLaunchKernelExC(&cfg, pilot_kernel_for<T>((int)(round_up(cols, 32) / 32), l1_ratio != T(0)), args));
     } else {
@@ -186,8 +177,8 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
 
 
 template int bcd_update<float>(modl_ctx *, float *, const float *, int64_t, const float *, float *, const int32_t *, int64_t,
-                               int64_t, float, int, cudaStream_t);
+                               int64_t, float, int, cudaStream_t, unsigned *, unsigned);
 template int bcd_update<double>(modl_ctx *, double *, const double *, int64_t, const double *, double *, const int32_t *,
-                                int64_t, int64_t, double, int, cudaStream_t);
+                                int64_t, int64_t, double, int, cudaStream_t, unsigned *, unsigned);
 
 }  // namespace modl

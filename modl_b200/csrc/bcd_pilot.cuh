@@ -165,6 +165,7 @@ bcd_pilot_kernel(BcdParams<T> P)
     // every peer is resident and its mbarriers initialised before anybody sends
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    if (g == 0 && tid == 0) bcd_signal_start(P);
     if (xstamp) xstamp[1] = clock64();
 
     if (wid >= BP_PW) {

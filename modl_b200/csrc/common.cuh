@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "../../include/modl_b200.h"
@@ -54,7 +55,7 @@ __host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return ceil_
 enum WsSlot {
     WS_SUBSET = 0,   // int64[s]
     WS_ORDER,        // int32[k]
-    WS_PANEL_DX,     // [D_sub ; X_sub]  (k+b) x s_pad
+    WS_PANEL_DX,     // D_sub  k x s_pad
     WS_PANEL_B,      // B_sub / gradient panel  k x s_pad
     WS_XNORM,        // real[b]
     WS_G,            // k x k
@@ -73,6 +74,14 @@ enum WsSlot {
     WS_GEMM_PART2,   // split-K partials of the side-stream statistics product
     WS_MISC,         // small scalars
     WS_INFO,         // int status flags
+    WS_SUBSET2,      // second copies of the per-step inputs: the step in flight keeps its own while the next
+    WS_ORDER2,       //   step's are prefetched on another stream (modl_step_params.slot)
+    WS_PANEL_B2,
+    WS_INDICES,      // int64[b] sample rows of a batch, two slots
+    WS_INDICES2,
+    WS_WSAMPLE,      // real[b] per-sample weights of the 'average' modes, two slots
+    WS_WSAMPLE2,
+    WS_PANEL_X,      // X_sub  b x s_pad
     WS_COUNT
 };
 
@@ -90,13 +99,14 @@ struct modl_ctx {
     int opt_force_global_gram = 0;// debug: never keep the Gram in shared memory
     int opt_bcd_pilot = 1;        // use the warp-specialised look-ahead dictionary kernel when the panel fits a cluster
     int opt_tc_gemm = 1;          // float contractions on the tensor cores (tcgen05 3xTF32); 0 = CUDA-core FFMA GEMM
-    int opt_bcd_block = 0;        // experimental: blocked dictionary update (deferred projection scalars, bcd_block.cuh)
-    int opt_bcd_flag_barrier = 0; // grid-wide dictionary update: per-CTA epoch flags instead of one atomic counter (to be validated)
-    int opt_bcd_coop_min_cols = 32; // grid-wide dictionary update: fewest columns per CTA (more = fewer CTAs at the grid barrier)
+    int opt_bcd_flag_barrier = 0; // grid-wide dictionary update: per-CTA epoch flags instead of one atomic counter (measured r02_a: slower, stays off)
+    int opt_bcd_coop_min_cols = 128; // grid-wide dictionary update: fewest columns per CTA (fewer CTAs at the per-atom grid barrier;
+                                    // measured r02_a: image shape 8.3 -> 5.5 us/atom at 128, worse again at 256)
     int opt_bcd_timing = 0;       // debug: record clock64 stamps inside the dictionary update
     int bcd_timing_k = 0;
-    int code_packed = 0;          // WS_TC_CODE holds the packed code^T of the current step
-    int panel_b_ready = 0;        // MODL_PHASE_APPLY_SUB left (1-w) B_[:, subset] + increments in WS_PANEL_B
+    int opt_bcd_pipeline = 1;     // pilot kernel, L2 ball without positivity: keep two norm exchanges in flight (bcd_pilot.cuh)
+    const float *code_packed = nullptr;   // packed code^T (A operand, 128-row blocks) of the current step, or NULL
+    int panel_b_ready = 0;        // the B_[:, subset] panel of the current step is complete in WS_PANEL_B[slot]
     // optional per-phase device timing of the fused step (modl_ctx_profile)
     int prof_on = 0;
     int prof_n = 0;                       // marks recorded in the current step
@@ -106,12 +116,35 @@ struct modl_ctx {
     int64_t prof_steps = 0;
     void *slot_ptr[modl::WS_COUNT] = {};
     size_t slot_bytes[modl::WS_COUNT] = {};
+    // one call at a time per context: the workspace slots and the per-step flags above are shared state
+    std::recursive_mutex mu;
 
     // returns a device pointer with at least `bytes` capacity (grow-only)
     int reserve(modl::WsSlot slot, size_t bytes, void **out);
 };
 
 namespace modl {
+
+// Every extern "C" entry that takes a context opens with one of these: it serialises the calls on that
+// context (workspace slots are shared state) and makes the context's device current for the duration of
+// the call, restoring the caller's device on exit -- a process may drive several GPUs.
+struct CtxGuard {
+    modl_ctx *c;
+    int prev = -1;
+    explicit CtxGuard(const modl_ctx *ctx) : c(const_cast<modl_ctx *>(ctx)) {
+        if (!c) return;
+        c->mu.lock();
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != c->device && cudaSetDevice(c->device) == cudaSuccess) prev = cur;
+    }
+    ~CtxGuard() {
+        if (!c) return;
+        if (prev >= 0) cudaSetDevice(prev);
+        c->mu.unlock();
+    }
+    CtxGuard(const CtxGuard &) = delete;
+    CtxGuard &operator=(const CtxGuard &) = delete;
+};
 
 // "phase `ph` starts now" (no-op unless profiling is on)
 inline void prof_mark(modl_ctx *ctx, cudaStream_t st, int ph) {

@@ -38,11 +38,16 @@ int ridge_solve(modl_ctx *ctx, const T *G, int64_t g_stride, T *Dx, T *code, con
 // bcd_launch.cu
 template <typename T>
 int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *comp_norm,
-               const int32_t *d_order, int64_t k, int64_t s, T l1_ratio, int positive, cudaStream_t st);
+               const int32_t *d_order, int64_t k, int64_t s, T l1_ratio, int positive, cudaStream_t st,
+               unsigned *start_flag = nullptr, unsigned start_serial = 0);
+
+// api.cu -- the phases of one minibatch step (modl_batch_fit_* without the context guard)
+template <typename T>
+int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream);
 
 // tc_gemm.cu -- tcgen05 3xTF32 GEMM on packed split panels (float only)
 size_t tc_packed_elems(int64_t rows, int64_t kd, int64_t rows_per_block = 128);
-int tc_pick_bn(const modl_ctx *ctx, int64_t N, int64_t mtiles);
+int tc_pick_bn(const modl_ctx *ctx, int64_t N, int64_t mtiles, int sm_avail = 0);
 int64_t tc_rows_padded(int64_t rows);
 int tc_pack_rows(modl_ctx *ctx, const float *src, int64_t ld, int64_t rows, int64_t p, const int64_t *subset,
                  int64_t kd, float *packed, int64_t row0, int64_t rows_pad_end, float *plain, int64_t ldp,

@@ -308,21 +308,21 @@ extern "C" {
     int modl_recsys_gram_dx_##SFX(modl_ctx *c, const T *Dt, int64_t ldt, const int64_t *indptr, const int32_t *indices,      \
                                   const T *data, const int64_t *rows, int64_t row0, int64_t b, int64_t k, int64_t p,        \
                                   double alpha, T *G, T *Dx, void *st)                                                      \
-    { return recsys_gram_dx<T>(c, Dt, ldt, indptr, indices, data, rows, row0, b, k, p, alpha, G, Dx, (cudaStream_t)st); }   \
+    { CtxGuard g_(c); return recsys_gram_dx<T>(c, Dt, ldt, indptr, indices, data, rows, row0, b, k, p, alpha, G, Dx, (cudaStream_t)st); }   \
     int modl_recsys_update_B_##SFX(modl_ctx *c, T *B, int64_t ldb, const T *code, const int64_t *subset,                    \
                                    const int64_t *col_ptr, const int64_t *entry_row, const T *entry_val,                    \
                                    int64_t *feature_n_iter, int64_t s, int64_t k, double w, int64_t n_iter, void *st)       \
-    { return recsys_update_B<T>(c, B, ldb, code, subset, col_ptr, entry_row, entry_val, feature_n_iter, s, k, w, n_iter,    \
+    { CtxGuard g_(c); return recsys_update_B<T>(c, B, ldb, code, subset, col_ptr, entry_row, entry_val, feature_n_iter, s, k, w, n_iter,    \
                                 (cudaStream_t)st); }                                                                        \
     int modl_recsys_update_C_##SFX(modl_ctx *c, T *C, const T *code, const int64_t *rows, int64_t b, int64_t k, double w,   \
                                    void *st)                                                                                \
-    { return recsys_update_C<T>(c, C, code, rows, b, k, w, (cudaStream_t)st); }                                             \
+    { CtxGuard g_(c); return recsys_update_C<T>(c, C, code, rows, b, k, w, (cudaStream_t)st); }                                             \
     int modl_recsys_sync_transposed_##SFX(modl_ctx *c, const T *D, int64_t ldd, T *Dt, int64_t ldt, const int64_t *subset,  \
                                           int64_t s, int64_t k, void *st)                                                   \
-    { return recsys_sync_transposed<T>(c, D, ldd, Dt, ldt, subset, s, k, (cudaStream_t)st); }                               \
+    { CtxGuard g_(c); return recsys_sync_transposed<T>(c, D, ldd, Dt, ldt, subset, s, k, (cudaStream_t)st); }                               \
     int modl_recsys_predict_##SFX(modl_ctx *c, const T *code, const T *Dt, int64_t ldt, const int64_t *indptr,              \
                                   const int32_t *indices, int64_t n_rows, int64_t k, double *out, void *st)                 \
-    { return recsys_predict<T>(c, code, Dt, ldt, indptr, indices, n_rows, k, out, (cudaStream_t)st); }
+    { CtxGuard g_(c); return recsys_predict<T>(c, code, Dt, ldt, indptr, indices, n_rows, k, out, (cudaStream_t)st); }
 
 MODL_DEFINE_RECSYS(f32, float)
 MODL_DEFINE_RECSYS(f64, double)

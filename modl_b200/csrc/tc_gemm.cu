@@ -9,14 +9,16 @@ size_t tc_packed_elems(int64_t rows, int64_t kd, int64_t rpb) { return tc_packed
 
 // Accumulator tile width for an N-column output produced by `mtiles` row tiles: the multiple of 16
 // in [128, 160] whose tile count wastes the least of the last wave over the SMs (one CTA per SM).
-// p = 10000, M = 256: bn = 144 -> 70 x 2 = 140 CTAs in ONE wave instead of 158 in two.
-int tc_pick_bn(const modl_ctx *ctx, int64_t N, int64_t mtiles)
+// p = 10000, M = 256: bn = 144 -> 70 x 2 = 140 CTAs in ONE wave instead of 158 in two; with sm_avail = 132 (the
+// dictionary update's 16-CTA cluster is resident on the others) bn = 160 -> 126 CTAs.
+int tc_pick_bn(const modl_ctx *ctx, int64_t N, int64_t mtiles, int sm_avail)
 {
     int best = TC_ROWS;
     double best_cost = 1e300;
+    const int64_t sms = sm_avail > 0 && sm_avail < ctx->sm_count ? sm_avail : ctx->sm_count;
     for (int bn = 128; bn <= 160; bn += 16) {
         const int64_t ctas = ceil_div(N, bn) * mtiles;
-        const int64_t waves = ceil_div(ctas, ctx->sm_count);
+        const int64_t waves = ceil_div(ctas, sms);
         const double cost = (double)waves * bn;            // time ~ waves x tile width
         if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
     }

@@ -172,7 +172,7 @@ class CodingMixin(TransformerMixin):
     def __getstate__(self):
         state = {}
         for key, val in self.__dict__.items():
-            if key in ("_pipeline", "_time_events", "_keepalive", "_ovl", "_prm", "_step_fn"):
+            if key in ("_pipeline", "_time_events", "_keepalive", "_ovl", "_prm", "_step_fn", "_fit_loop", "_fit_keep"):
                 continue
             if isinstance(val, torch.Tensor):
                 state[key] = ("__tensor__", val.detach().cpu().numpy())
@@ -196,7 +196,9 @@ class DictFact(CodingMixin, BaseEstimator):
 
     Parameters are those of the reference (see its docstring, :154-222).  `n_threads` is
     accepted and ignored.  Two extra keywords: `device` (torch device or index, default: the
-    current CUDA device) and `async_host_copy` (default False).  With `async_host_copy=True`,
+    current CUDA device) and `async_host_copy` (default False).  `partial_fit` takes one optional extra
+    argument, `code_out` (a pinned host tensor / array of n_rows x n_components that receives the codes of the
+    rows just seen, copied out on a stream of its own).  With `async_host_copy=True`,
     `partial_fit` on PINNED host rows returns as soon as the copies and kernels are enqueued --
     the usual contract of an asynchronous pinned-memory copy: the caller must leave those rows
     untouched until `synchronize()` (or any later read of a fitted attribute, which
@@ -292,10 +294,13 @@ class DictFact(CodingMixin, BaseEstimator):
             X = X[torch.as_tensor(permutation, device=X.device)] if tensor_in else X[permutation]
         return self
 
-    def partial_fit(self, X, sample_indices=None):
+    def partial_fit(self, X, sample_indices=None, code_out=None):
         """Update the factorisation with the rows of X, `batch_size` rows per step
         [ref: dict_fact.py:313-337].  X: NumPy array (host; pinned memory is copied without
-        staging), CPU tensor or CUDA tensor."""
+        staging), CPU tensor or CUDA tensor.  The whole call is ONE call into the C ABI
+        (`modl_partial_fit_*`: the loop over the batches, the host bookkeeping of every step and the
+        two-stream schedule); with `verbose` / `callback` set, or in a subclass that overrides
+        `_single_batch_fit`, the batches are walked here instead, one `modl_batch_fit_*` call each."""
         if self.__dict__.get("_d_components_") is None:
             raise AttributeError("call prepare() (or fit()) before partial_fit()")
         dev, dt = self._device, self._d_components_.dtype
@@ -309,17 +314,153 @@ class DictFact(CodingMixin, BaseEstimator):
         stream = torch.cuda.current_stream(dev)
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record(stream)
-        batches = list(gen_batches(n_samples, self.batch_size))
-        if Xt.is_cuda:
-            for batch in batches:
-                self._single_batch_fit(Xt[batch], get_sub_slice(sample_indices, batch))
+        if self._c_loop_ok():
+            self._partial_fit_c(Xt, sample_indices, code_out, stream)
         else:
-            self._partial_fit_host(Xt, batches, sample_indices, stream)
+            if code_out is not None:
+                raise ValueError("code_out needs the C minibatch loop (no verbose / callback / overridden step)")
+            batches = list(gen_batches(n_samples, self.batch_size))
+            if Xt.is_cuda:
+                for batch in batches:
+                    self._single_batch_fit(Xt[batch], get_sub_slice(sample_indices, batch))
+            else:
+                self._partial_fit_host(Xt, batches, sample_indices, stream)
         end.record(stream)
         self.__dict__.setdefault("_time_events", []).append((start, end))
         if len(self._time_events) > 256:
             _ = self.time_
         return self
+
+    # ------------------------------------------------------------------ the C minibatch loop
+    def _c_loop_ok(self):
+        """The C loop runs the step of THIS class; anything that hooks into the Python step (verbose printing, the
+        callback, a subclass with its own `_single_batch_fit`) keeps the per-batch Python walk."""
+        if self.verbose or self.callback is not None or self.__dict__.get("python_loop", False):
+            return False
+        return type(self)._single_batch_fit is DictFact._single_batch_fit
+
+    def _fit_loop_handle(self):
+        loop = self.__dict__.get("_fit_loop")
+        if loop is None or loop.ctx is not self._ctx():
+            loop = self.__dict__["_fit_loop"] = _lib.FitLoop(self._ctx())
+        return loop
+
+    def _fit_params(self, batch_rows):
+        D = self._d_components_
+        k, p = D.shape
+        prm = _lib.FitParams()
+        prm.n_samples, prm.n_features, prm.n_components, prm.batch_size = self._d_code_.shape[0], p, k, int(batch_rows)
+        prm.components, prm.code = D.data_ptr(), self._d_code_.data_ptr()
+        prm.C, prm.B, prm.comp_norm = self._d_C_.data_ptr(), self._d_B_.data_ptr(), self._d_comp_norm_.data_ptr()
+        for name, field in (("_d_G_", "G_full"), ("_d_Dx_average_", "Dx_average"), ("_d_G_average_", "G_average")):
+            t = self.__dict__.get(name)
+            setattr(prm, field, t.data_ptr() if t is not None else None)
+        prm.reduction, prm.learning_rate = float(self.reduction), float(self.learning_rate)
+        prm.code_alpha, prm.code_l1_ratio = float(self.code_alpha), float(self.code_l1_ratio)
+        prm.comp_l1_ratio, prm.tol, prm.step_size = float(self.comp_l1_ratio), float(self.tol), float(self.step_size)
+        prm.max_iter, prm.code_pos, prm.comp_pos = int(self.max_iter), int(bool(self.code_pos)), int(bool(self.comp_pos))
+        prm.Dx_agg, prm.G_agg = _lib.AGG[self.Dx_agg], _lib.AGG[self.G_agg]
+        prm.optimizer_sgd = int(self.optimizer == 'sgd')
+        return prm
+
+    def _partial_fit_c(self, Xt, sample_indices, code_out, stream, world=1):
+        """[ref: dict_fact.py:313-337 + :495-526] -- one `modl_partial_fit_*` call (per batch in the 'average'
+        modes, whose per-sample weights are NumPy expressions of the counters, :513)."""
+        dev = self._device
+        n, p = Xt.shape
+        k = self.n_components
+        bs = int(self.batch_size)
+        if n == 0:
+            return
+        if Xt.stride(1) != 1 or (Xt.is_cuda and Xt.stride(0) < p):
+            Xt = Xt.contiguous()
+        if sample_indices is None:
+            idx = None
+        else:
+            idx = get_sub_slice(sample_indices, slice(0, n))
+            idx = np.ascontiguousarray(idx, dtype=np.int64)
+            if idx.shape[0] != n:
+                raise ValueError("sample_indices and X do not match")
+            if n and (idx.min() < 0 or idx.max() >= self._d_code_.shape[0]):
+                raise IndexError("sample_indices out of range")
+        n_batches = -(-n // bs)
+        # the atom orders of this call, in batch order: the only draws the estimator's NumPy RandomState makes
+        # inside partial_fit [ref: :672]
+        orders = np.empty((n_batches, k), dtype=np.int64)
+        for i in range(n_batches):
+            orders[i] = self.random_state.permutation(k)
+        loop = self._fit_loop_handle()
+        fn = getattr(_lib.lib(), "modl_partial_fit_" + _lib.sfx_of(self._d_components_.dtype))
+        io = _lib.FitBatches()
+        io.ldx = Xt.stride(0)
+        io.x_location = 0 if Xt.is_cuda else (1 if Xt.is_pinned() else 2)
+        io.sampler = self.feature_sampler_._h
+        n_iter = C.c_int64(int(self.n_iter_))
+        io.h_n_iter = C.addressof(n_iter)
+        counters = self.sample_n_iter_
+        if counters.dtype != np.int64 or not counters.flags["C_CONTIGUOUS"]:
+            counters = self.sample_n_iter_ = np.ascontiguousarray(counters, dtype=np.int64)
+        io.h_sample_n_iter = counters.ctypes.data
+        last_subset = np.empty(max(p, 1), dtype=np.int64)
+        last_len = C.c_int64(0)
+        io.h_last_subset, io.h_last_subset_len = last_subset.ctypes.data, C.addressof(last_len)
+        sw = None
+        if self.__dict__.get("record_sweeps", False):
+            sw = self.__dict__.get("_d_sweeps")
+            if sw is None or sw.shape[0] < bs:
+                sw = self.__dict__["_d_sweeps"] = torch.zeros(bs, dtype=torch.int32, device=dev)
+            io.sweeps = sw.data_ptr()
+        keep = [Xt, idx, orders, counters, last_subset, sw]
+        co = None
+        if code_out is not None:
+            co = code_out if isinstance(code_out, torch.Tensor) else torch.from_numpy(code_out)
+            if co.is_cuda or co.dtype != self._d_components_.dtype or tuple(co.shape) != (n, k) or not co.is_contiguous():
+                raise ValueError("code_out must be a contiguous host array of shape (n_rows, n_components) and the estimator dtype")
+            io.h_code_out = co.data_ptr()
+            keep.append(co)
+        wait_host = 0 if getattr(self, "async_host_copy", False) else 1
+        io.wait_host = wait_host
+        itemsize = Xt.element_size()
+        average = self.G_agg == 'average' or self.Dx_agg == 'average'
+        st = C.c_void_p(stream.cuda_stream)
+        handle = loop.handle
+
+        def run(r0, r1, o0, upd, w_sample):
+            prm = self._fit_params(bs)
+            io.X = Xt.data_ptr() + r0 * Xt.stride(0) * itemsize
+            io.n_rows = r1 - r0
+            io.h_sample_indices = idx[r0:].ctypes.data if idx is not None else None
+            if idx is None and r0:
+                # rows r0.. of an un-indexed call are samples r0..: make that explicit for a partial call
+                ids = np.arange(r0, r1, dtype=np.int64)
+                keep.append(ids)
+                io.h_sample_indices = ids.ctypes.data
+            io.h_orders = orders[o0:].ctypes.data
+            io.update_counters = int(upd)
+            io.h_w_sample = w_sample.ctypes.data if w_sample is not None else None
+            if co is not None:
+                io.h_code_out = co.data_ptr() + r0 * k * itemsize
+            _lib.check(fn(handle, C.byref(prm), C.byref(io), st))
+
+        if not average:
+            run(0, n, 0, True, None)
+        else:
+            for i in range(n_batches):
+                r0, r1 = i * bs, min(n, (i + 1) * bs)
+                rows = idx[r0:r1] if idx is not None else np.arange(r0, r1)
+                n_iter.value += (r1 - r0) * world
+                counters[rows] += 1
+                w_sample = np.power(counters[rows], -self.sample_learning_rate).astype(self._np_dtype)   # [ref: :513]
+                keep.append(w_sample)
+                run(r0, r1, i, False, w_sample)
+        self.n_iter_ = int(n_iter.value)
+        self.__dict__["last_subset_"] = last_subset[:int(last_len.value)].copy()
+        self.__dict__["last_order_"] = orders[-1].copy()
+        # host buffers the asynchronous copies still read stay alive until the next synchronisation point
+        if wait_host:
+            keep = [Xt] if Xt.is_cuda else []
+        self.__dict__.setdefault("_fit_keep", []).append(keep)
+        del self._fit_keep[:-4]
 
     def _partial_fit_host(self, Xt, batches, sample_indices, stream):
         """Host rows -> device through two device staging slots on a side stream, so that the copy
@@ -375,7 +516,11 @@ class DictFact(CodingMixin, BaseEstimator):
         pipe = self.__dict__.get("_pipeline")
         if pipe is not None:
             pipe["copy_stream"].synchronize()
+        loop = self.__dict__.get("_fit_loop")
+        if loop is not None:
+            loop.synchronize()
         torch.cuda.current_stream(self._device).synchronize()
+        self.__dict__["_fit_keep"] = []
         return self
 
     def set_params(self, **params):
@@ -493,6 +638,10 @@ class DictFact(CodingMixin, BaseEstimator):
         if self.verbose:
             self.verbose_iter_ = np.linspace(0, n_samples * self.n_epochs, self.verbose).tolist()
         self.time_ = 0
+        # nothing cached for the previous fit (kernel entry points are dtype-specific, streams and scratch tensors
+        # are device-specific) survives a new prepare()
+        for name in ("_d_sweeps", "_pipeline", "_step_fn", "_prm", "_ovl", "_keepalive", "_d_inc_sub", "_d_inc", "_fit_keep"):
+            self.__dict__.pop(name, None)
         self.__dict__["_d_sweeps"] = None
         self.__dict__["_pipeline"] = None
         return self

@@ -49,7 +49,7 @@ class ShardedStepMixin(object):
             self.verbose_iter_ = self.verbose_iter_[1:]
             self._callback()
         b_local = X.shape[0]
-        b_global = b_local * world          # equal shards: every rank passes the same row count
+        b_global = self._global_rows(b_local, world)
         subset, sample_indices, w, order, w_sample = self._host_bookkeeping(b_global, sample_indices)
         if world > 1 and getattr(self, "overlap_exchange", False) and hasattr(self, "_overlapped_step"):
             self._overlapped_step(X, sample_indices, subset, order, w, w_sample, b_global)
@@ -60,6 +60,22 @@ class ShardedStepMixin(object):
             self._phase_apply_and_dict(X, sample_indices, subset, order, w, w_sample, inc, b_global)
         self.__dict__["last_subset_"] = subset
         self.__dict__["last_order_"] = order
+
+    def _global_rows(self, b_local, world):
+        """Rows of the whole minibatch.  Shards must be equal (the weights w and 1/b assume it, and n_iter_ must advance
+        identically on every rank): a full `batch_size` block is equal by construction; any other row count is
+        verified with one small collective, and unequal shards raise instead of silently mis-weighting the step."""
+        if world == 1 or b_local == self.batch_size:
+            return b_local * world
+        dev = getattr(self, "_device", None)
+        on_gpu = dev is not None and dist.get_backend(self.process_group) == "nccl"
+        t = torch.tensor([b_local, -b_local], dtype=torch.int64, device=dev if on_gpu else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.process_group)
+        hi, lo = int(t[0].item()), -int(t[1].item())
+        if hi != lo:
+            raise ValueError("sample-sharded step: ranks hold between %d and %d rows of this minibatch; shards must be "
+                             "equal (run a ragged tail through _replicated_step)" % (lo, hi))
+        return b_local * world
 
     def _replicated_step(self, X, sample_indices):
         """One minibatch processed WHOLE by every rank, without exchange (identical inputs and kernels on every
@@ -89,6 +105,54 @@ class ShardedDictFact(ShardedStepMixin, DictFact):
     @classmethod
     def _get_param_names(cls):
         return sorted(set(DictFact._get_param_names()) | {"process_group", "overlap_exchange"})
+
+    # -- the C minibatch loop with its own NCCL communicators --------------------------------------
+    # Full `batch_size` blocks go through modl_partial_fit_* (one C call per partial_fit: the loop, the host
+    # bookkeeping, both streams and both all-reduces live in the library; include/modl_b200.h,
+    # modl_fit_set_comm); a ragged tail takes the Python walk below, which verifies that the shards are equal.
+    def _c_loop_ok(self):
+        if self.verbose or self.callback is not None or self.__dict__.get("python_loop", False):
+            return False
+        if type(self)._single_batch_fit is not ShardedStepMixin._single_batch_fit:
+            return False
+        world, _ = self._world()
+        if world == 1:
+            return True
+        return (dist.get_backend(self.process_group) == "nccl" and self.G_agg != 'average' and self.Dx_agg != 'average'
+                and self.optimizer != 'sgd')
+
+    def _comm_loop(self):
+        world, rank = self._world()
+        loop = self._fit_loop_handle()
+        if loop.world != world:
+            ids = [_lib.nccl_unique_id(), _lib.nccl_unique_id()] if rank == 0 else [None, None]
+            src = dist.get_global_rank(self.process_group, 0) if self.process_group is not None else 0
+            dist.broadcast_object_list(ids, src=src, group=self.process_group, device=self._device)
+            loop.set_comm(world, rank, ids[0], ids[1])       # collective: every rank reaches it at its first step
+            loop.set_option("overlap", int(bool(self.overlap_exchange)))
+        return loop
+
+    def _partial_fit_c(self, Xt, sample_indices, code_out, stream, world=1):
+        world, _ = self._world()
+        if world == 1:
+            return DictFact._partial_fit_c(self, Xt, sample_indices, code_out, stream)
+        self._comm_loop()
+        n, bs = Xt.shape[0], int(self.batch_size)
+        n_full = (n // bs) * bs
+        idx = None
+        if sample_indices is not None:
+            from .dict_fact import get_sub_slice
+            idx = np.ascontiguousarray(get_sub_slice(sample_indices, slice(0, n)), dtype=np.int64)
+        if n_full:
+            DictFact._partial_fit_c(self, Xt[:n_full], idx[:n_full] if idx is not None else None,
+                                    code_out[:n_full] if code_out is not None else None, stream, world=world)
+        if n_full < n:
+            if code_out is not None:
+                raise ValueError("code_out with a ragged sharded tail is not supported")
+            tail = Xt[n_full:]
+            if not tail.is_cuda:
+                tail = tail.to(self._device, non_blocking=False)
+            self._single_batch_fit(tail, idx[n_full:] if idx is not None else np.arange(n_full, n))
 
     # -- overlapped exchange ---------------------------------------------------------------------
     # The dictionary update needs C_ and only the SUBSET columns of B_ (dict_fact.py:532), so the

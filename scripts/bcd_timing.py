@@ -10,7 +10,6 @@ from modl_b200 import DictFact
 
 X = make_data(4 * B)
 ctx = _lib.get_context(0)
-ctx.set_option("bcd_block", 0)
 for cluster in (16, 8):
     ctx.set_option("bcd_cluster", cluster)
     ctx.set_option("bcd_timing", 1)

@@ -66,7 +66,7 @@ for f in ("bench.json", "bench_ref.json"):
         shutil.copy(os.path.join(src, f), os.path.join(dst, tag + "_" + f))
 # per-phase DRAM traffic of one step (bytes), summed over the captured launches of the phase's kernels
 import json
-PHASE_OF = [("bcd_pilot", "dict_bcd"), ("bcd_block", "dict_bcd"), ("cd_regression", "code"), ("tc_pack_rows", "gather"),
+PHASE_OF = [("bcd_pilot", "dict_bcd"), ("cd_regression", "code"), ("tc_pack_rows", "gather"),
             ("tc_pack_cols", "stats"), ("tc_gemm", None)]
 traffic, gemm_seen = {}, 0
 for f in sorted(os.listdir(src)):

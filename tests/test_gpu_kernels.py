@@ -180,15 +180,20 @@ def test_ridge_reports_non_spd(dev):
                                      np.ones((3, 8), np.float32), np.arange(3), 0., 0.1, False, 1e-2, 10)
 
 
+VARIANTS = {"pipelined": dict(bcd_pilot=1, bcd_pipeline=1), "pilot": dict(bcd_pilot=1, bcd_pipeline=0),
+            "plain": dict(bcd_pilot=0, bcd_pipeline=0)}
+
+
 def _run_update_dict(dev, D0, B, C, norm0, subset, order, l1, pos, G0=None, mode=0, w=0.5, step=1.0, cluster=None,
-                     block=1):
+                     variant="pipelined"):
     from modl_b200 import _lib
     from modl_b200._util import ptr, stream_of
     k, p = D0.shape
     ctx = _lib.get_context(0)
     if cluster is not None:
         ctx.set_option("bcd_cluster", cluster)
-    ctx.set_option("bcd_block", block)
+    for name, val in VARIANTS[variant].items():
+        ctx.set_option(name, val)
     try:
         Dd, Bd, Cd, nd, sd = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (D0, B, C, norm0, subset))
         Gd = torch.from_numpy(G0.copy()).to(dev) if G0 is not None else None
@@ -200,16 +205,17 @@ def _run_update_dict(dev, D0, B, C, norm0, subset, order, l1, pos, G0=None, mode
     finally:
         if cluster is not None:
             ctx.set_option("bcd_cluster", 16)
-        ctx.set_option("bcd_block", 0)
+        for name, val in VARIANTS["pipelined"].items():
+            ctx.set_option(name, val)
     return Dd.cpu().numpy(), nd.cpu().numpy(), (Gd.cpu().numpy() if Gd is not None else None)
 
 
-@pytest.mark.parametrize("block", [1, 0])
+@pytest.mark.parametrize("variant", ["pipelined", "pilot", "plain"])
 @pytest.mark.parametrize("cluster", [16, 8, 2, 0])
-def test_update_dict_golden(dev, golden, cluster, block):
+def test_update_dict_golden(dev, golden, cluster, variant):
     """One BCD dictionary step vs the reference's _update_dict (golden), for every barrier
-    flavour (16/8/2-CTA clusters, cooperative global barrier) and both L2-ball kernels
-    (block=1: blocked update with deferred projection scalars; block=0: per-atom kernels)."""
+    flavour (16/8/2-CTA clusters, cooperative global barrier) and every kernel variant (look-ahead
+    pilot kernel with and without the pipelined norm exchange, plain per-atom kernel)."""
     g = golden("update_dict.npz")
     for dt in (np.float32, np.float64):
         for ci, (l1, pos, full) in enumerate(g["cases"]):
@@ -217,7 +223,7 @@ def test_update_dict_golden(dev, golden, cluster, block):
             G0 = g["G0_" + tag] if full else None
             D1, n1, G1 = _run_update_dict(dev, g["D0_" + tag], g["B_" + tag], g["C_" + tag], g["norm0_" + tag],
                                           g["subset_" + tag], g["order_" + tag], l1, pos, G0, cluster=cluster,
-                                          block=block)
+                                          variant=variant)
             tol = 2e-5 if dt == np.float32 else 1e-11
             assert rel_err(D1, g["D1_" + tag]) < tol, (tag, cluster, rel_err(D1, g["D1_" + tag]))
             assert np.abs(n1 - g["norm1_" + tag]).max() < 10 * tol, (tag, cluster)
@@ -229,17 +235,17 @@ def test_update_dict_golden(dev, golden, cluster, block):
             np.testing.assert_array_equal(D1[:, mask], g["D0_" + tag][:, mask])
 
 
-@pytest.mark.parametrize("block", [1, 0])
+@pytest.mark.parametrize("variant", ["pipelined", "pilot"])
 @pytest.mark.parametrize("shape", [(256, 10000, 1250), (70, 30000, 2500), (64, 4000, 4000), (256, 6000, 300), (37, 900, 333),
                                    (70, 40000, 17000), (24, 9000, 9000, "f64")])
-def test_update_dict_bench_shapes(dev, oracle, shape, block):
+def test_update_dict_bench_shapes(dev, oracle, shape, variant):
     """Config-2 / config-4-like panels against the oracle's BCD, L2 and L1 balls.  The last two shapes are the
     grid-wide (cooperative) kernel with the candidate row of the L1 projection held in registers: s = 17 000 is
     the subset of BASELINE configs[3] (p = 2e5, reduction 12); the float64 one takes the 48-per-thread variant."""
     k, p, s = shape[:3]
     dt = np.float64 if len(shape) > 3 else np.float32
-    if block and len(shape) > 3:
-        pytest.skip("one pass is enough for the float64 shape")
+    if variant != "pipelined" and (len(shape) > 3 or shape[2] >= 4000):
+        pytest.skip("panels beyond one cluster take the grid-wide kernel whatever the variant: one pass is enough")
     rng = np.random.RandomState(5)
     for l1, pos in ((0., False), (1., False), (0.3, True)):
         D0 = rng.randn(k, p).astype(dt)
@@ -259,7 +265,7 @@ def test_update_dict_bench_shapes(dev, oracle, shape, block):
         oracle.update_dict_panel(Dw, gw, C, nw, order, l1, pos)
         want = D0.copy()
         want[:, subset] = Dw
-        D1, n1, _ = _run_update_dict(dev, D0, B, C, norm0, subset, order, l1, pos, block=block)
+        D1, n1, _ = _run_update_dict(dev, D0, B, C, norm0, subset, order, l1, pos, variant=variant)
         tol = 5e-5 if dt == np.float32 else 1e-11
         assert rel_err(D1, want) < tol, (shape, l1, pos, rel_err(D1, want))
         assert np.abs(n1 - nw).max() < 10 * tol, (shape, l1, np.abs(n1 - nw).max())

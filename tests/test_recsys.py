@@ -328,8 +328,6 @@ def test_recsys_fits_match_the_reference(gold):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="bookkeeping='epoch' was added after the round-1 GPU budget was spent: its host "
-                                        "logic is pinned on CPU, the device run is to be confirmed in round 2")
 def test_recsys_fits_epoch_bookkeeping(gold):
     _gpu()
     from modl_b200 import recsys
