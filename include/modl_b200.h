@@ -382,6 +382,13 @@ void modl_fit_destroy(modl_fit *fit);
 int modl_fit_set_option(modl_fit *fit, const char *name, int value);
 /* Blocks until the loop's own streams (copies, second stream, code read-back) are idle. */
 int modl_fit_synchronize(modl_fit *fit);
+/* Debug: timeline of the next `steps` steps of the two-stream schedule (0 = off), then
+ * modl_fit_trace_read: h_ms[step][10] = milliseconds since arming at which each point was reached on its stream
+ * (NaN = not recorded): 0 H2D start, 1 H2D end (copy stream); 2 PREFETCH start, 3 PREFETCH end (second stream);
+ * 4 critical path start, 5 codes + subset statistics done, 6 dictionary update done (caller's stream); 7 full-width
+ * product start, 8 full-width product end (second stream); 9 code read-back done. */
+int modl_fit_trace(modl_fit *fit, int steps);
+int modl_fit_trace_read(modl_fit *fit, double *h_ms, int capacity_steps, int *h_steps);
 int modl_partial_fit_f32(modl_fit *fit, const modl_fit_params *est, const modl_fit_batches *io, void *stream);
 int modl_partial_fit_f64(modl_fit *fit, const modl_fit_params *est, const modl_fit_batches *io, void *stream);
 

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmodl_b200.so")
+LIB_PATH = os.environ.get("MODL_B200_LIB") or os.path.join(_HERE, "libmodl_b200.so")     # the override is for A/B builds
 
 MODL_OK, MODL_EINVAL, MODL_ECUDA, MODL_ENOTSPD, MODL_ENOMEM = 0, 1, 2, 3, 4
 AGG = {"masked": 0, "full": 1, "average": 2}
@@ -99,6 +99,8 @@ def _declare(L):
     fn("modl_fit_destroy", None, [vp])
     fn("modl_fit_set_option", ci, [vp, C.c_char_p, ci])
     fn("modl_fit_synchronize", ci, [vp])
+    fn("modl_fit_trace", ci, [vp, ci])
+    fn("modl_fit_trace_read", ci, [vp, vp, ci, vp])
     fn("modl_nccl_unique_id", ci, [vp, i64])
     fn("modl_fit_set_comm", ci, [vp, ci, ci, vp, vp])
     for sfx, real in (("f32", f32), ("f64", f64)):
@@ -130,7 +132,7 @@ EXPORTED = (
      "modl_sampler_yield_subset", "modl_batch_weight", "modl_ctx_create", "modl_ctx_destroy",
      "modl_ctx_sm_count", "modl_ctx_launch_count", "modl_ctx_set_option", "modl_ctx_check_info",
      "modl_ctx_profile", "modl_ctx_profile_read", "modl_fit_create", "modl_fit_destroy", "modl_fit_set_option",
-     "modl_fit_synchronize", "modl_nccl_unique_id", "modl_fit_set_comm"]
+     "modl_fit_synchronize", "modl_fit_trace", "modl_fit_trace_read", "modl_nccl_unique_id", "modl_fit_set_comm"]
     + [n + s for s in ("f32", "f64") for n in (
         "modl_enet_norm_", "modl_enet_projection_", "modl_enet_scale_", "modl_gram_dx_",
         "modl_enet_regression_single_gram_", "modl_enet_regression_multi_gram_",
@@ -223,6 +225,26 @@ class FitLoop(object):
 
     def synchronize(self):
         check(lib().modl_fit_synchronize(self.handle))
+
+    TRACE_POINTS = ("h2d_start", "h2d_end", "prefetch_start", "prefetch_end", "main_start", "codes_done", "dict_done",
+                    "stats_b_start", "stats_b_end", "d2h_done")
+
+    def trace(self, steps):
+        """Arm a timeline of the next `steps` steps (0 = off); read it back with trace_read()."""
+        check(lib().modl_fit_trace(self.handle, int(steps)))
+        self._trace_cap = int(steps)
+
+    def trace_read(self):
+        """-> list of {point: ms since arming} for the traced steps."""
+        cap = getattr(self, "_trace_cap", 0)
+        buf = (C.c_double * (cap * len(self.TRACE_POINTS)))()
+        n = C.c_int(0)
+        check(lib().modl_fit_trace_read(self.handle, buf, cap, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            row = buf[i * len(self.TRACE_POINTS):(i + 1) * len(self.TRACE_POINTS)]
+            out.append({name: v for name, v in zip(self.TRACE_POINTS, row) if v == v})
+        return out
 
     def set_comm(self, world, rank, id_main, id_side):
         check(lib().modl_fit_set_comm(self.handle, int(world), int(rank), id_main, id_side))

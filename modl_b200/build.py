@@ -28,8 +28,12 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant / defines: an A/B build (`libmodl_b200_<variant>.so`, objects in `_obj_<variant>`) compiled with extra -D
+    flags; modl_b200._lib loads it when MODL_B200_LIB points at it."""
     nvcc = os.environ.get("NVCC", "nvcc")
+    OBJ = os.path.join(HERE, "csrc", "_obj" + ("_" + variant if variant else ""))
+    OUT = os.path.join(HERE, "libmodl_b200" + ("_" + variant if variant else "") + ".so")
     os.makedirs(OBJ, exist_ok=True)
     objs, procs = [], []
     hdr = headers()
@@ -38,7 +42,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + hdr):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
@@ -57,4 +61,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    kw = {}
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        kw = dict(variant=sys.argv[i + 1], defines=sys.argv[i + 2].split(","))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, **kw))

@@ -138,6 +138,13 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
     unsigned done = 0;
+#ifdef MODL_UNBOUNDED_WAIT
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+    return;
+#endif
     for (unsigned spin = 0; !done; ++spin) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");

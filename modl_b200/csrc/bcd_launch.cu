@@ -11,22 +11,24 @@ namespace modl {
 // ---------------------------------------------------------------------------------------
 // dictionary update
 // ---------------------------------------------------------------------------------------
-template <typename T, bool ENET>
+template <typename T, bool ENET, bool PIPE>
 static const void *pilot_kernel_for_e(int ncl)
 {
     switch (ncl) {
-        case 1: return (const void *)bcd_pilot_kernel<T, 1, ENET>;
-        case 2: return (const void *)bcd_pilot_kernel<T, 2, ENET>;
-        case 3: return (const void *)bcd_pilot_kernel<T, 3, ENET>;
-        case 4: return (const void *)bcd_pilot_kernel<T, 4, ENET>;
-        case 5: return (const void *)bcd_pilot_kernel<T, 5, ENET>;
-        default: return (const void *)bcd_pilot_kernel<T, 6, ENET>;
+        case 1: return (const void *)bcd_pilot_kernel<T, 1, ENET, PIPE>;
+        case 2: return (const void *)bcd_pilot_kernel<T, 2, ENET, PIPE>;
+        case 3: return (const void *)bcd_pilot_kernel<T, 3, ENET, PIPE>;
+        case 4: return (const void *)bcd_pilot_kernel<T, 4, ENET, PIPE>;
+        case 5: return (const void *)bcd_pilot_kernel<T, 5, ENET, PIPE>;
+        default: return (const void *)bcd_pilot_kernel<T, 6, ENET, PIPE>;
     }
 }
+// pipe: two norm exchanges in flight (L2 ball, no positivity clamp: the candidate row is linear in the previous scale)
 template <typename T>
-static const void *pilot_kernel_for(int ncl, bool enet)
+static const void *pilot_kernel_for(int ncl, bool enet, bool pipe)
 {
-    return enet ? pilot_kernel_for_e<T, true>(ncl) : pilot_kernel_for_e<T, false>(ncl);
+    if (enet) return pilot_kernel_for_e<T, true, false>(ncl);
+    return pipe ? pilot_kernel_for_e<T, false, true>(ncl) : pilot_kernel_for_e<T, false, false>(ncl);
 }
 
 template <typename T>
@@ -46,6 +48,7 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
     P.k = (int)k; P.s = (int)s; P.lds = (int)lds; P.l1_ratio = l1_ratio; P.positive = positive;
     P.start_flag = start_flag; P.start_serial = start_serial;
 
+    const bool pipe = ctx->opt_bcd_pipeline != 0 && l1_ratio == T(0) && !positive;
     int nblk = 0, use_cluster = 0, d_in_smem = 0, use_pilot = 0;
     int64_t cols = 0;
     size_t smem = 0;
@@ -65,7 +68,7 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
                     if (ncp > 2 * BCD_THREADS) continue;
                 }
                 if (need > budget) continue;
-                const void *fn = pilot ? pilot_kernel_for<T>((int)(ncp / 32), l1_ratio != T(0)) : (const void *)kern;
+                const void *fn = pilot ? pilot_kernel_for<T>((int)(ncp / 32), l1_ratio != T(0), pipe) : (const void *)kern;
                 // (kernel, cluster size, shared memory) combinations already validated on this device: skip the
                 // attribute and occupancy queries (tens of microseconds of host time per step)
                 struct Seen { const void *fn; int cs; size_t need; int device; };
@@ -167,7 +170,7 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
     cfg.attrs = at; cfg.numAttrs = 1;
     if (use_pilot) {
         void *args[] = {&P};
-        MODL_CUDA_TRY(cudaLaunchKernelExC(&cfg, pilot_kernel_for<T>((int)(round_up(cols, 32) / 32), l1_ratio != T(0)), args));
+        MODL_CUDA_TRY(cudaLaunchKernelExC(&cfg, pilot_kernel_for<T>((int)(round_up(cols, 32) / 32), l1_ratio != T(0), pipe), args));
     } else {
         MODL_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P));
     }

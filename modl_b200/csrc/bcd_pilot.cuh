@@ -18,6 +18,17 @@
 // Roles synchronise once per block of 8 atoms with named barriers; new atom rows are staged and
 // committed to the shared D slice at block boundaries so the workers always read a consistent
 // snapshot.
+//
+//   * pipelined norm exchange (PIPE, L2 ball without positivity -- the benchmark configuration).  The only
+//     thing atom t needs from the rest of the cluster is a scalar: |v_t|^2, the squared norm of its candidate
+//     row, which fixes the projection scale alpha_t.  The candidate is LINEAR in the previous atom's scale,
+//         v_t = u_t - g_t alpha_{t-1} v_{t-1},     g_t = C[a_t, a_{t-1}] / C[a_t, a_t],
+//     with u_t free of alpha_{t-1} (it needs alpha_{t-2} and older only), so
+//         |v_t|^2 = |u_t|^2 - 2 g_t alpha_{t-1} <u_t, v_{t-1}> + (g_t alpha_{t-1})^2 |v_{t-1}|^2 .
+//     The cluster therefore exchanges the partial sums of (|u_t|^2, <u_t, v_{t-1}>) one atom EARLY: the all-to-all
+//     of atom t+1 is sent before the one of atom t is waited for, two exchanges are in flight, and the per-atom
+//     period drops from (local work + exchange latency) to max(local work, exchange latency).  Exact algebra; the
+//     squared norm is assembled from three terms instead of summed directly (relative difference ~1e-7 in float).
 #pragma once
 #include "bcd_kernels.cuh"
 
@@ -49,7 +60,7 @@ __host__ __device__ inline size_t bcd_pilot_smem_bytes(int64_t k, int64_t ncp)
                           + 2 * BP_M * ncp       // brows
                           + 4 * BP_M * ncp       // vnew, delta (two blocks each)
                           + 2 * kp               // cnorm, rad
-                          + 2 * BCD_MAX_CLUSTER * BCD_NPART   // xch
+                          + 4 * BCD_MAX_CLUSTER * BCD_NPART   // xch (BP_XRING)
                           + igw * BP_M * ncp     // red
                           + 2 * 224;             // per-block tables (two coefficient tables, diagonals, atom ids), x2
     return (size_t)elems * sizeof(T) + 40 * sizeof(double) + (size_t)k * ncp * sizeof(T);
@@ -93,10 +104,13 @@ __device__ T enet_threshold_warp(Load load, int n, T radius_over_l1, T gamma, bo
     return (T)l;
 }
 
-template <typename T, int NCL, bool ENET>
+constexpr int BP_XRING = 4;                   // exchange slots / mbarriers in rotation (two exchanges in flight need four)
+
+template <typename T, int NCL, bool ENET, bool PIPE = false>
 __global__ void __launch_bounds__(BP_THREADS, 1)
 bcd_pilot_kernel(BcdParams<T> P)
 {
+    static_assert(!(ENET && PIPE), "the pipelined exchange is for the L2 ball");
     extern __shared__ __align__(16) unsigned char bp_smem_raw[];
     const int k = P.k, s = P.s, lds = P.lds;
     const int nblk = gridDim.x, g = blockIdx.x;
@@ -120,12 +134,12 @@ bcd_pilot_kernel(BcdParams<T> P)
     T *delta = vnew + 2 * BP_M * ncp;                         // [2][M][ncp] new - old, by block parity
     T *cnorm = delta + 2 * BP_M * ncp;                        // [kp] comp_norm_ on entry
     T *rad = cnorm + kp;                                      // [kp] radius used for every atom
-    T *xch = rad + kp;                                        // [2][16][4] exchange slots
-    T *red = xch + 2 * BCD_MAX_CLUSTER * BCD_NPART;           // [IGW][M][ncp]
+    T *xch = rad + kp;                                        // [BP_XRING][16][4] exchange slots
+    T *red = xch + BP_XRING * BCD_MAX_CLUSTER * BCD_NPART;    // [IGW][M][ncp]
     T *tabs = red + (size_t)IGW * BP_M * ncp;                 // [2][TAB]
     double *dscratch = reinterpret_cast<double *>(tabs + 2 * TAB);
     T *Ds = reinterpret_cast<T *>(dscratch + 40);             // [k][ncp]
-    __shared__ __align__(8) unsigned long long xbar[2];
+    __shared__ __align__(8) unsigned long long xbar[BP_XRING];
     const unsigned xbar_addr = (unsigned)__cvta_generic_to_shared(xbar);
     const unsigned xch_addr = (unsigned)__cvta_generic_to_shared(xch);
     constexpr unsigned kSlotBytes = BCD_NPART * sizeof(T);
@@ -155,10 +169,9 @@ bcd_pilot_kernel(BcdParams<T> P)
     }
     for (int i = tid; i < k; i += BP_THREADS) cnorm[i] = P.comp_norm[i];
     for (int e = tid; e < 4 * BP_M * ncp; e += BP_THREADS) vnew[e] = T(0);       // vnew and delta (contiguous)
-    for (int e = tid; e < 2 * BCD_MAX_CLUSTER * BCD_NPART; e += BP_THREADS) xch[e] = T(0);
+    for (int e = tid; e < BP_XRING * BCD_MAX_CLUSTER * BCD_NPART; e += BP_THREADS) xch[e] = T(0);
     if (tid == 0) {
-        mbar_init(xbar_addr, 1);
-        mbar_init(xbar_addr + 8, 1);
+        for (int r = 0; r < BP_XRING; ++r) mbar_init(xbar_addr + 8 * r, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -248,6 +261,229 @@ bcd_pilot_kernel(BcdParams<T> P)
             named_arrive(BP_BAR_PRODUCT, BP_SYNCED);
         }
     } else {
+        if constexpr (PIPE) {
+        // =========================== pilots, pipelined norm exchange ===========================
+        constexpr int NCLW = (NCL + BP_PW - 1) / BP_PW;    // column groups per pilot warp
+        __shared__ double ppsum_raw[BP_XRING * BP_PW * 3];
+        T *ppsum = reinterpret_cast<T *>(ppsum_raw);       // [ring][BP_PW][3] per-warp partial sums
+        unsigned rslot[BP_XRING], rbar[BP_XRING];
+#pragma unroll
+        for (unsigned r = 0; r < BP_XRING; ++r) {
+            const unsigned peer = (unsigned)(lane < nblk ? lane : 0);
+            rslot[r] = mapa_u32(xch_addr + (r * BCD_MAX_CLUSTER + (unsigned)g) * kSlotBytes, peer);
+            rbar[r] = mapa_u32(xbar_addr + 8 * r, peer);
+        }
+        // exchange number t uses ring entry t & 3, phase (t >> 2) & 1 of its mbarrier.  Entry t+1 may be written into a
+        // peer while that peer has not consumed entry t yet; entry t+1 replaces entry t-3, which the peer read before it
+        // sent its entry t-1 -- and that one has been received here.
+        auto xsend = [&](int t, T p0, T p1, T p2) {
+            const unsigned r = (unsigned)t & (BP_XRING - 1);
+            if (tid == 0) mbar_expect_tx(xbar_addr + 8 * r, (unsigned)nblk * kSlotBytes);
+            p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2);
+            T *ps = ppsum + r * (3 * BP_PW);
+            if (lane == 0) { ps[3 * wid] = p0; ps[3 * wid + 1] = p1; ps[3 * wid + 2] = p2; }
+            named_sync(BP_BAR_PILOTS, 32 * BP_PW);
+            if (wid == 0) {
+                T t0 = ps[0], t1 = ps[1], t2 = ps[2];
+#pragma unroll
+                for (int w = 1; w < BP_PW; ++w) { t0 += ps[3 * w]; t1 += ps[3 * w + 1]; t2 += ps[3 * w + 2]; }   // fixed order
+                if (lane < nblk) st_async_triplet(rslot[r], rbar[r], t0, t1, t2);
+            }
+        };
+        auto xwait = [&](int t, T &o0, T &o1, T &o2) {
+            const unsigned r = (unsigned)t & (BP_XRING - 1);
+            mbar_wait(xbar_addr + 8 * r, ((unsigned)t >> 2) & 1u);
+            const T *src = xch + (size_t)r * BCD_MAX_CLUSTER * BCD_NPART;
+            T a0[4], a1[4], a2[4];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                a0[c4] = src[(4 * c4) * BCD_NPART];
+                a1[c4] = src[(4 * c4) * BCD_NPART + 1];
+                a2[c4] = src[(4 * c4) * BCD_NPART + 2];
+#pragma unroll
+                for (int u = 1; u < 4; ++u) {
+                    a0[c4] += src[(4 * c4 + u) * BCD_NPART];
+                    a1[c4] += src[(4 * c4 + u) * BCD_NPART + 1];
+                    a2[c4] += src[(4 * c4 + u) * BCD_NPART + 2];
+                }
+            }
+            o0 = (a0[0] + a0[1]) + (a0[2] + a0[3]);
+            o1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+            o2 = (a2[0] + a2[1]) + (a2[2] + a2[3]);
+        };
+        // per-block tables of atom t
+        auto tab_of = [&](int t) { return tabs + ((t / BP_M) & 1) * TAB; };
+        // coupling of atom t with the atom updated just before it (c1) and two before it (c2): C[a_t, a_{t-1}], C[a_t, a_{t-2}]
+        auto coef1 = [&](int t) -> T {
+            const int j = t % BP_M;
+            const T *tb = tab_of(t);
+            return j >= 1 ? tb[j * BP_M + j - 1] : (t >= BP_M ? tb[64 + BP_M - 1] : T(0));
+        };
+        auto coef2 = [&](int t) -> T {
+            const int j = t % BP_M;
+            const T *tb = tab_of(t);
+            return j >= 2 ? tb[j * BP_M + j - 2] : (t >= BP_M ? tb[64 + j * BP_M + BP_M - 2 + j] : T(0));
+        };
+        // pre_t = B_sub[a_t] - (look-ahead product + repairs for every atom up to t-3), the old row of atom t and its
+        // enet_norm partial: everything of atom t that is known once atom t-3 is final.
+        auto precompute = [&](int t, T (&pre)[NCLW], T (&dold)[NCLW], T &nb_l) {
+            const int b = t / BP_M, jn = t % BP_M, cur = b & 1;
+            if (jn == 0) named_sync(BP_BAR_PRODUCT, BP_SYNCED);      // look-ahead product, B rows and tables of block b are ready
+            const T *Rb = Rbuf + cur * BP_M * ncp;
+            const T *Bb = brows + cur * BP_M * ncp;
+            const T *tb = tabs + cur * TAB;
+            const T *cfm = tb, *cfp = tb + 64;
+            const int a = reinterpret_cast<const int *>(tb + 144)[jn];
+            const T *dcur = delta + cur * BP_M * ncp;
+            const T *dprev = delta + (cur ^ 1) * BP_M * ncp;
+            const int nprev = BP_M - (jn < 2 ? 2 - jn : 0);          // atoms of the previous block that are final (t-3 and older)
+            nb_l = T(0);
+#pragma unroll
+            for (int mm = 0; mm < NCLW; ++mm) {
+                const int m = wid + mm * BP_PW;
+                pre[mm] = dold[mm] = T(0);
+                if (m >= NCL) continue;
+                const int c = lane + 32 * m;
+                T dot = Rb[jn * ncp + c], dot2 = T(0);
+#pragma unroll
+                for (int jp = 0; jp < BP_M; ++jp)
+                    if (jp < nprev) dot = fma(cfp[jn * BP_M + jp], dprev[jp * ncp + c], dot);
+#pragma unroll
+                for (int jp = 0; jp < BP_M - 3; ++jp)
+                    if (jp < jn - 2) dot2 = fma(cfm[jn * BP_M + jp], dcur[jp * ncp + c], dot2);
+                dold[mm] = Ds[a * ncp + c];
+                pre[mm] = Bb[jn * ncp + c] - (dot + dot2);
+                nb_l += enet_term(dold[mm], P.l1_ratio);
+            }
+        };
+        // u_t from its base row:  u = (base + C[a_t, a_{t-1}] d_old[t-1] + C[a_t, a_t] d_old[t]) / C[a_t, a_t]   [ref: :676-685]
+        auto make_u = [&](int t, const T (&base)[NCLW], const T (&dold_prev)[NCLW], const T (&dold)[NCLW], T (&u)[NCLW], T &g_out) {
+            const T *tb = tab_of(t);
+            const int j = t % BP_M;
+            const T caa = tb[136 + j], rcaa = tb[128 + j];
+            const bool upd = caa > T(1e-20);                         // [ref: :681-683]
+            const T c1 = coef1(t);
+            T gq = c1 * rcaa;
+            gq = fma(fma(-gq, caa, c1), rcaa, gq);                   // c1 / caa, Newton-corrected
+            g_out = upd ? gq : T(0);
+#pragma unroll
+            for (int mm = 0; mm < NCLW; ++mm) {
+                const T grad = fma(c1, dold_prev[mm], base[mm]) + caa * dold[mm];
+                T q = grad * rcaa;
+                q = fma(fma(-q, caa, grad), rcaa, q);
+                u[mm] = upd ? q : dold[mm];
+            }
+        };
+        // projection scale of atom t from the exchanged sums  [ref: enet.pyx:62-70]
+        auto scale_of = [&](int t, T nb, T sv2, T &rnrm, T &nrm) {
+            const int a = reinterpret_cast<const int *>(tab_of(t) + 144)[t % BP_M];
+            const T radius = cnorm[a] + nb;                          // comp_norm_[k] += subset_norm  [ref: :676-678]
+            if (tid == 0) rad[a] = radius;
+            rnrm = T(1); nrm = T(1);
+            if (radius == T(0)) {
+                rnrm = T(0);
+            } else {
+                const T x = sv2 / radius;
+                if (x > T(1)) { rnrm = bcd_rsqrt(x); nrm = x * rnrm; }
+            }
+        };
+        // final row of atom t: v / nrm, staged for the workers, and its change
+        auto finalize = [&](int t, const T (&v)[NCLW], const T (&dold)[NCLW], T rnrm, T nrm, T (&dnew)[NCLW], T (&dlt)[NCLW]) {
+            const int cur = (t / BP_M) & 1, j = t % BP_M;
+            T *vcur = vnew + cur * BP_M * ncp;
+            T *dcur = delta + cur * BP_M * ncp;
+#pragma unroll
+            for (int mm = 0; mm < NCLW; ++mm) {
+                const int m = wid + mm * BP_PW;
+                dnew[mm] = dlt[mm] = T(0);
+                if (m >= NCL) continue;
+                const int c = lane + 32 * m;
+                const T tt = v[mm] * rnrm;
+                const T q = fma(fma(-tt, nrm, v[mm]), rnrm, tt);     // v / nrm [ref: enet.pyx:69-70]; 0 when radius == 0
+                dnew[mm] = q;
+                dlt[mm] = q - dold[mm];
+                vcur[j * ncp + c] = q;
+                dcur[j * ncp + c] = dlt[mm];
+            }
+        };
+
+        T vp[NCLW], dop[NCLW], uc[NCLW], doc[NCLW], pn[NCLW], don[NCLW], nbn = T(0);
+        T gc = T(0), sv2p = T(0), rnrm = T(1), nrm = T(1);
+        {   // ---- prologue: atoms 0 and 1 enter the pipeline ----
+            T pre0[NCLW], nb0, g0;
+            T zero[NCLW];
+#pragma unroll
+            for (int mm = 0; mm < NCLW; ++mm) zero[mm] = T(0);
+            precompute(0, pre0, dop, nb0);
+            if (nbk > 1) named_arrive(BP_BAR_SNAPSHOT, BP_SYNCED);   // workers may start on block 1
+            make_u(0, pre0, zero, dop, vp, g0);                      // no predecessor: v_0 = u_0
+            T s11 = T(0);
+#pragma unroll
+            for (int mm = 0; mm < NCLW; ++mm) s11 = fma(vp[mm], vp[mm], s11);
+            xsend(0, nb0, s11, T(0));
+            if (k > 1) {
+                T pre1[NCLW], nb1;
+                precompute(1, pre1, doc, nb1);                       // nothing final yet: the bare product
+                make_u(1, pre1, dop, doc, uc, gc);
+                T s1 = T(0), s2 = T(0);
+#pragma unroll
+                for (int mm = 0; mm < NCLW; ++mm) { s1 = fma(uc[mm], uc[mm], s1); s2 = fma(uc[mm], vp[mm], s2); }
+                xsend(1, nb1, s1, s2);
+            }
+            if (k > 2) precompute(2, pn, don, nbn);
+            T nb, u2, uv;
+            xwait(0, nb, u2, uv);
+            sv2p = u2;
+            scale_of(0, nb, sv2p, rnrm, nrm);
+        }
+        for (int t = 1; t < k; ++t) {
+            if (P.timing && g == 0 && tid == 0) P.timing[(int64_t)t * 8] = clock64();
+            // A: atom t-1 is final
+            T dnew[NCLW], dlt[NCLW];
+            finalize(t - 1, vp, dop, rnrm, nrm, dnew, dlt);
+            if (t % BP_M == 0 && t / BP_M + 1 < nbk) named_arrive(BP_BAR_SNAPSHOT, BP_SYNCED);   // block t/8 - 1 is complete: its buffers may be recycled
+            // B: candidate row of atom t
+            T vc[NCLW];
+#pragma unroll
+            for (int mm = 0; mm < NCLW; ++mm) vc[mm] = fma(-gc, dnew[mm], uc[mm]);
+            // C, D: u of atom t+1 and its sums leave one exchange early
+            T un[NCLW], gn = T(0);
+            if (t + 1 < k) {
+                const T c2 = coef2(t + 1);
+                T base[NCLW];
+#pragma unroll
+                for (int mm = 0; mm < NCLW; ++mm) base[mm] = fma(-c2, dlt[mm], pn[mm]);
+                make_u(t + 1, base, doc, don, un, gn);
+                T s1 = T(0), s2 = T(0);
+#pragma unroll
+                for (int mm = 0; mm < NCLW; ++mm) { s1 = fma(un[mm], un[mm], s1); s2 = fma(un[mm], vc[mm], s2); }
+                xsend(t + 1, nbn, s1, s2);
+            }
+            // between the send and the wait: everything of atom t+2 that is already determined
+            T pn2[NCLW], don2[NCLW], nbn2 = T(0);
+#pragma unroll
+            for (int mm = 0; mm < NCLW; ++mm) pn2[mm] = don2[mm] = T(0);
+            if (t + 2 < k) precompute(t + 2, pn2, don2, nbn2);
+            // E, F: |v_t|^2 from the sums sent one atom ago, then the projection scale of atom t
+            T nb, u2, uv;
+            xwait(t, nb, u2, uv);
+            const T h = gc * rnrm;                                   // g_t alpha_{t-1}
+            T sv2 = fma(h, fma(h, sv2p, T(-2) * uv), u2);
+            sv2 = sv2 > T(0) ? sv2 : T(0);
+            scale_of(t, nb, sv2, rnrm, nrm);
+            sv2p = sv2;
+#pragma unroll
+            for (int mm = 0; mm < NCLW; ++mm) {
+                vp[mm] = vc[mm]; dop[mm] = doc[mm]; uc[mm] = un[mm]; doc[mm] = don[mm]; pn[mm] = pn2[mm]; don[mm] = don2[mm];
+            }
+            gc = gn;
+            nbn = nbn2;
+        }
+        {   // the last atom
+            T dnew[NCLW], dlt[NCLW];
+            finalize(k - 1, vp, dop, rnrm, nrm, dnew, dlt);
+        }
+        } else {
         // =========================== pilots: the dependent chain ===========================
         // Pilot warp w owns the 32-column groups m = w, w + BP_PW, ... (< NCL) of the CTA's slice, lane l
         // the column l + 32 m; padded columns carry zeros through every formula.
@@ -443,6 +679,7 @@ bcd_pilot_kernel(BcdParams<T> P)
             tstamp = nullptr;
         }
 #undef BP_STAMP
+            }   // !PIPE
     }
     // ---- epilogue: commit the last two staged blocks, norms of the new atoms, write-back ----
     if (xstamp) xstamp[2] = clock64();

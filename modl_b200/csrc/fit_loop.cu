@@ -28,6 +28,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cmath>
 #include <new>
 #include <vector>
 
@@ -111,7 +112,7 @@ using namespace modl;
 // ---------------------------------------------------------------------------------------
 struct modl_fit {
     static constexpr int NSTAGE = 3;     // device slots of host batches in flight
-    static constexpr int NRING = 4;      // pinned copies of the small per-step inputs in flight
+    static constexpr int NRING = 8;      // pinned copies of the small per-step inputs in flight
 
     modl_ctx *ctx = nullptr;
     cudaStream_t side = nullptr, copy = nullptr, d2h = nullptr;
@@ -143,6 +144,15 @@ struct modl_fit {
 
     int overlap = 1;                     // 0: one stream, one fused call per step (the round-1 schedule)
     int gate = 1;                        // side stream waits for the dictionary kernel to be resident
+    cudaEvent_t ev_call = nullptr;       // "the caller's stream has reached this partial_fit call"
+    cudaEvent_t code_ev[2] = {};         // the event that marked ev_code of the last step on each slot (a trace event when tracing)
+
+    // optional timeline of the first steps (modl_fit_trace): CUDA events with timing on the streams of the loop
+    static constexpr int TRACE_POINTS = 10;
+    int trace_cap = 0, trace_n = 0;
+    cudaEvent_t trace_base = nullptr;
+    std::vector<cudaEvent_t> trace_ev;   // [trace_cap][TRACE_POINTS]
+    std::vector<unsigned char> trace_set;
 };
 
 namespace modl {
@@ -176,6 +186,7 @@ static int fit_init(modl_fit *f)
         MODL_CUDA_TRY(cudaEventCreateWithFlags(&f->ev_free[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < modl_fit::NRING; ++i) MODL_CUDA_TRY(cudaEventCreateWithFlags(&f->ev_ring[i], cudaEventDisableTiming));
+    MODL_CUDA_TRY(cudaEventCreateWithFlags(&f->ev_call, cudaEventDisableTiming));
     MODL_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&f->d_flag), 256));
     MODL_CUDA_TRY(cudaMemset(f->d_flag, 0, 256));
     if (const char *e = getenv("MODL_FIT_OVERLAP")) f->overlap = atoi(e);
@@ -205,6 +216,9 @@ static void fit_free(modl_fit *f)
         if (f->ev_ring[i]) cudaEventDestroy(f->ev_ring[i]);
         if (f->ring[i]) cudaFreeHost(f->ring[i]);
     }
+    if (f->ev_call) cudaEventDestroy(f->ev_call);
+    if (f->trace_base) cudaEventDestroy(f->trace_base);
+    for (cudaEvent_t e : f->trace_ev) if (e) cudaEventDestroy(e);
     if (f->d_flag) cudaFree(f->d_flag);
     if (f->inc) cudaFree(f->inc);
     if (f->inc_sub) cudaFree(f->inc_sub);
@@ -236,6 +250,17 @@ static int ring_slot(modl_fit *f, int64_t step, size_t need, unsigned char **out
     return MODL_OK;
 }
 
+// timeline point `pt` of the step being enqueued (no-op unless tracing); returns the event so that it can double as a
+// dependency
+static cudaEvent_t trace_mark(modl_fit *f, int pt, cudaStream_t st)
+{
+    if (f->trace_n >= f->trace_cap) return nullptr;
+    const size_t i = (size_t)f->trace_n * modl_fit::TRACE_POINTS + (size_t)pt;
+    cudaEventRecord(f->trace_ev[i], st);
+    f->trace_set[i] = 1;
+    return f->trace_ev[i];
+}
+
 // issue the host -> device copy of one batch into the next staging slot (copy stream)
 template <typename T>
 static int stage_batch(modl_fit *f, const T *h_rows, int64_t ldx, int64_t rows, int64_t p, int pinned, int *slot_out)
@@ -257,12 +282,17 @@ static int stage_batch(modl_fit *f, const T *h_rows, int64_t ldx, int64_t rows, 
         src = f->bounce[j];
         src_pitch = (size_t)p * sizeof(T);
     }
+    if (f->trace_n < f->trace_cap && f->trace_cap > 0) {
+        // (attributed to the step that will consume the slot only when it is the next one: good enough for a timeline)
+        trace_mark(f, 0, f->copy);
+    }
     if (src_pitch == (size_t)p * sizeof(T))
         MODL_CUDA_TRY(cudaMemcpyAsync(f->stage[j], src, bytes, cudaMemcpyHostToDevice, f->copy));
     else
         MODL_CUDA_TRY(cudaMemcpy2DAsync(f->stage[j], (size_t)p * sizeof(T), src, src_pitch, (size_t)p * sizeof(T), (size_t)rows,
                                         cudaMemcpyHostToDevice, f->copy));
     MODL_CUDA_TRY(cudaEventRecord(f->ev_copied[j], f->copy));
+    if (f->trace_n < f->trace_cap) trace_mark(f, 1, f->copy);
     f->stage_copied[j] = true;
     f->host_batches += 1;
     *slot_out = j;
@@ -319,6 +349,12 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
         MODL_TRY(grow(&f->inc_sub, &f->inc_sub_bytes, sizeof(T) * (size_t)(k * k + k * panel_ld(p))));
     }
 
+    if (overlap) {
+        // whatever the caller enqueued on its stream before this call (a new X, a state array set by hand) is visible to
+        // the streams of the loop
+        MODL_CUDA_TRY(cudaEventRecord(f->ev_call, main_st));
+        MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, f->ev_call, 0));
+    }
     const size_t ring_need = sizeof(int64_t) * (size_t)(p + k + bs) + sizeof(T) * (size_t)bs + 64;
     std::vector<int> staged((size_t)nb, -1);
     int64_t issued = 0;                      // host batches of this call whose copy has been issued
@@ -392,7 +428,7 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
         if (overlap && f->side_pending[prev]) {
             // the buffers PREFETCH rewrites were last read before ev_code of the previous step; B_ (gathered below on one
             // GPU) is final once the previous step's full-width product has run -- same stream, in order
-            MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, f->ev_code[prev], 0));
+            MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, f->code_ev[prev], 0));
         }
         if (!contiguous) {
             int64_t *d_idx = nullptr;
@@ -438,9 +474,11 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
 
         // ---- side: everything of the step that does not depend on the dictionary ----
         if (host_x) MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, f->ev_copied[sj], 0));
+        trace_mark(f, 2, f->side);
         q.phases = MODL_PHASE_PREFETCH | (sharded ? 0 : MODL_PHASE_FUSED_APPLY);
         MODL_TRY(batch_fit_impl<T>(ctx, &q, f->side));
         MODL_CUDA_TRY(cudaEventRecord(f->ev_pre[slot], f->side));
+        trace_mark(f, 3, f->side);
         MODL_CUDA_TRY(cudaEventRecord(f->ev_ring[f->step % modl_fit::NRING], f->side));
         f->ring_busy[f->step % modl_fit::NRING] = true;
 
@@ -453,16 +491,24 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
         f->serial += 1;
         q.start_flag = gate ? f->d_flag : nullptr;
         q.start_serial = f->serial;
+        trace_mark(f, 4, main_st);
+        // ev_code: the codes are solved, the subset statistics folded in; the dictionary update follows on this stream
+        cudaEvent_t evc = f->ev_code[slot];
+        if (f->trace_n < f->trace_cap) {
+            evc = f->trace_ev[(size_t)f->trace_n * modl_fit::TRACE_POINTS + 5];
+            f->trace_set[(size_t)f->trace_n * modl_fit::TRACE_POINTS + 5] = 1;
+        }
+        f->code_ev[slot] = evc;
         if (!sharded) {
             q.phases = MODL_PHASE_CODE | MODL_PHASE_STATS_SUB | MODL_PHASE_DICT | MODL_PHASE_INPUTS_READY | MODL_PHASE_FUSED_APPLY;
-            q.ev_after_apply_sub = f->ev_code[slot];        // recorded between the subset statistics and the dictionary update
+            q.ev_after_apply_sub = evc;                     // recorded between the subset statistics and the dictionary update
             MODL_TRY(batch_fit_impl<T>(ctx, &q, main_st));
         } else {
             q.stats_inc = f->inc;
             q.inc_sub = f->inc_sub;
             q.phases = MODL_PHASE_CODE | MODL_PHASE_STATS_SUB | MODL_PHASE_INPUTS_READY;
             MODL_TRY(batch_fit_impl<T>(ctx, &q, main_st));
-            MODL_CUDA_TRY(cudaEventRecord(f->ev_code[slot], main_st));
+            MODL_CUDA_TRY(cudaEventRecord(evc, main_st));
             MODL_NCCL_TRY(nccl_api()->AllReduce(f->inc_sub, f->inc_sub, (size_t)(k * k + k * panel_ld(s)),
                                                 sizeof(T) == 4 ? ncclFloat : ncclDouble, ncclSum, f->comm_main, main_st));
             q.phases = MODL_PHASE_APPLY_SUB | MODL_PHASE_DICT | MODL_PHASE_INPUTS_READY;
@@ -471,19 +517,22 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
         }
         if (gate)    // whatever the dictionary phase launched (or did not: empty subset), the flag reaches the serial
             smo->write32((CUstream)main_st, (CUdeviceptr)(uintptr_t)f->d_flag, f->serial, CU_STREAM_WRITE_VALUE_DEFAULT);
+        trace_mark(f, 6, main_st);
 
         // ---- read-back of the batch code (optional), on its own stream ----
         if (io->h_code_out) {
-            MODL_CUDA_TRY(cudaStreamWaitEvent(f->d2h, f->ev_code[slot], 0));
+            MODL_CUDA_TRY(cudaStreamWaitEvent(f->d2h, evc, 0));
             MODL_CUDA_TRY(cudaMemcpyAsync(static_cast<T *>(io->h_code_out) + r0 * k, ctx->slot_ptr[WS_CODE_BATCH],
                                           sizeof(T) * (size_t)(b * k), cudaMemcpyDeviceToHost, f->d2h));
             MODL_CUDA_TRY(cudaEventRecord(f->ev_d2h[slot], f->d2h));
+            trace_mark(f, 9, f->d2h);
             f->d2h_pending[slot] = true;
         }
 
         // ---- side: the full-width statistic, behind the dictionary update ----
-        MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, f->ev_code[slot], 0));
+        MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, evc, 0));
         if (gate) smo->wait32((CUstream)f->side, (CUdeviceptr)(uintptr_t)f->d_flag, f->serial, CU_STREAM_WAIT_VALUE_GEQ);
+        trace_mark(f, 7, f->side);
         q.phases = MODL_PHASE_STATS_B;
         q.inc_sub = nullptr;
         q.ev_after_apply_sub = nullptr;
@@ -497,6 +546,8 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
             MODL_TRY(batch_fit_impl<T>(ctx, &q, f->side));
         }
         MODL_CUDA_TRY(cudaEventRecord(f->ev_side[slot], f->side));
+        trace_mark(f, 8, f->side);
+        if (f->trace_n < f->trace_cap) f->trace_n += 1;
         f->side_pending[slot] = true;
         if (host_x) {
             MODL_CUDA_TRY(cudaEventRecord(f->ev_free[sj], f->side));
@@ -563,6 +614,48 @@ int modl_fit_set_option(modl_fit *f, const char *name, int value)
     if (!strcmp(name, "overlap")) f->overlap = value;
     else if (!strcmp(name, "gate")) f->gate = value;
     else { set_error("unknown option %s", name); return MODL_EINVAL; }
+    return MODL_OK;
+}
+
+/* Debug: timeline of the next `steps` steps of the two-stream schedule (0 = off).  modl_fit_trace_read synchronises the
+ * device and writes, per traced step, the milliseconds since the trace was armed at which each of these points was
+ * reached on its stream (NaN = not recorded):  0 H2D start, 1 H2D end (copy stream); 2 PREFETCH start, 3 PREFETCH end
+ * (second stream); 4 critical path start, 5 codes + subset statistics done, 6 dictionary update done (caller's stream);
+ * 7 full-width product start, 8 full-width product end (second stream); 9 code read-back done. */
+int modl_fit_trace(modl_fit *f, int steps)
+{
+    MODL_REQUIRE(f && steps >= 0 && steps <= 4096, "trace steps");
+    CtxGuard g_(f->ctx);
+    MODL_CUDA_TRY(cudaDeviceSynchronize());
+    for (cudaEvent_t e : f->trace_ev) if (e) cudaEventDestroy(e);
+    f->trace_ev.clear(); f->trace_set.clear();
+    f->trace_cap = steps; f->trace_n = 0;
+    if (steps == 0) return MODL_OK;
+    if (!f->trace_base) MODL_CUDA_TRY(cudaEventCreate(&f->trace_base));
+    f->trace_ev.assign((size_t)steps * modl_fit::TRACE_POINTS, nullptr);
+    f->trace_set.assign((size_t)steps * modl_fit::TRACE_POINTS, 0);
+    for (cudaEvent_t &e : f->trace_ev) MODL_CUDA_TRY(cudaEventCreate(&e));
+    MODL_CUDA_TRY(cudaEventRecord(f->trace_base, nullptr));
+    MODL_CUDA_TRY(cudaEventSynchronize(f->trace_base));
+    return MODL_OK;
+}
+
+int modl_fit_trace_read(modl_fit *f, double *h_ms, int capacity_steps, int *h_steps)
+{
+    MODL_REQUIRE(f && h_ms && h_steps && capacity_steps >= 0, "trace buffers");
+    CtxGuard g_(f->ctx);
+    MODL_CUDA_TRY(cudaDeviceSynchronize());
+    const int n = f->trace_n < capacity_steps ? f->trace_n : capacity_steps;
+    for (int i = 0; i < n; ++i)
+        for (int pt = 0; pt < modl_fit::TRACE_POINTS; ++pt) {
+            const size_t e = (size_t)i * modl_fit::TRACE_POINTS + (size_t)pt;
+            float ms = 0.f;
+            double v = std::nan("");
+            if (f->trace_set[e] && cudaEventElapsedTime(&ms, f->trace_base, f->trace_ev[e]) == cudaSuccess) v = ms;
+            h_ms[e] = v;
+        }
+    cudaGetLastError();
+    *h_steps = n;
     return MODL_OK;
 }
 

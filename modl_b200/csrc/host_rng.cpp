@@ -4,7 +4,7 @@
 //   * FeatureSampler    <-> modl/utils/randomkit/sampler.pyx:10-69
 //   * modl_batch_weight <-> modl/decomposition/dict_fact_fast.pyx:115-122
 // The subset / permutation streams decide WHICH columns and atoms every kernel touches, so
-// they must reproduce the reference integer for integer; tests/test_host_rng.py
+// they must reproduce the reference integer for integer; tests/test_host_bookkeeping.py
 // checks the reference's known-answer vectors through this C ABI.
 #include <cmath>
 #include <cstdint>

@@ -807,8 +807,12 @@ class Coder(CodingMixin, BaseEstimator):
     """Sparse coder over a fixed dictionary [ref: dict_fact.py:724-745]."""
 
     def __init__(self, dictionary, code_alpha=1, code_l1_ratio=1, tol=1e-2, max_iter=100, code_pos=False,
-                 random_state=None, n_threads=1):
+                 random_state=None, n_threads=1, device=None):
         self.dictionary = dictionary
+        self.device = device
+        if device is not None:           # the dictionary lands on this device, not on whichever one is current
+            dev = torch.device(device)
+            self.__dict__["_device"] = dev if dev.index is not None else torch.device('cuda', torch.cuda.current_device())
         self._set_coding_params(dictionary.shape[0], code_l1_ratio=code_l1_ratio, code_alpha=code_alpha,
                                 code_pos=code_pos, random_state=random_state, tol=tol, max_iter=max_iter,
                                 n_threads=n_threads)

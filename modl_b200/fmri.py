@@ -214,8 +214,10 @@ def _sharded_record_fit(dict_fact, masked_data, permutation, sample_indices, bat
     [m b, m b + t); rank g solves the g-th of `world` equal shares and the statistics increments are summed over
     ranks (`ShardedDictFact`).  A ragged last minibatch whose size does not divide by `world` is run REPLICATED
     -- every rank processes all of its rows, no exchange -- which keeps the replicas bit-identical without
-    unequal shards.  Sample index = position in the permuted record (fmri.py:528-531 as executed), so a
-    position is always solved by the same rank."""
+    unequal shards.  Sample index = position in the permuted record (fmri.py:528-531 as executed).  Which rank solves
+    a position depends on the record's length (a shorter record re-partitions its tail minibatch), so the rows of
+    `code_` a rank holds are NOT a fixed set across records: harmless here because the fMRI codes are ridge solutions
+    (code_l1_ratio = 0: no warm start is read back), and the reason `code_` must not be compared across ranks."""
     n = permutation.shape[0]
     plan, mine = [], []
     for lo in range(0, n, batch_size):
@@ -393,7 +395,8 @@ class fMRICoderMixin(BaseEstimator, TransformerMixin):
     def _set_components(self, components):
         self.components_ = components
         self.components_img_ = self.masker_.inverse_transform(components)
-        self.coder_ = Coder(dictionary=components, code_alpha=self.alpha, code_l1_ratio=0, n_threads=self.n_jobs).fit()
+        self.coder_ = Coder(dictionary=components, code_alpha=self.alpha, code_l1_ratio=0, n_threads=self.n_jobs,
+                            device=self.device).fit()
 
     def _base_fit(self, imgs=None, confounds=None):
         if imgs is not None:

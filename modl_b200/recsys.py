@@ -216,6 +216,7 @@ class RecsysDictFact(BaseEstimator):
             else:
                 for batch in gen_batches(n_samples, batch_size):
                     self._single_batch_fit(Xd, permutation[batch])
+            self._check_solves()
         self._refit(Xd)
         return self
 
@@ -232,6 +233,13 @@ class RecsysDictFact(BaseEstimator):
             b = sl.stop - sl.start
             kern.gram_dx(Dt, Xd.indptr, Xd.indices, Xd.data, None, sl.start, b, n_features, self.alpha, G, Dx)
             kern.solve(G, Dx, code[sl], None, b)
+        self._check_solves()
+
+    def _check_solves(self):
+        """The reference solves every row with `linalg.solve`, which raises on a singular system [ref: recsys.py:178,
+        :265]; the device Cholesky records a non-positive pivot in a sticky flag instead, read here (one
+        synchronisation per refit / per epoch)."""
+        _lib.get_context(self._device.index).check_info(torch.cuda.current_stream(self._device).cuda_stream)
 
     def _batch_entries(self, Xd, batch):
         """The stored entries of the rows `batch`, ordered by (column, position of the row in the batch):
@@ -333,7 +341,8 @@ class RecsysDictFact(BaseEstimator):
     # ---------------------------------------------------------------- predict / score
     def predict(self, X):
         """Values of the factorisation at the stored entries of X, as a CSR matrix with the same structure
-        [ref: recsys.py:215-244]."""
+        [ref: recsys.py:215-244].  The values are floating point whatever the dtype of X.data (the reference computes them
+        in a double buffer, recsys_fast.pyx:10-37)."""
         X = _as_csr(X)
         if X.shape != (self._d_code_.shape[0], self._d_components_.shape[1]):
             raise ValueError("X has shape %s, the model %s" % (X.shape, (self._d_code_.shape[0],
@@ -343,7 +352,8 @@ class RecsysDictFact(BaseEstimator):
         indices = torch.from_numpy(np.ascontiguousarray(X.indices, dtype=np.int32)).to(dev)
         out_d = torch.zeros((X.nnz,), dtype=torch.float64, device=dev)
         self._kernels.predict(self._d_code_, self._d_Dt, indptr, indices, out_d)
-        out = out_d.cpu().numpy().astype(X.data.dtype, copy=False)
+        out_dtype = X.data.dtype if X.data.dtype in (np.float32, np.float64) else np.float64
+        out = out_d.cpu().numpy().astype(out_dtype, copy=False)
         if self.detrend:
             out += np.repeat(self.row_mean_, np.diff(X.indptr))
             out += self.col_mean_.take(X.indices, mode='clip')
