@@ -59,6 +59,10 @@ class _DeviceKernels(object):
         self._call("modl_enet_regression_multi_gram_", ptr(G), ptr(Dx), None, 0, 0, None, ptr(code), ptr(rows),
                    int(b), k, 0.0, 0.0, 0, 0.0, 0, None)
 
+    def check_solves(self):
+        """Raise if any Cholesky since the last check met a non-positive pivot (sticky device flag, one sync)."""
+        self.ctx.check_info(torch.cuda.current_stream(self.device).cuda_stream)
+
     def update_B(self, B, code, subset, col_ptr, entry_row, entry_val, feature_n_iter, w, n_iter):
         self._call("modl_recsys_update_B_", ptr(B), B.stride(0), ptr(code), ptr(subset), ptr(col_ptr), ptr(entry_row),
                    ptr(entry_val), ptr(feature_n_iter), subset.shape[0], code.shape[1], float(w), int(n_iter))
@@ -239,7 +243,7 @@ class RecsysDictFact(BaseEstimator):
         """The reference solves every row with `linalg.solve`, which raises on a singular system [ref: recsys.py:178,
         :265]; the device Cholesky records a non-positive pivot in a sticky flag instead, read here (one
         synchronisation per refit / per epoch)."""
-        _lib.get_context(self._device.index).check_info(torch.cuda.current_stream(self._device).cuda_stream)
+        self._kernels.check_solves()
 
     def _batch_entries(self, Xd, batch):
         """The stored entries of the rows `batch`, ordered by (column, position of the row in the batch):
