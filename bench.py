@@ -257,6 +257,9 @@ class Runner(object):
         kw.update(over)
         est = self.est_cls(device=self.dev, **kw)
         est.prepare(n_samples=N_SAMPLES_STATE, X=X0[:K])
+        # the device-resident legs pass rows that were uploaded before the timed regions: nothing pending on the stream
+        # writes them, so the loop's second stream need not wait for the caller's stream at every call
+        est.device_rows_final = True
         return est
 
     def idx_of(self, i):

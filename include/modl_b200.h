@@ -373,6 +373,12 @@ typedef struct modl_fit_batches {      /* one partial_fit call */
                                           of its own as soon as the block's solve has finished */
     int wait_host;                     /* 1: return once X has been consumed and h_code_out is complete; 0: fully asynchronous
                                           (the caller keeps X untouched until modl_fit_synchronize) */
+    int fence;                         /* do the loop's own streams wait for what the caller enqueued on `stream` before this
+                                          call?  0 = automatic: yes for device rows (they may be the output of a pending kernel),
+                                          no for host rows; 1 = yes (the caller wrote a state array or X with device work since the
+                                          last call); 2 = no (device rows that are final: nothing pending on `stream` writes them).
+                                          The first call of a loop object always waits.  The wait serialises the next block's
+                                          input preparation behind the previous call's dictionary update (both are on `stream`). */
 } modl_fit_batches;
 
 int modl_fit_create(modl_ctx *ctx, modl_fit **out);

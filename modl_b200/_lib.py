@@ -52,6 +52,7 @@ class FitBatches(C.Structure):
         ("h_sample_indices", vp), ("sampler", vp), ("h_n_iter", vp), ("h_sample_n_iter", vp),
         ("update_counters", ci), ("h_orders", vp), ("h_w_sample", vp), ("sweeps", vp),
         ("h_last_subset", vp), ("h_last_subset_len", vp), ("h_code_out", vp), ("wait_host", ci),
+        ("fence", ci),
     ]
 
 

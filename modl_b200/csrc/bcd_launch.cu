@@ -1,6 +1,7 @@
 // bcd_launch.cu -- launch geometry of the dictionary-update kernels (bcd_kernels.cuh, bcd_pilot.cuh).
 #include "bcd_kernels.cuh"
 #include "bcd_pilot.cuh"
+#include "bcd_blocked.cuh"
 #include "launch.h"
 
 #include <mutex>
@@ -57,10 +58,17 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
         for (int cs = 16; cs >= 2 && !nblk; cs >>= 1) {
             if (cs > ctx->opt_bcd_cluster) continue;
             const int64_t c = round_up(ceil_div(s, cs), 4), ncp = round_up(c, 32);
-            // variant 1 = per-atom look-ahead pilot, 0 = plain per-atom kernel
-            for (int pilot = ctx->opt_bcd_pilot ? 1 : 0; pilot >= 0 && !nblk; --pilot) {
+            // variant 2 = block-wise coefficient-space solve (L2 ball, no positivity), 1 = per-atom look-ahead pilot,
+            // 0 = plain per-atom kernel
+            const bool blocked_ok = ctx->opt_bcd_blocked != 0 && l1_ratio == T(0) && !positive;
+            for (int pilot = blocked_ok ? 2 : (ctx->opt_bcd_pilot ? 1 : 0); pilot >= 0 && !nblk; --pilot) {
                 size_t need;
-                if (pilot) {
+                if (pilot == 2) {
+                    if (bcd_blocked_red_elems(ncp) > (int64_t)BCD_MAX_CLUSTER * BB_GRAM) continue;
+                    need = bcd_blocked_smem_bytes<T>(k, ncp);
+                } else if (pilot == 1 && !ctx->opt_bcd_pilot) {
+                    continue;
+                } else if (pilot) {
                     if (ncp > 192) continue;
                     need = bcd_pilot_smem_bytes<T>(k, ncp);
                 } else {
@@ -68,7 +76,8 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
                     if (ncp > 2 * BCD_THREADS) continue;
                 }
                 if (need > budget) continue;
-                const void *fn = pilot ? pilot_kernel_for<T>((int)(ncp / 32), l1_ratio != T(0), pipe) : (const void *)kern;
+                const void *fn = pilot == 2 ? (const void *)bcd_blocked_kernel<T>
+                                 : pilot ? pilot_kernel_for<T>((int)(ncp / 32), l1_ratio != T(0), pipe) : (const void *)kern;
                 // (kernel, cluster size, shared memory) combinations already validated on this device: skip the
                 // attribute and occupancy queries (tens of microseconds of host time per step)
                 struct Seen { const void *fn; int cs; size_t need; int device; };
@@ -92,7 +101,7 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
                     continue;
                 }
                 cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(cs); cfg.blockDim = dim3(pilot ? BP_THREADS : BCD_THREADS);
+                cfg.gridDim = dim3(cs); cfg.blockDim = dim3(pilot == 2 ? BB_THREADS : pilot ? BP_THREADS : BCD_THREADS);
                 cfg.dynamicSmemBytes = need; cfg.stream = st;
                 cudaLaunchAttribute at[1];
                 at[0].id = cudaLaunchAttributeClusterDimension;
@@ -157,7 +166,7 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
     }
 
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(use_pilot ? BP_THREADS : BCD_THREADS);
+    cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(use_pilot == 2 ? BB_THREADS : use_pilot ? BP_THREADS : BCD_THREADS);
     cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     if (use_cluster) {
@@ -168,7 +177,9 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
         at[0].val.cooperative = 1;
     }
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (use_pilot) {
+    if (use_pilot == 2) {
+        MODL_CUDA_TRY(cudaLaunchKernelEx(&cfg, bcd_blocked_kernel<T>, P));
+    } else if (use_pilot) {
         void *args[] = {&P};
         MODL_CUDA_TRY(cudaLaunchKernelExC(&cfg, pilot_kernel_for<T>((int)(round_up(cols, 32) / 32), l1_ratio != T(0), pipe), args));
     } else {

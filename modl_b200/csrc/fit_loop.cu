@@ -349,9 +349,12 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
         MODL_TRY(grow(&f->inc_sub, &f->inc_sub_bytes, sizeof(T) * (size_t)(k * k + k * panel_ld(p))));
     }
 
-    if (overlap) {
+    MODL_REQUIRE(io->fence >= 0 && io->fence <= 2, "fence");
+    const bool fence = io->fence == 1 || (io->fence == 0 && !host_x) || f->step == 0;
+    if (overlap && fence) {
         // whatever the caller enqueued on its stream before this call (a new X, a state array set by hand) is visible to
-        // the streams of the loop
+        // the streams of the loop.  The previous call's dictionary update is on that stream too, so this also keeps the next
+        // block's input preparation from starting under it: callers whose rows are final say so (io->fence)
         MODL_CUDA_TRY(cudaEventRecord(f->ev_call, main_st));
         MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, f->ev_call, 0));
     }

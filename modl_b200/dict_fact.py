@@ -75,6 +75,7 @@ class _DeviceArray(object):
             t = value.to(dev)
         else:
             t = torch.from_numpy(np.ascontiguousarray(value)).to(dev)
+        obj.__dict__["_state_dirty"] = True     # the next partial_fit orders its own streams behind this write
         if cur is not None and cur.shape == t.shape:
             cur.copy_(t)            # keep the storage (and dtype) the kernels already point at
         else:
@@ -420,6 +421,14 @@ class DictFact(CodingMixin, BaseEstimator):
             keep.append(co)
         wait_host = 0 if getattr(self, "async_host_copy", False) else 1
         io.wait_host = wait_host
+        # stream ordering against the caller (modl_fit_batches.fence): state written since the last call -> wait;
+        # device rows declared final (`device_rows_final = True`) -> do not; otherwise automatic
+        if self.__dict__.pop("_state_dirty", True):
+            io.fence = 1
+        elif Xt.is_cuda and self.__dict__.get("device_rows_final", False):
+            io.fence = 2
+        else:
+            io.fence = 0
         itemsize = Xt.element_size()
         average = self.G_agg == 'average' or self.Dx_agg == 'average'
         st = C.c_void_p(stream.cuda_stream)
@@ -534,6 +543,7 @@ class DictFact(CodingMixin, BaseEstimator):
                 self._gram_dx(D, None, G, None, None)
                 self.__dict__["_d_G_"] = G
             self.G_agg = 'full'
+        self.__dict__["_state_dirty"] = True
         BaseEstimator.set_params(self, **params)
         # A switch to Dx_agg='average' after prepare() (the 'gram' schedules of the front-ends,
         # image.py:142-144, fmri.py:497-499) finds no Dx_average_ in the reference and raises there;
@@ -554,6 +564,7 @@ class DictFact(CodingMixin, BaseEstimator):
         if self.Dx_agg == 'average':
             arrays.append(self._d_Dx_average_)
         perm = random_state.shuffle_with_trace(arrays)
+        self.__dict__["_state_dirty"] = True
         self.labels_ = self.labels_[perm]
         return perm
 
@@ -644,6 +655,7 @@ class DictFact(CodingMixin, BaseEstimator):
             self.__dict__.pop(name, None)
         self.__dict__["_d_sweeps"] = None
         self.__dict__["_pipeline"] = None
+        self.__dict__["_state_dirty"] = True
         return self
 
     def _callback(self):

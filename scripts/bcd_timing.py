@@ -1,6 +1,7 @@
-"""Debug: clock cycles per atom of the cluster dictionary-update kernel at the config-2 shape (CTA 0 stamps), for the
-kernel variants: look-ahead pilot with the pipelined norm exchange, without it, and the per-stage breakdown of the
-latter (0-1 candidate, 1-2 warp sums, 2-3 send, 3-4 wait, 4-5 sums, 5-6 projection)."""
+"""Debug: clock cycles of the cluster dictionary-update kernels at the config-2 shape (CTA 0 stamps): the block-wise
+coefficient-space kernel (per-phase breakdown of a block of 16 atoms), the look-ahead pilot with the pipelined norm
+exchange, and the pilot without it (per-stage breakdown: 0-1 candidate, 1-2 warp sums, 2-3 send, 3-4 wait, 4-5 sums,
+5-6 projection)."""
 import ctypes as C
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,26 +19,40 @@ L.modl_debug_bcd_timing.restype = C.c_int
 L.modl_debug_bcd_stamps.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 L.modl_debug_bcd_stamps.restype = C.c_int
 print("library:", _lib.LIB_PATH)
-for pipe in (1, 0):
+Xd = torch.from_numpy(X).cuda()
+for name, blocked, pipe in (("blocked", 1, 1), ("pipelined pilot", 0, 1), ("pilot", 0, 0)):
+    ctx.set_option("bcd_blocked", blocked)
     ctx.set_option("bcd_pipeline", pipe)
     ctx.set_option("bcd_timing", 1)
     est = DictFact(**EST_KW)
     est.python_loop = True          # one stream, one fused call per step
     est.prepare(n_samples=4 * B, X=X[:K])
-    Xd = torch.from_numpy(X).cuda()
     for i in range(3):
         est.partial_fit(Xd[i * B:(i + 1) * B], np.arange(i * B, (i + 1) * B))
     torch.cuda.synchronize()
     st = (C.c_longlong * (8 * K + 16))()
     L.modl_debug_bcd_stamps(ctx.handle, st, 8 * K + 16)
-    t0 = [st[8 * t] for t in range(K)]
-    per = (t0[K - 1] - t0[8]) / (K - 9)
-    print("pipeline", pipe, "cycles per atom (atoms 8..%d): %.0f" % (K - 1, per),
-          " kernel prologue %d, loop %d cycles" % (st[8 * K + 1] - st[8 * K], st[8 * K + 2] - st[8 * K + 1]))
-    if not pipe:
-        gaps = (C.c_double * 7)()
-        L.modl_debug_bcd_timing(ctx.handle, gaps)
-        names = ["0-1", "1-2", "2-3", "3-4", "4-5", "5-6", "6-7"]
-        print("   stages", {n: round(g) for n, g in zip(names, gaps)}, "total", round(sum(gaps)))
+    g = [st[8 * K + i] for i in range(5)]
+    if blocked:
+        nbk = (K + 15) // 16
+        ph = np.array([[st[8 * b + i] for i in range(7)] for b in range(nbk)], dtype=np.int64)
+        d = np.diff(ph, axis=1)[1:]            # blocks 1.. (block 0 has no previous block to apply)
+        names = ["S0a apply", "S0b repair+basis", "S1 gram", "cluster wait", "S2 exchange", "S3 sum", "S4 solve | look-ahead"]
+        print(name, "| kernel %d cycles: prologue %d (load %d, first product %d), blocks %d, epilogue %d"
+              % (g[4] - g[0], g[2] - g[0], g[1] - g[0], g[2] - g[1], g[3] - g[2], g[4] - g[3]))
+        per_block = (ph[-1, 6] - ph[1, 0]) / (nbk - 1)
+        print("   cycles per block of 16: %.0f  (%.0f per atom)" % (per_block, per_block / 16))
+        print("   phases (mean over blocks 1..):", {n: int(round(v)) for n, v in zip(names[:6] + [names[6]], list(d.mean(axis=0)))})
+    else:
+        t0 = [st[8 * t] for t in range(K)]
+        per = (t0[K - 1] - t0[8]) / (K - 9)
+        print(name, "| cycles per atom (atoms 8..%d): %.0f" % (K - 1, per),
+              " kernel prologue %d, loop %d cycles" % (g[1] - g[0], g[2] - g[1]))
+        if not pipe:
+            gaps = (C.c_double * 7)()
+            L.modl_debug_bcd_timing(ctx.handle, gaps)
+            names = ["0-1", "1-2", "2-3", "3-4", "4-5", "5-6", "6-7"]
+            print("   stages", {n: round(g_) for n, g_ in zip(names, gaps)}, "total", round(sum(gaps)))
 ctx.set_option("bcd_timing", 0)
 ctx.set_option("bcd_pipeline", 1)
+ctx.set_option("bcd_blocked", 1)

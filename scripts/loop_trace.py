@@ -16,6 +16,7 @@ X = make_data((steps + 6) * B)
 rows = torch.from_numpy(X).cuda() if mode == "device" else torch.from_numpy(X).pin_memory()
 est = DictFact(async_host_copy=True, **EST_KW)
 est.prepare(n_samples=X.shape[0], X=X[:K])
+est.device_rows_final = os.environ.get("MODL_TRACE_FENCE", "0") != "1"     # rows uploaded once, above
 out = torch.empty((B, K), dtype=torch.float32).pin_memory() if mode != "device" else None
 for i in range(6):
     est.partial_fit(rows[i * B:(i + 1) * B], np.arange(i * B, (i + 1) * B), code_out=out)

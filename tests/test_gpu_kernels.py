@@ -180,12 +180,14 @@ def test_ridge_reports_non_spd(dev):
                                      np.ones((3, 8), np.float32), np.arange(3), 0., 0.1, False, 1e-2, 10)
 
 
-VARIANTS = {"pipelined": dict(bcd_pilot=1, bcd_pipeline=1), "pilot": dict(bcd_pilot=1, bcd_pipeline=0),
-            "plain": dict(bcd_pilot=0, bcd_pipeline=0)}
+VARIANTS = {"blocked": dict(bcd_blocked=1, bcd_pilot=1, bcd_pipeline=1),
+            "pipelined": dict(bcd_blocked=0, bcd_pilot=1, bcd_pipeline=1),
+            "pilot": dict(bcd_blocked=0, bcd_pilot=1, bcd_pipeline=0),
+            "plain": dict(bcd_blocked=0, bcd_pilot=0, bcd_pipeline=0)}
 
 
 def _run_update_dict(dev, D0, B, C, norm0, subset, order, l1, pos, G0=None, mode=0, w=0.5, step=1.0, cluster=None,
-                     variant="pipelined"):
+                     variant="blocked"):
     from modl_b200 import _lib
     from modl_b200._util import ptr, stream_of
     k, p = D0.shape
@@ -205,17 +207,18 @@ def _run_update_dict(dev, D0, B, C, norm0, subset, order, l1, pos, G0=None, mode
     finally:
         if cluster is not None:
             ctx.set_option("bcd_cluster", 16)
-        for name, val in VARIANTS["pipelined"].items():
+        for name, val in VARIANTS["blocked"].items():
             ctx.set_option(name, val)
     return Dd.cpu().numpy(), nd.cpu().numpy(), (Gd.cpu().numpy() if Gd is not None else None)
 
 
-@pytest.mark.parametrize("variant", ["pipelined", "pilot", "plain"])
+@pytest.mark.parametrize("variant", ["blocked", "pipelined", "pilot", "plain"])
 @pytest.mark.parametrize("cluster", [16, 8, 2, 0])
 def test_update_dict_golden(dev, golden, cluster, variant):
     """One BCD dictionary step vs the reference's _update_dict (golden), for every barrier
-    flavour (16/8/2-CTA clusters, cooperative global barrier) and every kernel variant (look-ahead
-    pilot kernel with and without the pipelined norm exchange, plain per-atom kernel)."""
+    flavour (16/8/2-CTA clusters, cooperative global barrier) and every kernel variant (block-wise
+    coefficient-space solve, look-ahead pilot kernel with and without the pipelined norm exchange, plain
+    per-atom kernel)."""
     g = golden("update_dict.npz")
     for dt in (np.float32, np.float64):
         for ci, (l1, pos, full) in enumerate(g["cases"]):
@@ -235,7 +238,7 @@ def test_update_dict_golden(dev, golden, cluster, variant):
             np.testing.assert_array_equal(D1[:, mask], g["D0_" + tag][:, mask])
 
 
-@pytest.mark.parametrize("variant", ["pipelined", "pilot"])
+@pytest.mark.parametrize("variant", ["blocked", "pipelined", "pilot"])
 @pytest.mark.parametrize("shape", [(256, 10000, 1250), (70, 30000, 2500), (64, 4000, 4000), (256, 6000, 300), (37, 900, 333),
                                    (70, 40000, 17000), (24, 9000, 9000, "f64")])
 def test_update_dict_bench_shapes(dev, oracle, shape, variant):
@@ -244,7 +247,7 @@ def test_update_dict_bench_shapes(dev, oracle, shape, variant):
     the subset of BASELINE configs[3] (p = 2e5, reduction 12); the float64 one takes the 48-per-thread variant."""
     k, p, s = shape[:3]
     dt = np.float64 if len(shape) > 3 else np.float32
-    if variant != "pipelined" and (len(shape) > 3 or shape[2] >= 4000):
+    if variant != "blocked" and (len(shape) > 3 or shape[2] >= 4000):
         pytest.skip("panels beyond one cluster take the grid-wide kernel whatever the variant: one pass is enough")
     rng = np.random.RandomState(5)
     for l1, pos in ((0., False), (1., False), (0.3, True)):
