@@ -43,6 +43,22 @@ constexpr int BB_LA = 8;                 // atoms per pass of the look-ahead pro
 constexpr int BB_MLD = BB_NB + 1;        // row pitch of the Gram matrix in shared memory
 enum { BB_BAR_WORKERS = 1 };
 
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+// acc.xy += a.xy * b.xy  (float: one packed FFMA2 -- the fma pipe issues an FFMA2 at the rate of an FFMA)
+__device__ __forceinline__ void pair_mul_fma(const Pair<float> &a, const Pair<float> &b, Pair<float> &acc)
+{
+    const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(acc.x, acc.y));
+    acc.x = r.x; acc.y = r.y;
+}
+__device__ __forceinline__ void pair_mul_fma(const Pair<double> &a, const Pair<double> &b, Pair<double> &acc)
+{
+    acc.x = fma(a.x, b.x, acc.x); acc.y = fma(a.y, b.y, acc.y);
+}
+
 // shared-memory footprint in bytes -- must match the carve-up in the kernel
 template <typename T>
 __host__ __device__ inline size_t bcd_blocked_smem_bytes(int64_t k, int64_t ncp)
@@ -54,7 +70,7 @@ __host__ __device__ inline size_t bcd_blocked_smem_bytes(int64_t k, int64_t ncp)
                           + BB_NB * ncp           // basis
                           + BB_M * ncp            // dlt
                           + BB_M * BB_NB          // coef
-                          + BB_M * BB_M           // Lblk
+                          + 2 * BB_M * BB_M       // Lblk, Cx
                           + BB_NB * BB_MLD + 32   // Mfull (padded to a multiple of 4)
                           + 2 * kp                // cnorm, rad
                           + 2 * BB_M              // caa, rcaa
@@ -85,17 +101,19 @@ bcd_blocked_kernel(BcdParams<T> P)
     const int kp = (int)round_up(k, 32);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nbk = (k + BB_M - 1) / BB_M;
+    const int NP = ncp >> 1;                                 // column pairs of the slice
 
     // ---- shared memory carve-up (see bcd_blocked_smem_bytes) ----
     T *Ds = reinterpret_cast<T *>(bb_smem_raw);              // [k][ncp]   the CTA's slice of D_sub
-    T *Cblk = Ds + (size_t)k * ncp;                          // [kp][M]    C[a_j, i] at [i*M + j] for the block in flight / ahead
+    T *Cblk = Ds + (size_t)k * ncp;                          // [M][kp]    C[a_j, :] of the block in flight / ahead
     T *Rraw = Cblk + kp * BB_M;                              // [M][ncp]   look-ahead product C[a_j,:] . D_sub (previous block not applied)
     T *Brow = Rraw + BB_M * ncp;                             // [M][ncp]   B_sub rows of the block
     T *basis = Brow + BB_M * ncp;                            // [2M][ncp]  g_1..g_M, d_1..d_M
     T *dlt = basis + BB_NB * ncp;                            // [M][ncp]   deltas of the block just applied
     T *coef = dlt + BB_M * ncp;                              // [M][2M]    n_t = sum_r coef[t][r] basis_r
     T *Lblk = coef + BB_M * BB_NB;                           // [M][M]     L_tj (j < t), zero elsewhere
-    T *Mfull = Lblk + BB_M * BB_M;                           // [2M][2M+1] Gram matrix of the basis
+    T *Cx = Lblk + BB_M * BB_M;                              // [M][M]     C[a_j, a_i(previous block)] at [i*M + j]
+    T *Mfull = Cx + BB_M * BB_M;                             // [2M][2M+1] Gram matrix of the basis
     T *cnorm = Mfull + BB_NB * BB_MLD + 32;                  // [kp]       comp_norm_ on entry
     T *rad = cnorm + kp;                                     // [kp]       radius used for every atom
     T *caa = rad + kp;                                       // [M]        C[a_t, a_t]
@@ -109,38 +127,76 @@ bcd_blocked_kernel(BcdParams<T> P)
     const unsigned xbar_addr = (unsigned)__cvta_generic_to_shared(&xbar);
     constexpr unsigned kGramBytes = BB_GRAM * sizeof(T);
 
-    long long *stamp = (P.timing && g == 0 && tid == 0) ? P.timing : nullptr;   // debug: [nbk][8] phase stamps, then 8 global
+    // debug stamps of CTA 0: thread 0 (solver warp) [b][8] phase starts, thread 32 (first product warp) look-ahead
+    // start / end per block at 8k + 16 + 2b, kernel-level stamps at 8k .. 8k + 7
+    long long *stamp = (P.timing && g == 0 && tid == 0) ? P.timing : nullptr;
+    long long *wstamp = (P.timing && g == 0 && tid == 32) ? P.timing + (int64_t)8 * k + 16 : nullptr;
 #define BB_STAMP(b_, slot_) do { if (stamp) stamp[(int64_t)(b_) * 8 + (slot_)] = clock64(); } while (0)
     if (stamp) stamp[(int64_t)8 * k] = clock64();
 
-    // ---- prologue: D slice, norms, order, tables ----
-    const T *Dg = P.Dp + c0;
-    constexpr int VE = 16 / (int)sizeof(T);
-    const bool vec_ok = (lds % VE == 0) && (c0 % VE == 0) && ((reinterpret_cast<uintptr_t>(P.Dp) & 15) == 0);
-    if (vec_ok) {
-        const int nv = ncp / VE;
-#pragma unroll 4
-        for (int e = tid; e < k * nv; e += BB_THREADS) {
-            const int i = e / nv, cv = (e % nv) * VE;
-            alignas(16) T tmp[VE];
-#pragma unroll
-            for (int u = 0; u < VE; ++u) tmp[u] = T(0);
-            if (cv < nc) *reinterpret_cast<uint4 *>(tmp) = *reinterpret_cast<const uint4 *>(Dg + (int64_t)i * lds + cv);
-#pragma unroll
-            for (int u = 0; u < VE; ++u) Ds[i * ncp + cv + u] = (cv + u < nc) ? tmp[u] : T(0);
+    constexpr int VE = 16 / (int)sizeof(T);                  // elements per 16-byte copy
+    const bool c_vec = (k % VE == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+    const bool p_vec = (lds % VE == 0) && (c0 % VE == 0) && ((reinterpret_cast<uintptr_t>(P.Dp) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(P.Bp) & 15) == 0);
+
+    // operands of block b: C[a_j, :] and B_sub[a_j, my columns]; every copy asynchronous and in flight at once
+    auto issue_loads = [&](int b) {
+        const int mb = min(BB_M, k - b * BB_M);
+        if (c_vec) {
+            const int nv = k / VE;
+            for (int e = tid; e < BB_M * nv; e += BB_THREADS) {
+                const int j = e / nv, iv = (e % nv) * VE;
+                if (j < mb) cp_async_16(Cblk + j * kp + iv, P.C + (int64_t)ord_s[b * BB_M + j] * k + iv);
+            }
+        } else {
+            for (int e = tid; e < BB_M * k; e += BB_THREADS) {
+                const int j = e / k, i = e % k;
+                if (j < mb) cp_async_elem(Cblk + j * kp + i, P.C + (int64_t)ord_s[b * BB_M + j] * k + i);
+            }
         }
-    } else {
-        for (int e = tid; e < k * ncp; e += BB_THREADS) {
-            const int i = e / ncp, c = e % ncp;
-            Ds[e] = (c < nc) ? Dg[(int64_t)i * lds + c] : T(0);
+        const int nvb = ncp / VE;
+        for (int e = tid; e < BB_M * nvb; e += BB_THREADS) {
+            const int j = e / nvb, cv = (e % nvb) * VE;
+            T *dst = Brow + j * ncp + cv;
+            if (j < mb && p_vec && cv + VE <= nc) {
+                cp_async_16(dst, P.Bp + (int64_t)ord_s[b * BB_M + j] * lds + c0 + cv);
+            } else {
+#pragma unroll
+                for (int u = 0; u < VE; ++u) {
+                    if (j < mb && cv + u < nc) cp_async_elem(dst + u, P.Bp + (int64_t)ord_s[b * BB_M + j] * lds + c0 + cv + u);
+                    else dst[u] = T(0);
+                }
+            }
         }
-    }
+        cp_async_commit();
+    };
+
+    // ---- prologue: D slice (asynchronous copies), norms, order, tables ----
     for (int i = tid; i < kp; i += BB_THREADS) {
         cnorm[i] = i < k ? P.comp_norm[i] : T(0);
         ord_s[i] = i < k ? P.order[i] : 0;
     }
+    {
+        const T *Dg = P.Dp + c0;
+        const int nv = ncp / VE;
+        for (int e = tid; e < k * nv; e += BB_THREADS) {
+            const int i = e / nv, cv = (e % nv) * VE;
+            T *dst = Ds + i * ncp + cv;
+            if (p_vec && cv + VE <= nc) {
+                cp_async_16(dst, Dg + (int64_t)i * lds + cv);
+            } else {
+#pragma unroll
+                for (int u = 0; u < VE; ++u) {
+                    if (cv + u < nc) cp_async_elem(dst + u, Dg + (int64_t)i * lds + cv + u);
+                    else dst[u] = T(0);
+                }
+            }
+        }
+    }
+    for (int e = tid; e < BB_M * kp; e += BB_THREADS) Cblk[e] = T(0);       // rows of a short last block stay zero
     for (int e = tid; e < BB_M * ncp; e += BB_THREADS) dlt[e] = T(0);
     for (int e = tid; e < BB_M * BB_NB; e += BB_THREADS) coef[e] = T(0);
+    for (int e = tid; e < BB_M * BB_M; e += BB_THREADS) Cx[e] = T(0);
     if (tid < BB_TILES) {
         int I = 0, rem = tid;
         while (rem >= 8 - I) { rem -= 8 - I; ++I; }
@@ -151,59 +207,49 @@ bcd_blocked_kernel(BcdParams<T> P)
         mbar_init(xbar_addr, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    __syncthreads();
+    __syncthreads();                        // ord_s, zeroed Cblk
+    issue_loads(0);
     // every peer is resident and its mbarrier initialised before anybody sends
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     if (g == 0 && tid == 0) bcd_signal_start(P);
+    cp_async_wait_all();
+    __syncthreads();
     if (stamp) stamp[(int64_t)8 * k + 1] = clock64();
 
-    // operands of block b: C[a_j, :] (transposed) and B_sub[a_j, my columns]; all copies in flight at once
-    auto issue_loads = [&](int b) {
-        const int mb = min(BB_M, k - b * BB_M);
-        for (int e = tid; e < k * BB_M; e += BB_THREADS) {
-            const int j = e / k, i = e % k;
-            if (j < mb) cp_async_elem(Cblk + i * BB_M + j, P.C + (int64_t)ord_s[b * BB_M + j] * k + i);
-            else Cblk[i * BB_M + j] = T(0);
-        }
-        for (int e = tid; e < BB_M * ncp; e += BB_THREADS) {
-            const int j = e / ncp, c = e % ncp;
-            if (j < mb && c < nc) cp_async_elem(Brow + e, P.Bp + (int64_t)ord_s[b * BB_M + j] * lds + c0 + c);
-            else Brow[e] = T(0);
-        }
-        cp_async_commit();
-    };
-
-    // look-ahead product of block b against the shared slice as it is now (warps 1..11): Rraw[j] = C[a_j,:] . D_sub
+    // look-ahead product of the block whose C rows are in Cblk, against the shared slice as it is now (warps 1..11):
+    // Rraw[j] = C[a_j,:] . D_sub.  Thread = (column pair, group of rows), BB_LA atoms per pass, FFMA2.
     auto lookahead = [&]() {
         constexpr int NW = BB_THREADS - 32;
         const int wt = tid - 32;
-        const int NP = ncp >> 1;
         const int IGW = max(1, NW / NP);
         const int pr = wt % NP, ig = wt / NP;
         const int RB = (((k + IGW - 1) / IGW) + 3) & ~3;
-        const int rs = ncp >> 1;
         for (int pass = 0; pass < BB_M / BB_LA; ++pass) {
             if (ig < IGW) {
                 const int r0 = ig * RB, r1 = min(k, r0 + RB);
                 const Pair<T> *dcol = reinterpret_cast<const Pair<T> *>(Ds) + pr;
-                const T *Cb = Cblk + pass * BB_LA;
+                const T *Cb = Cblk + pass * BB_LA * kp;
                 Pair<T> acc[BB_LA];
 #pragma unroll
                 for (int j = 0; j < BB_LA; ++j) acc[j].x = acc[j].y = T(0);
-#pragma unroll 2
-                for (int i = r0; i < r1; ++i) {
-                    const Pair<T> d = dcol[i * rs];
-                    const Quad<T> q0 = *reinterpret_cast<const Quad<T> *>(Cb + i * BB_M);
-                    const Quad<T> q1 = *reinterpret_cast<const Quad<T> *>(Cb + i * BB_M + 4);
-                    pair_fma(q0.x, d, acc[0]); pair_fma(q0.y, d, acc[1]); pair_fma(q0.z, d, acc[2]); pair_fma(q0.w, d, acc[3]);
-                    pair_fma(q1.x, d, acc[4]); pair_fma(q1.y, d, acc[5]); pair_fma(q1.z, d, acc[6]); pair_fma(q1.w, d, acc[7]);
+                int i = r0;
+                for (; i + 4 <= r1; i += 4) {
+                    const Pair<T> d0 = dcol[(i + 0) * NP], d1 = dcol[(i + 1) * NP], d2 = dcol[(i + 2) * NP], d3 = dcol[(i + 3) * NP];
+#pragma unroll
+                    for (int j = 0; j < BB_LA; ++j) {
+                        const Quad<T> cq = *reinterpret_cast<const Quad<T> *>(Cb + j * kp + i);
+                        pair_fma(cq.x, d0, acc[j]); pair_fma(cq.y, d1, acc[j]); pair_fma(cq.z, d2, acc[j]); pair_fma(cq.w, d3, acc[j]);
+                    }
+                }
+                for (; i < r1; ++i) {
+                    const Pair<T> d = dcol[i * NP];
+#pragma unroll
+                    for (int j = 0; j < BB_LA; ++j) pair_fma(Cb[j * kp + i], d, acc[j]);
                 }
 #pragma unroll
-                for (int j = 0; j < BB_LA; ++j) {
-                    red[((size_t)ig * BB_LA + j) * ncp + 2 * pr] = acc[j].x;
-                    red[((size_t)ig * BB_LA + j) * ncp + 2 * pr + 1] = acc[j].y;
-                }
+                for (int j = 0; j < BB_LA; ++j)
+                    *reinterpret_cast<Pair<T> *>(red + ((size_t)ig * BB_LA + j) * ncp + 2 * pr) = acc[j];
             }
             named_sync(BB_BAR_WORKERS, NW);
             for (int e = wt; e < BB_LA * ncp; e += NW) {
@@ -215,41 +261,38 @@ bcd_blocked_kernel(BcdParams<T> P)
         }
     };
 
-    issue_loads(0);
-    cp_async_wait_all();
-    __syncthreads();
     if (wid > 0) lookahead();
     __syncthreads();
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");      // matched by the wait before the first send
     if (stamp) stamp[(int64_t)8 * k + 2] = clock64();
 
-    // new rows and deltas of block pb on my columns, from the coefficients the solver left: thread = (column, 4 atoms)
+    // new rows and deltas of block pb on my columns, from the coefficients the solver left.
+    // item = (column pair, pair of atoms); FFMA2 over the column pair.
     auto apply_block = [&](int pb) {
         const int mbp = min(BB_M, k - pb * BB_M);
-        for (int e = tid; e < 4 * ncp; e += BB_THREADS) {
-            const int q = e / ncp, c = e % ncp;
-            T acc[4] = {T(0), T(0), T(0), T(0)};
+        for (int e = tid; e < (BB_M / 2) * NP; e += BB_THREADS) {
+            const int q = e / NP, pr = e % NP;
+            const Pair<T> *bcol = reinterpret_cast<const Pair<T> *>(basis) + pr;
+            Pair<T> acc0 = {T(0), T(0)}, acc1 = {T(0), T(0)};
 #pragma unroll
             for (int r = 0; r < BB_NB; r += 4) {
-                const T b0 = basis[(r + 0) * ncp + c], b1 = basis[(r + 1) * ncp + c], b2 = basis[(r + 2) * ncp + c],
-                        b3 = basis[(r + 3) * ncp + c];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const Quad<T> cf = *reinterpret_cast<const Quad<T> *>(coef + (4 * q + u) * BB_NB + r);
-                    acc[u] = fma(cf.x, b0, acc[u]); acc[u] = fma(cf.y, b1, acc[u]);
-                    acc[u] = fma(cf.z, b2, acc[u]); acc[u] = fma(cf.w, b3, acc[u]);
-                }
+                const Pair<T> b0 = bcol[(r + 0) * NP], b1 = bcol[(r + 1) * NP], b2 = bcol[(r + 2) * NP], b3 = bcol[(r + 3) * NP];
+                const Quad<T> f0 = *reinterpret_cast<const Quad<T> *>(coef + (2 * q) * BB_NB + r);
+                const Quad<T> f1 = *reinterpret_cast<const Quad<T> *>(coef + (2 * q + 1) * BB_NB + r);
+                pair_fma(f0.x, b0, acc0); pair_fma(f0.y, b1, acc0); pair_fma(f0.z, b2, acc0); pair_fma(f0.w, b3, acc0);
+                pair_fma(f1.x, b0, acc1); pair_fma(f1.y, b1, acc1); pair_fma(f1.z, b2, acc1); pair_fma(f1.w, b3, acc1);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = 4 * q + u;
+            for (int u = 0; u < 2; ++u) {
+                const int j = 2 * q + u;
+                const Pair<T> nv = u ? acc1 : acc0;
+                Pair<T> dv = {T(0), T(0)};
                 if (j < mbp) {
-                    const T dold = basis[(BB_M + j) * ncp + c];
-                    dlt[j * ncp + c] = acc[u] - dold;
-                    Ds[ord_s[pb * BB_M + j] * ncp + c] = acc[u];
-                } else {
-                    dlt[j * ncp + c] = T(0);
+                    const Pair<T> dold = bcol[(BB_M + j) * NP];
+                    dv.x = nv.x - dold.x; dv.y = nv.y - dold.y;
+                    *reinterpret_cast<Pair<T> *>(Ds + ord_s[pb * BB_M + j] * ncp + 2 * pr) = nv;
                 }
+                *reinterpret_cast<Pair<T> *>(dlt + j * ncp + 2 * pr) = dv;
             }
         }
     };
@@ -258,51 +301,58 @@ bcd_blocked_kernel(BcdParams<T> P)
         const int mb = min(BB_M, k - b * BB_M);
         const int par = b & 1;
         BB_STAMP(b, 0);
-        // ---- S0a: diagonal tables of this block; apply the previous block ----
+        // ---- S0a: small tables of this block (its C rows are resident); apply the previous block ----
         if (tid < BB_M) {
-            const T d = (tid < mb) ? Cblk[ord_s[b * BB_M + tid] * BB_M + tid] : T(1);
+            const T d = (tid < mb) ? Cblk[tid * kp + ord_s[b * BB_M + tid]] : T(1);
             caa[tid] = d;
             rcaa[tid] = T(1) / d;
+        }
+        if (b > 0 && tid < BB_M * BB_M) {
+            const int i = tid / BB_M, j = tid % BB_M;
+            Cx[tid] = Cblk[j * kp + ord_s[(b - 1) * BB_M + i]];                 // C[a_j, a_i(prev)]
         }
         if (b > 0) apply_block(b - 1);
         __syncthreads();
         BB_STAMP(b, 1);
         // ---- S0b: repair the look-ahead product with the previous block's deltas; basis of this block ----
-        for (int e = tid; e < 4 * ncp; e += BB_THREADS) {
-            const int q = e / ncp, c = e % ncp;
-            T dot[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) dot[u] = Rraw[(4 * q + u) * ncp + c];
+        for (int e = tid; e < (BB_M / 2) * NP; e += BB_THREADS) {
+            const int q = e / NP, pr = e % NP;
+            Pair<T> dot0 = *reinterpret_cast<const Pair<T> *>(Rraw + (2 * q) * ncp + 2 * pr);
+            Pair<T> dot1 = *reinterpret_cast<const Pair<T> *>(Rraw + (2 * q + 1) * ncp + 2 * pr);
             if (b > 0) {
-#pragma unroll 4
+#pragma unroll
                 for (int i = 0; i < BB_M; ++i) {
-                    const T dv = dlt[i * ncp + c];
-                    const Quad<T> cq = *reinterpret_cast<const Quad<T> *>(Cblk + ord_s[(b - 1) * BB_M + i] * BB_M + 4 * q);   // C[a_j, a_i(prev)]
-                    dot[0] = fma(cq.x, dv, dot[0]); dot[1] = fma(cq.y, dv, dot[1]);
-                    dot[2] = fma(cq.z, dv, dot[2]); dot[3] = fma(cq.w, dv, dot[3]);
+                    const Pair<T> dv = *reinterpret_cast<const Pair<T> *>(dlt + i * ncp + 2 * pr);
+                    const Pair<T> cq = *reinterpret_cast<const Pair<T> *>(Cx + i * BB_M + 2 * q);
+                    pair_fma(cq.x, dv, dot0);
+                    pair_fma(cq.y, dv, dot1);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = 4 * q + u;
-                T gv = T(0), dold = T(0);
+            for (int u = 0; u < 2; ++u) {
+                const int j = 2 * q + u;
+                Pair<T> gv = {T(0), T(0)}, dold = {T(0), T(0)};
                 if (j < mb) {
                     const T ca = caa[j], rc = rcaa[j];
-                    dold = Ds[ord_s[b * BB_M + j] * ncp + c];
-                    const T grad = (Brow[j * ncp + c] - dot[u]) + ca * dold;       // [ref: :679-683]
-                    T qv = grad * rc;
-                    qv = fma(fma(-qv, ca, grad), rc, qv);                         // grad / caa, Newton-corrected
-                    gv = ca > T(1e-20) ? qv : dold;                               // else do not update [ref: :681-683]
+                    const Pair<T> dot = u ? dot1 : dot0;
+                    dold = *reinterpret_cast<const Pair<T> *>(Ds + ord_s[b * BB_M + j] * ncp + 2 * pr);
+                    const Pair<T> bv = *reinterpret_cast<const Pair<T> *>(Brow + j * ncp + 2 * pr);
+                    const T gx = (bv.x - dot.x) + ca * dold.x, gy = (bv.y - dot.y) + ca * dold.y;   // [ref: :679-683]
+                    T qx = gx * rc, qy = gy * rc;
+                    qx = fma(fma(-qx, ca, gx), rc, qx);                            // grad / caa, Newton-corrected
+                    qy = fma(fma(-qy, ca, gy), rc, qy);
+                    const bool upd = ca > T(1e-20);                                // else do not update [ref: :681-683]
+                    gv.x = upd ? qx : dold.x; gv.y = upd ? qy : dold.y;
                 }
-                basis[j * ncp + c] = gv;
-                basis[(BB_M + j) * ncp + c] = dold;
+                *reinterpret_cast<Pair<T> *>(basis + j * ncp + 2 * pr) = gv;
+                *reinterpret_cast<Pair<T> *>(basis + (BB_M + j) * ncp + 2 * pr) = dold;
             }
         }
         if (tid < BB_M * BB_M) {
             const int t = tid / BB_M, j = tid % BB_M;
             T l = T(0);
             if (j < t && t < mb && caa[t] > T(1e-20)) {
-                const T c1 = Cblk[ord_s[b * BB_M + j] * BB_M + t], ca = caa[t], rc = rcaa[t];   // C[a_t, a_j]
+                const T c1 = Cblk[t * kp + ord_s[b * BB_M + j]], ca = caa[t], rc = rcaa[t];   // C[a_t, a_j]
                 l = c1 * rc;
                 l = fma(fma(-l, ca, c1), rc, l);
             }
@@ -311,18 +361,18 @@ bcd_blocked_kernel(BcdParams<T> P)
         __syncthreads();
         BB_STAMP(b, 2);
         if (b + 1 < nbk) issue_loads(b + 1);        // Cblk / Brow of block b are consumed
-        // ---- S1: partial Gram of the 32 basis vectors over my columns ----
+        // ---- S1: partial Gram of the 32 basis vectors over my columns (4x4 register tiles, 8 column parts) ----
         if (wid < BB_TILES / 4) {
             const int ti = 4 * wid + (lane >> 3), part = lane & 7;
             const int I = tile_i[ti], J = tile_j[ti];
             const Quad<T> *ri = reinterpret_cast<const Quad<T> *>(basis + (4 * I) * ncp);
             const Quad<T> *rj = reinterpret_cast<const Quad<T> *>(basis + (4 * J) * ncp);
             const int nq = ncp >> 2;                                            // float4 groups per row
-            T acc[4][4];
+            Pair<T> acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int bb = 0; bb < 4; ++bb) acc[a][bb] = T(0);
+                for (int bb = 0; bb < 4; ++bb) acc[a][bb].x = acc[a][bb].y = T(0);
             for (int f = part; f < nq; f += 8) {
                 Quad<T> x[4], y[4];
 #pragma unroll
@@ -331,28 +381,27 @@ bcd_blocked_kernel(BcdParams<T> P)
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
                     for (int bb = 0; bb < 4; ++bb) {
-                        acc[a][bb] = fma(x[a].x, y[bb].x, acc[a][bb]);
-                        acc[a][bb] = fma(x[a].y, y[bb].y, acc[a][bb]);
-                        acc[a][bb] = fma(x[a].z, y[bb].z, acc[a][bb]);
-                        acc[a][bb] = fma(x[a].w, y[bb].w, acc[a][bb]);
+                        pair_mul_fma(Pair<T>{x[a].x, x[a].y}, Pair<T>{y[bb].x, y[bb].y}, acc[a][bb]);
+                        pair_mul_fma(Pair<T>{x[a].z, x[a].w}, Pair<T>{y[bb].z, y[bb].w}, acc[a][bb]);
                     }
             }
+            T out[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int bb = 0; bb < 4; ++bb) {
-                    T v = acc[a][bb];
+                    T v = acc[a][bb].x + acc[a][bb].y;
                     v += __shfl_xor_sync(kFullMask, v, 1);
                     v += __shfl_xor_sync(kFullMask, v, 2);
                     v += __shfl_xor_sync(kFullMask, v, 4);
-                    acc[a][bb] = v;
+                    out[a][bb] = v;
                 }
             if (part == 0) {
                 T *dst = stage + par * BB_GRAM + ti * 16;
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
                     Quad<T> o;
-                    o.x = acc[a][0]; o.y = acc[a][1]; o.z = acc[a][2]; o.w = acc[a][3];
+                    o.x = out[a][0]; o.y = out[a][1]; o.z = out[a][2]; o.w = out[a][3];
                     *reinterpret_cast<Quad<T> *>(dst + 4 * a) = o;
                 }
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // visible to the bulk copies below
@@ -362,6 +411,7 @@ bcd_blocked_kernel(BcdParams<T> P)
         BB_STAMP(b, 3);
         // every peer has consumed the previous exchange (and finished the scratch use of its receive area)
         asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        BB_STAMP(b, 4);
         // ---- S2: all-to-all of the partial Grams ----
         if (tid == 0) mbar_expect_tx(xbar_addr, (unsigned)nblk * kGramBytes);
         if (tid < nblk) {
@@ -372,7 +422,7 @@ bcd_blocked_kernel(BcdParams<T> P)
                          ::"r"(dst), "r"(src), "r"(kGramBytes), "r"(bar) : "memory");
         }
         mbar_wait(xbar_addr, (unsigned)par);
-        BB_STAMP(b, 4);
+        BB_STAMP(b, 5);
         // ---- S3: G = sum of the partials, in CTA order ----
         for (int v = tid; v < BB_GRAM; v += BB_THREADS) {
             T part[BCD_MAX_CLUSTER];
@@ -388,7 +438,7 @@ bcd_blocked_kernel(BcdParams<T> P)
         }
         cp_async_wait_all();
         __syncthreads();
-        BB_STAMP(b, 5);
+        BB_STAMP(b, 6);
         // ---- S4: warp 0 solves the block's scalars; the other warps run the look-ahead product of the next block ----
         if (wid == 0) {
             T Mrow[BB_NB];
@@ -429,17 +479,20 @@ bcd_blocked_kernel(BcdParams<T> P)
                     dl[t] = zz[t] = T(0);
                 }
             }
+            BB_STAMP(b, 7);
         } else if (b + 1 < nbk) {
+            if (wstamp) wstamp[2 * b] = clock64();
             lookahead();
+            if (wstamp) wstamp[2 * b + 1] = clock64();
         }
         __syncthreads();
-        BB_STAMP(b, 6);
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     }
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     if (stamp) stamp[(int64_t)8 * k + 3] = clock64();
     apply_block(nbk - 1);
     __syncthreads();
+    if (stamp) stamp[(int64_t)8 * k + 4] = clock64();
 
     // ---- epilogue: norms of the new atoms, write-back (as in bcd_pilot_kernel) ----
     T *napart = P.part;                                        // [nblk][k]
@@ -449,9 +502,8 @@ bcd_blocked_kernel(BcdParams<T> P)
         acc = warp_sum(acc);
         if (lane == 0) napart[(int64_t)g * k + i] = acc;
     }
-    if (vec_ok) {
+    if (p_vec) {
         const int nv = ncp / VE;
-#pragma unroll 4
         for (int e = tid; e < k * nv; e += BB_THREADS) {
             const int i = e / nv, cv = (e % nv) * VE;
             if (cv + VE <= nc) {
@@ -467,9 +519,11 @@ bcd_blocked_kernel(BcdParams<T> P)
             if (c < nc) P.Dp[(int64_t)i * lds + c0 + c] = Ds[e];
         }
     }
+    if (stamp) stamp[(int64_t)8 * k + 5] = clock64();
     __threadfence();
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    if (stamp) stamp[(int64_t)8 * k + 6] = clock64();
     if (g == 0) {
         for (int i = tid; i < k; i += BB_THREADS) {
             T part[BCD_MAX_CLUSTER];
@@ -481,7 +535,7 @@ bcd_blocked_kernel(BcdParams<T> P)
             P.comp_norm[i] = rad[i] - na;                                                // [ref: :690-692]
         }
     }
-    if (stamp) stamp[(int64_t)8 * k + 4] = clock64();
+    if (stamp) stamp[(int64_t)8 * k + 7] = clock64();
 #undef BB_STAMP
 }
 

@@ -423,7 +423,7 @@ class DictFact(CodingMixin, BaseEstimator):
         io.wait_host = wait_host
         # stream ordering against the caller (modl_fit_batches.fence): state written since the last call -> wait;
         # device rows declared final (`device_rows_final = True`) -> do not; otherwise automatic
-        if self.__dict__.pop("_state_dirty", True):
+        if self.__dict__.pop("_state_dirty", False):
             io.fence = 1
         elif Xt.is_cuda and self.__dict__.get("device_rows_final", False):
             io.fence = 2

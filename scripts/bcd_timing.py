@@ -30,24 +30,30 @@ for name, blocked, pipe in (("blocked", 1, 1), ("pipelined pilot", 0, 1), ("pilo
     for i in range(3):
         est.partial_fit(Xd[i * B:(i + 1) * B], np.arange(i * B, (i + 1) * B))
     torch.cuda.synchronize()
-    st = (C.c_longlong * (8 * K + 16))()
-    L.modl_debug_bcd_stamps(ctx.handle, st, 8 * K + 16)
-    g = [st[8 * K + i] for i in range(5)]
+    NST = 8 * K + 16 + 2 * ((K + 7) // 8) + 8
+    st = (C.c_longlong * NST)()
+    L.modl_debug_bcd_stamps(ctx.handle, st, NST)
+    g = [st[8 * K + i] for i in range(8)]
     if blocked:
         nbk = (K + 15) // 16
-        ph = np.array([[st[8 * b + i] for i in range(7)] for b in range(nbk)], dtype=np.int64)
-        d = np.diff(ph, axis=1)[1:]            # blocks 1.. (block 0 has no previous block to apply)
-        names = ["S0a apply", "S0b repair+basis", "S1 gram", "cluster wait", "S2 exchange", "S3 sum", "S4 solve | look-ahead"]
-        print(name, "| kernel %d cycles: prologue %d (load %d, first product %d), blocks %d, epilogue %d"
-              % (g[4] - g[0], g[2] - g[0], g[1] - g[0], g[2] - g[1], g[3] - g[2], g[4] - g[3]))
-        per_block = (ph[-1, 6] - ph[1, 0]) / (nbk - 1)
+        ph = np.array([[st[8 * b + i] for i in range(8)] for b in range(nbk)], dtype=np.int64)
+        nxt = np.concatenate([ph[1:, 0], [g[3]]])              # start of the next block = end of S4 (after its barrier)
+        iv = np.column_stack([np.diff(ph[:, :8], axis=1), nxt - ph[:, 6]])[1:-1]     # blocks 1 .. nbk-2
+        names = ["S0a tables+apply", "S0b repair+basis", "S1 loads+gram", "cluster wait", "S2 exchange", "S3 sum",
+                 "S4 solver alone", "S4 whole (solver | look-ahead)"]
+        la = np.array([st[8 * K + 16 + 2 * b + 1] - st[8 * K + 16 + 2 * b] for b in range(1, nbk - 1)])
+        print(name, "| kernel %d cycles: loads %d, first product %d, blocks %d, last apply %d, norms+write-back %d, "
+              "fence+cluster barrier %d, comp_norm %d" % (g[7] - g[0], g[1] - g[0], g[2] - g[1], g[3] - g[2], g[4] - g[3],
+                                                          g[5] - g[4], g[6] - g[5], g[7] - g[6]))
+        per_block = (ph[-1, 0] - ph[1, 0]) / (nbk - 2)
         print("   cycles per block of 16: %.0f  (%.0f per atom)" % (per_block, per_block / 16))
-        print("   phases (mean over blocks 1..):", {n: int(round(v)) for n, v in zip(names[:6] + [names[6]], list(d.mean(axis=0)))})
+        print("   phases (mean over blocks 1..%d):" % (nbk - 2), {n: int(round(v)) for n, v in zip(names, list(iv.mean(axis=0)))},
+              "look-ahead (warp 1) %d" % la.mean())
     else:
         t0 = [st[8 * t] for t in range(K)]
         per = (t0[K - 1] - t0[8]) / (K - 9)
         print(name, "| cycles per atom (atoms 8..%d): %.0f" % (K - 1, per),
-              " kernel prologue %d, loop %d cycles" % (g[1] - g[0], g[2] - g[1]))
+              " kernel prologue %d, loop %d, epilogue %d cycles" % (g[1] - g[0], g[2] - g[1], g[4] - g[2]))
         if not pipe:
             gaps = (C.c_double * 7)()
             L.modl_debug_bcd_timing(ctx.handle, gaps)
