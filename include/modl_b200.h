@@ -307,6 +307,10 @@ typedef struct modl_step_params {
     int sm_avail;
     void *start_flag;
     uint32_t start_serial;
+    /* 1: h_subset / h_order sit in PINNED (mapped) host memory that stays untouched until the step has run; the
+     * device then fetches them with a small kernel that reads the host memory directly instead of two host->device
+     * copies -- copies would queue on the copy engine behind a 20 MB batch upload in flight (0.4 ms). */
+    int h_inputs_mapped;
 } modl_step_params;
 
 /* MODL_PHASE_STATS_SUB (same call as MODL_PHASE_CODE) computes ONLY what the dictionary update waits

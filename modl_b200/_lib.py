@@ -30,7 +30,7 @@ class StepParams(C.Structure):
         ("optimizer_sgd", ci),
         ("sweeps", vp),
         ("phases", ci), ("global_batch", i64), ("stats_inc", vp), ("inc_sub", vp), ("ev_after_apply_sub", vp),
-        ("slot", ci), ("sm_avail", ci), ("start_flag", vp), ("start_serial", C.c_uint32),
+        ("slot", ci), ("sm_avail", ci), ("start_flag", vp), ("start_serial", C.c_uint32), ("h_inputs_mapped", ci),
     ]
 
 class FitParams(C.Structure):

@@ -242,6 +242,17 @@ static int regression(modl_ctx *ctx, const T *G, int64_t g_stride, T *Dx, const 
                         alpha * (T(1) - l1_ratio), tol, max_iter, positive, sweeps, st);
 }
 
+// The small per-step inputs straight out of pinned (mapped) host memory: feature subset (int64) and atom order
+// (int64 -> int32).  One launch, no copy-engine traffic.
+__global__ void __launch_bounds__(256)
+fetch_step_inputs_kernel(const int64_t *__restrict__ h_subset, int64_t *__restrict__ d_subset, int s,
+                         const int64_t *__restrict__ h_order, int32_t *__restrict__ d_order, int k)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, n = gridDim.x * blockDim.x;
+    for (int i = t; i < s; i += n) d_subset[i] = h_subset[i];
+    for (int i = t; i < k; i += n) d_order[i] = (int32_t)h_order[i];
+}
+
 // upload the atom order as int32 (two buffers: the step in flight and the one being prefetched)
 static int upload_order(modl_ctx *ctx, const int64_t *h_order, int64_t k, int32_t **d_order, cudaStream_t st, int slot = 0,
                         bool ready = false)
@@ -661,7 +672,8 @@ int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream)
     // subset -> device
     int64_t *d_subset = nullptr;
     MODL_TRY(ws<int64_t>(ctx, slot ? WS_SUBSET2 : WS_SUBSET, (size_t)(s > 0 ? s : 1), &d_subset));
-    if (s > 0 && !reuse_subset)
+    const bool fetch_mapped = q->h_inputs_mapped != 0 && phases == MODL_PHASE_PREFETCH;
+    if (s > 0 && !reuse_subset && !fetch_mapped)
         MODL_CUDA_TRY(cudaMemcpyAsync(d_subset, q->h_subset, sizeof(int64_t) * (size_t)s, cudaMemcpyHostToDevice, st));
 
     T *xnorm2 = nullptr, *Gw = nullptr, *Dxw = nullptr, *cb = nullptr, *panel = nullptr;
@@ -677,7 +689,17 @@ int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream)
         // B_[:, subset] panel the fused statistics product accumulates into.  Runs on another stream while
         // the previous step's dictionary update holds its 16 SMs.
         int32_t *d_order = nullptr;
-        MODL_TRY(upload_order(ctx, q->h_order, k, &d_order, st, slot));
+        if (fetch_mapped) {
+            for (int64_t i = 0; i < k; ++i)
+                MODL_REQUIRE(q->h_order[i] >= 0 && q->h_order[i] < k, "order is not a permutation of range(k)");
+            MODL_TRY(ws<int32_t>(ctx, slot ? WS_ORDER2 : WS_ORDER, (size_t)k, &d_order));
+            const int64_t n = s > k ? s : k;
+            fetch_step_inputs_kernel<<<(unsigned)(n < 2048 ? 1 : (n + 2047) / 2048), 256, 0, st>>>(q->h_subset, d_subset, (int)s,
+                                                                                                    q->h_order, d_order, (int)k);
+            MODL_LAUNCH_CHECK(ctx);
+        } else {
+            MODL_TRY(upload_order(ctx, q->h_order, k, &d_order, st, slot));
+        }
         if (x_ahead) {
             MODL_TRY(gram_dx_impl<T>(ctx, D, p, X, q->ldx, d_subset, s, k, b, p, r, g_sub ? Gw : (T *)nullptr, Dxw, xnorm2, &panel, st, 1));
             if constexpr (std::is_same<T, float>::value) {

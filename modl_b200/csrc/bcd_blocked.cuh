@@ -38,10 +38,12 @@ constexpr int BB_M = 16;                 // atoms per block
 constexpr int BB_NB = 2 * BB_M;          // basis vectors per block (= warp size)
 constexpr int BB_THREADS = 384;
 constexpr int BB_TILES = 36;             // 4x4 tiles of the upper triangle of the 32x32 Gram (8x8 tile grid)
-constexpr int BB_GRAM = BB_TILES * 16;   // values each CTA contributes per block
-constexpr int BB_LA = 8;                 // atoms per pass of the look-ahead product
+constexpr int BB_GRAM = BB_TILES * 16;   // entries of the (tile-packed) Gram
 constexpr int BB_MLD = BB_NB + 1;        // row pitch of the Gram matrix in shared memory
+constexpr int BB_RS_SLOTS = 52;          // (owned tile, sender) slots of the reduce-scatter: ceil(36 / n) * n <= 51 for n <= 16
+constexpr int BB_RED_CAP = 9216;         // scratch of the look-ahead product (elements)
 enum { BB_BAR_WORKERS = 1 };
+constexpr int BB_SOLVER = BB_THREADS / 32 - 1;   // the solver warp: the HIGHEST warp id (the issue arbiter favours high ids)
 
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src)
 {
@@ -58,6 +60,20 @@ __device__ __forceinline__ void pair_mul_fma(const Pair<double> &a, const Pair<d
 {
     acc.x = fma(a.x, b.x, acc.x); acc.y = fma(a.y, b.y, acc.y);
 }
+// four values into a peer's shared memory, completing their bytes on the PEER's mbarrier (one-way, no fences)
+__device__ __forceinline__ void st_async_quad(unsigned remote, unsigned remote_mbar, float a, float b, float c, float d)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n"
+                 ::"r"(remote), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)),
+                   "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_quad(unsigned remote, unsigned remote_mbar, double a, double b, double c, double d)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];\n"
+                 ::"r"(remote), "l"(__double_as_longlong(a)), "l"(__double_as_longlong(b)), "r"(remote_mbar) : "memory");
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];\n"
+                 ::"r"(remote + 16u), "l"(__double_as_longlong(c)), "l"(__double_as_longlong(d)), "r"(remote_mbar) : "memory");
+}
 
 // shared-memory footprint in bytes -- must match the carve-up in the kernel
 template <typename T>
@@ -70,22 +86,18 @@ __host__ __device__ inline size_t bcd_blocked_smem_bytes(int64_t k, int64_t ncp)
                           + BB_NB * ncp           // basis
                           + BB_M * ncp            // dlt
                           + BB_M * BB_NB          // coef
-                          + 2 * BB_M * BB_M       // Lblk, Cx
+                          + 2 * BB_M * BB_M       // LT, Cx
                           + BB_NB * BB_MLD + 32   // Mfull (padded to a multiple of 4)
-                          + 2 * kp                // cnorm, rad
+                          + kp                    // cnorm
                           + 2 * BB_M              // caa, rcaa
-                          + 2 * BB_GRAM           // stage (two blocks)
-                          + BCD_MAX_CLUSTER * BB_GRAM;   // recv (also: scratch of the look-ahead product)
+                          + BB_GRAM               // Mflat
+                          + 2 * BB_RS_SLOTS * 16  // rsrecv (by block parity)
+                          + BB_RED_CAP;           // red
     return (size_t)elems * sizeof(T) + (size_t)kp * sizeof(int) + 64;
 }
 
-// largest scratch the look-ahead product needs (elements), must fit the recv area
-__host__ __device__ inline int64_t bcd_blocked_red_elems(int64_t ncp)
-{
-    const int64_t np = ncp / 2;
-    const int64_t igw = (BB_THREADS - 32) / np > 0 ? (BB_THREADS - 32) / np : 1;
-    return igw * BB_LA * ncp;
-}
+// the look-ahead product needs at least one row group of 16 x ncp partial sums in its scratch
+__host__ __device__ inline bool bcd_blocked_fits(int64_t ncp) { return BB_M * ncp <= BB_RED_CAP; }
 
 template <typename T>
 __global__ void __launch_bounds__(BB_THREADS, 1)
@@ -111,26 +123,27 @@ bcd_blocked_kernel(BcdParams<T> P)
     T *basis = Brow + BB_M * ncp;                            // [2M][ncp]  g_1..g_M, d_1..d_M
     T *dlt = basis + BB_NB * ncp;                            // [M][ncp]   deltas of the block just applied
     T *coef = dlt + BB_M * ncp;                              // [M][2M]    n_t = sum_r coef[t][r] basis_r
-    T *Lblk = coef + BB_M * BB_NB;                           // [M][M]     L_tj (j < t), zero elsewhere
-    T *Cx = Lblk + BB_M * BB_M;                              // [M][M]     C[a_j, a_i(previous block)] at [i*M + j]
+    T *LT = coef + BB_M * BB_NB;                             // [M][M]     L_tj at [j*M + t] (j < t), zero elsewhere
+    T *Cx = LT + BB_M * BB_M;                                // [M][M]     C[a_j, a_i(previous block)] at [i*M + j]
     T *Mfull = Cx + BB_M * BB_M;                             // [2M][2M+1] Gram matrix of the basis
     T *cnorm = Mfull + BB_NB * BB_MLD + 32;                  // [kp]       comp_norm_ on entry
-    T *rad = cnorm + kp;                                     // [kp]       radius used for every atom
-    T *caa = rad + kp;                                       // [M]        C[a_t, a_t]
+    T *caa = cnorm + kp;                                     // [M]        C[a_t, a_t]
     T *rcaa = caa + BB_M;                                    // [M]        1 / C[a_t, a_t]
-    T *stage = rcaa + BB_M;                                  // [2][GRAM]  this CTA's partial Gram, by block parity
-    T *recv = stage + 2 * BB_GRAM;                           // [16][GRAM] partial Grams of every CTA
-    T *red = recv;                                           //            scratch of the look-ahead product (S4 only)
-    int *ord_s = reinterpret_cast<int *>(recv + BCD_MAX_CLUSTER * BB_GRAM);   // [kp] update order
-    __shared__ __align__(8) unsigned long long xbar;
+    T *Mflat = rcaa + BB_M;                                  // [36][16]   the summed Gram, tile-packed (all-gather target)
+    T *rsrecv = Mflat + BB_GRAM;                             // [2][slot][sender][16] partial tiles this CTA sums (reduce-scatter target, by block parity)
+    T *red = rsrecv + 2 * BB_RS_SLOTS * 16;                  // scratch of the look-ahead product
+    int *ord_s = reinterpret_cast<int *>(red + BB_RED_CAP);  // [kp] update order
+    __shared__ __align__(8) unsigned long long xbar[2];      // [0] reduce-scatter arrivals, [1] all-gather arrivals
     __shared__ unsigned char tile_i[BB_TILES], tile_j[BB_TILES];
-    const unsigned xbar_addr = (unsigned)__cvta_generic_to_shared(&xbar);
-    constexpr unsigned kGramBytes = BB_GRAM * sizeof(T);
+    const unsigned bar1 = (unsigned)__cvta_generic_to_shared(&xbar[0]);
+    const unsigned bar2 = bar1 + 8;
+    const int n_owned = (BB_TILES - g + nblk - 1) / nblk;    // tiles ti with ti % nblk == g  (g < nblk <= 16 < 36)
 
-    // debug stamps of CTA 0: thread 0 (solver warp) [b][8] phase starts, thread 32 (first product warp) look-ahead
+    // debug stamps of CTA 0: thread 0 [b][0..6] phase starts and the look-ahead, lane 0 of the solver warp [b][7] = solver done;
     // start / end per block at 8k + 16 + 2b, kernel-level stamps at 8k .. 8k + 7
     long long *stamp = (P.timing && g == 0 && tid == 0) ? P.timing : nullptr;
-    long long *wstamp = (P.timing && g == 0 && tid == 32) ? P.timing + (int64_t)8 * k + 16 : nullptr;
+    long long *wstamp = (P.timing && g == 0 && tid == 0) ? P.timing + (int64_t)8 * k + 16 : nullptr;
+    long long *sstamp = (P.timing && g == 0 && tid == 32 * BB_SOLVER) ? P.timing : nullptr;
 #define BB_STAMP(b_, slot_) do { if (stamp) stamp[(int64_t)(b_) * 8 + (slot_)] = clock64(); } while (0)
     if (stamp) stamp[(int64_t)8 * k] = clock64();
 
@@ -204,12 +217,13 @@ bcd_blocked_kernel(BcdParams<T> P)
         tile_j[tid] = (unsigned char)(I + rem);
     }
     if (tid == 0) {
-        mbar_init(xbar_addr, 1);
+        mbar_init(bar1, 1);
+        mbar_init(bar2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();                        // ord_s, zeroed Cblk
     issue_loads(0);
-    // every peer is resident and its mbarrier initialised before anybody sends
+    // every peer is resident and its mbarriers initialised before anybody sends
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     if (g == 0 && tid == 0) bcd_signal_start(P);
@@ -217,151 +231,228 @@ bcd_blocked_kernel(BcdParams<T> P)
     __syncthreads();
     if (stamp) stamp[(int64_t)8 * k + 1] = clock64();
 
-    // look-ahead product of the block whose C rows are in Cblk, against the shared slice as it is now (warps 1..11):
-    // Rraw[j] = C[a_j,:] . D_sub.  Thread = (column pair, group of rows), BB_LA atoms per pass, FFMA2.
+    // look-ahead product of the block whose C rows are in Cblk, against the shared slice as it is now (warps 0..10;
+    // warp 11 is the solver): Rraw[j] = C[a_j,:] . D_sub.  The shared-memory port bounds this loop (a broadcast load
+    // costs one port cycle per 4 bytes), so a thread owns FOUR columns x all 16 atoms x a group of rows: per 4 rows
+    // 4 + 16 128-bit loads feed 128 FFMA2.  Row groups are combined through a scratch that holds half of them: the
+    // first half stores, the second half adds in place, then the halves' sums are added in group order (fixed order).
     auto lookahead = [&]() {
         constexpr int NW = BB_THREADS - 32;
-        const int wt = tid - 32;
-        const int IGW = max(1, NW / NP);
-        const int pr = wt % NP, ig = wt / NP;
-        const int RB = (((k + IGW - 1) / IGW) + 3) & ~3;
-        for (int pass = 0; pass < BB_M / BB_LA; ++pass) {
+        if constexpr (sizeof(T) == 8) {
+            // double: two columns per thread (the four-column tile would not fit the register file), one round
+            const int IGW = max(1, min(NW / NP, BB_RED_CAP / (BB_M * ncp)));
+            const int pr = tid % NP, ig = tid / NP;
+            const int RB = (((k + IGW - 1) / IGW) + 3) & ~3;
             if (ig < IGW) {
-                const int r0 = ig * RB, r1 = min(k, r0 + RB);
+                const int r0 = min(k, ig * RB), r1 = min(k, r0 + RB);
                 const Pair<T> *dcol = reinterpret_cast<const Pair<T> *>(Ds) + pr;
-                const T *Cb = Cblk + pass * BB_LA * kp;
-                Pair<T> acc[BB_LA];
+                Pair<T> acc[BB_M];
 #pragma unroll
-                for (int j = 0; j < BB_LA; ++j) acc[j].x = acc[j].y = T(0);
-                int i = r0;
-                for (; i + 4 <= r1; i += 4) {
-                    const Pair<T> d0 = dcol[(i + 0) * NP], d1 = dcol[(i + 1) * NP], d2 = dcol[(i + 2) * NP], d3 = dcol[(i + 3) * NP];
-#pragma unroll
-                    for (int j = 0; j < BB_LA; ++j) {
-                        const Quad<T> cq = *reinterpret_cast<const Quad<T> *>(Cb + j * kp + i);
-                        pair_fma(cq.x, d0, acc[j]); pair_fma(cq.y, d1, acc[j]); pair_fma(cq.z, d2, acc[j]); pair_fma(cq.w, d3, acc[j]);
-                    }
-                }
-                for (; i < r1; ++i) {
+                for (int j = 0; j < BB_M; ++j) acc[j].x = acc[j].y = T(0);
+                for (int i = r0; i < r1; ++i) {
                     const Pair<T> d = dcol[i * NP];
 #pragma unroll
-                    for (int j = 0; j < BB_LA; ++j) pair_fma(Cb[j * kp + i], d, acc[j]);
+                    for (int j = 0; j < BB_M; ++j) pair_fma(Cblk[j * kp + i], d, acc[j]);
                 }
 #pragma unroll
-                for (int j = 0; j < BB_LA; ++j)
-                    *reinterpret_cast<Pair<T> *>(red + ((size_t)ig * BB_LA + j) * ncp + 2 * pr) = acc[j];
+                for (int j = 0; j < BB_M; ++j)
+                    *reinterpret_cast<Pair<T> *>(red + ((size_t)ig * BB_M + j) * ncp + 2 * pr) = acc[j];
             }
             named_sync(BB_BAR_WORKERS, NW);
-            for (int e = wt; e < BB_LA * ncp; e += NW) {
+            for (int e = tid; e < BB_M * ncp; e += NW) {
                 T sum = T(0);
-                for (int gi = 0; gi < IGW; ++gi) sum += red[(size_t)gi * BB_LA * ncp + e];   // fixed order
-                Rraw[pass * BB_LA * ncp + e] = sum;
+                for (int gi = 0; gi < IGW; ++gi) sum += red[(size_t)gi * BB_M * ncp + e];   // fixed order
+                Rraw[e] = sum;
             }
-            named_sync(BB_BAR_WORKERS, NW);
+            return;
+        }
+        const int NQ = ncp >> 2;
+        const int half = max(1, BB_RED_CAP / (BB_M * ncp));
+        const int IGW = max(1, min(NW / NQ, 2 * half));
+        const int cq = tid % NQ, ig = tid / NQ;
+        const int RB = (((k + IGW - 1) / IGW) + 3) & ~3;
+        Pair<T> acc[BB_M][2];
+        const bool on = ig < IGW;
+        if (on) {
+            const int r0 = min(k, ig * RB), r1 = min(k, r0 + RB);
+            const Quad<T> *dcol = reinterpret_cast<const Quad<T> *>(Ds) + cq;
+#pragma unroll
+            for (int j = 0; j < BB_M; ++j) acc[j][0].x = acc[j][0].y = acc[j][1].x = acc[j][1].y = T(0);
+            int i = r0;
+            for (; i + 4 <= r1; i += 4) {
+                const Quad<T> d0 = dcol[(i + 0) * NQ], d1 = dcol[(i + 1) * NQ], d2 = dcol[(i + 2) * NQ], d3 = dcol[(i + 3) * NQ];
+#pragma unroll
+                for (int h = 0; h < BB_M; h += 8) {
+                    Quad<T> c4[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) c4[j] = *reinterpret_cast<const Quad<T> *>(Cblk + (h + j) * kp + i);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        pair_fma(c4[j].x, Pair<T>{d0.x, d0.y}, acc[h + j][0]); pair_fma(c4[j].x, Pair<T>{d0.z, d0.w}, acc[h + j][1]);
+                        pair_fma(c4[j].y, Pair<T>{d1.x, d1.y}, acc[h + j][0]); pair_fma(c4[j].y, Pair<T>{d1.z, d1.w}, acc[h + j][1]);
+                        pair_fma(c4[j].z, Pair<T>{d2.x, d2.y}, acc[h + j][0]); pair_fma(c4[j].z, Pair<T>{d2.z, d2.w}, acc[h + j][1]);
+                        pair_fma(c4[j].w, Pair<T>{d3.x, d3.y}, acc[h + j][0]); pair_fma(c4[j].w, Pair<T>{d3.z, d3.w}, acc[h + j][1]);
+                    }
+                }
+            }
+            for (; i < r1; ++i) {
+                const Quad<T> d = dcol[i * NQ];
+#pragma unroll
+                for (int j = 0; j < BB_M; ++j) {
+                    const T c = Cblk[j * kp + i];
+                    pair_fma(c, Pair<T>{d.x, d.y}, acc[j][0]); pair_fma(c, Pair<T>{d.z, d.w}, acc[j][1]);
+                }
+            }
+            if (ig < half) {
+#pragma unroll
+                for (int j = 0; j < BB_M; ++j) {
+                    Quad<T> o; o.x = acc[j][0].x; o.y = acc[j][0].y; o.z = acc[j][1].x; o.w = acc[j][1].y;
+                    *reinterpret_cast<Quad<T> *>(red + ((size_t)ig * BB_M + j) * ncp + 4 * cq) = o;
+                }
+            }
+        }
+        named_sync(BB_BAR_WORKERS, NW);
+        if (on && ig >= half) {
+#pragma unroll
+            for (int j = 0; j < BB_M; ++j) {
+                Quad<T> *slot = reinterpret_cast<Quad<T> *>(red + ((size_t)(ig - half) * BB_M + j) * ncp + 4 * cq);
+                Quad<T> o = *slot;
+                o.x += acc[j][0].x; o.y += acc[j][0].y; o.z += acc[j][1].x; o.w += acc[j][1].y;
+                *slot = o;
+            }
+        }
+        named_sync(BB_BAR_WORKERS, NW);
+        const int nsum = min(IGW, half);
+        for (int e = tid; e < BB_M * ncp; e += NW) {
+            T sum = T(0);
+            for (int gi = 0; gi < nsum; ++gi) sum += red[(size_t)gi * BB_M * ncp + e];   // fixed order
+            Rraw[e] = sum;
         }
     };
 
-    if (wid > 0) lookahead();
+    if (wid != BB_SOLVER) lookahead();
     __syncthreads();
-    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");      // matched by the wait before the first send
     if (stamp) stamp[(int64_t)8 * k + 2] = clock64();
 
-    // new rows and deltas of block pb on my columns, from the coefficients the solver left.
-    // item = (column pair, pair of atoms); FFMA2 over the column pair.
+    // new rows and deltas of block pb on my columns, from the coefficients the solver left:  n_j = sum_r coef[j][r] basis_r.
+    // item = (4 columns, 4 atoms): 8 128-bit loads feed 32 FFMA2 (the shared-memory port bounds this phase too).
     auto apply_block = [&](int pb) {
         const int mbp = min(BB_M, k - pb * BB_M);
-        for (int e = tid; e < (BB_M / 2) * NP; e += BB_THREADS) {
-            const int q = e / NP, pr = e % NP;
-            const Pair<T> *bcol = reinterpret_cast<const Pair<T> *>(basis) + pr;
-            Pair<T> acc0 = {T(0), T(0)}, acc1 = {T(0), T(0)};
+        const int NQ = ncp >> 2;
+        for (int e = tid; e < 4 * NQ; e += BB_THREADS) {
+            const int aq = e / NQ, cq = e % NQ;
+            const Quad<T> *bcol = reinterpret_cast<const Quad<T> *>(basis) + cq;
+            Pair<T> acc[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u][0].x = acc[u][0].y = acc[u][1].x = acc[u][1].y = T(0);
 #pragma unroll
             for (int r = 0; r < BB_NB; r += 4) {
-                const Pair<T> b0 = bcol[(r + 0) * NP], b1 = bcol[(r + 1) * NP], b2 = bcol[(r + 2) * NP], b3 = bcol[(r + 3) * NP];
-                const Quad<T> f0 = *reinterpret_cast<const Quad<T> *>(coef + (2 * q) * BB_NB + r);
-                const Quad<T> f1 = *reinterpret_cast<const Quad<T> *>(coef + (2 * q + 1) * BB_NB + r);
-                pair_fma(f0.x, b0, acc0); pair_fma(f0.y, b1, acc0); pair_fma(f0.z, b2, acc0); pair_fma(f0.w, b3, acc0);
-                pair_fma(f1.x, b0, acc1); pair_fma(f1.y, b1, acc1); pair_fma(f1.z, b2, acc1); pair_fma(f1.w, b3, acc1);
+                const Quad<T> b0 = bcol[(r + 0) * NQ], b1 = bcol[(r + 1) * NQ], b2 = bcol[(r + 2) * NQ], b3 = bcol[(r + 3) * NQ];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const Quad<T> f = *reinterpret_cast<const Quad<T> *>(coef + (4 * aq + u) * BB_NB + r);
+                    pair_fma(f.x, Pair<T>{b0.x, b0.y}, acc[u][0]); pair_fma(f.x, Pair<T>{b0.z, b0.w}, acc[u][1]);
+                    pair_fma(f.y, Pair<T>{b1.x, b1.y}, acc[u][0]); pair_fma(f.y, Pair<T>{b1.z, b1.w}, acc[u][1]);
+                    pair_fma(f.z, Pair<T>{b2.x, b2.y}, acc[u][0]); pair_fma(f.z, Pair<T>{b2.z, b2.w}, acc[u][1]);
+                    pair_fma(f.w, Pair<T>{b3.x, b3.y}, acc[u][0]); pair_fma(f.w, Pair<T>{b3.z, b3.w}, acc[u][1]);
+                }
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int j = 2 * q + u;
-                const Pair<T> nv = u ? acc1 : acc0;
-                Pair<T> dv = {T(0), T(0)};
+            for (int u = 0; u < 4; ++u) {
+                const int j = 4 * aq + u;
+                Quad<T> nv; nv.x = acc[u][0].x; nv.y = acc[u][0].y; nv.z = acc[u][1].x; nv.w = acc[u][1].y;
+                Quad<T> dv; dv.x = dv.y = dv.z = dv.w = T(0);
                 if (j < mbp) {
-                    const Pair<T> dold = bcol[(BB_M + j) * NP];
-                    dv.x = nv.x - dold.x; dv.y = nv.y - dold.y;
-                    *reinterpret_cast<Pair<T> *>(Ds + ord_s[pb * BB_M + j] * ncp + 2 * pr) = nv;
+                    const Quad<T> dold = bcol[(BB_M + j) * NQ];
+                    dv.x = nv.x - dold.x; dv.y = nv.y - dold.y; dv.z = nv.z - dold.z; dv.w = nv.w - dold.w;
+                    *reinterpret_cast<Quad<T> *>(Ds + ord_s[pb * BB_M + j] * ncp + 4 * cq) = nv;
                 }
-                *reinterpret_cast<Pair<T> *>(dlt + j * ncp + 2 * pr) = dv;
+                *reinterpret_cast<Quad<T> *>(dlt + j * ncp + 4 * cq) = dv;
             }
         }
     };
 
     for (int b = 0; b < nbk; ++b) {
         const int mb = min(BB_M, k - b * BB_M);
-        const int par = b & 1;
+        const unsigned par = (unsigned)(b & 1);
         BB_STAMP(b, 0);
         // ---- S0a: small tables of this block (its C rows are resident); apply the previous block ----
-        if (tid < BB_M) {
-            const T d = (tid < mb) ? Cblk[tid * kp + ord_s[b * BB_M + tid]] : T(1);
-            caa[tid] = d;
-            rcaa[tid] = T(1) / d;
-        }
-        if (b > 0 && tid < BB_M * BB_M) {
-            const int i = tid / BB_M, j = tid % BB_M;
-            Cx[tid] = Cblk[j * kp + ord_s[(b - 1) * BB_M + i]];                 // C[a_j, a_i(prev)]
+        if (tid >= BB_THREADS - BB_M) {                      // (the low threads carry the apply below)
+            const int t = tid - (BB_THREADS - BB_M);
+            const T d = (t < mb) ? Cblk[t * kp + ord_s[b * BB_M + t]] : T(1);
+            caa[t] = d;
+            rcaa[t] = T(1) / d;
+        } else if (b > 0 && tid >= 96 && tid < 96 + BB_M * BB_M) {
+            const int e = tid - 96, i = e / BB_M, j = e % BB_M;
+            Cx[e] = Cblk[j * kp + ord_s[(b - 1) * BB_M + i]];                   // C[a_j, a_i(prev)]
         }
         if (b > 0) apply_block(b - 1);
         __syncthreads();
         BB_STAMP(b, 1);
-        // ---- S0b: repair the look-ahead product with the previous block's deltas; basis of this block ----
-        for (int e = tid; e < (BB_M / 2) * NP; e += BB_THREADS) {
-            const int q = e / NP, pr = e % NP;
-            Pair<T> dot0 = *reinterpret_cast<const Pair<T> *>(Rraw + (2 * q) * ncp + 2 * pr);
-            Pair<T> dot1 = *reinterpret_cast<const Pair<T> *>(Rraw + (2 * q + 1) * ncp + 2 * pr);
+        // ---- S0b: repair the look-ahead product with the previous block's deltas; basis of this block.
+        //      item = (4 columns, 4 atoms) ----
+        for (int e = tid; e < 4 * (ncp >> 2); e += BB_THREADS) {
+            const int NQ = ncp >> 2;
+            const int aq = e / NQ, cq = e % NQ;
+            Pair<T> dot[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const Quad<T> rr = *reinterpret_cast<const Quad<T> *>(Rraw + (4 * aq + u) * ncp + 4 * cq);
+                dot[u][0].x = rr.x; dot[u][0].y = rr.y; dot[u][1].x = rr.z; dot[u][1].y = rr.w;
+            }
             if (b > 0) {
 #pragma unroll
                 for (int i = 0; i < BB_M; ++i) {
-                    const Pair<T> dv = *reinterpret_cast<const Pair<T> *>(dlt + i * ncp + 2 * pr);
-                    const Pair<T> cq = *reinterpret_cast<const Pair<T> *>(Cx + i * BB_M + 2 * q);
-                    pair_fma(cq.x, dv, dot0);
-                    pair_fma(cq.y, dv, dot1);
+                    const Quad<T> dv = *reinterpret_cast<const Quad<T> *>(dlt + i * ncp + 4 * cq);
+                    const Quad<T> cx = *reinterpret_cast<const Quad<T> *>(Cx + i * BB_M + 4 * aq);
+                    pair_fma(cx.x, Pair<T>{dv.x, dv.y}, dot[0][0]); pair_fma(cx.x, Pair<T>{dv.z, dv.w}, dot[0][1]);
+                    pair_fma(cx.y, Pair<T>{dv.x, dv.y}, dot[1][0]); pair_fma(cx.y, Pair<T>{dv.z, dv.w}, dot[1][1]);
+                    pair_fma(cx.z, Pair<T>{dv.x, dv.y}, dot[2][0]); pair_fma(cx.z, Pair<T>{dv.z, dv.w}, dot[2][1]);
+                    pair_fma(cx.w, Pair<T>{dv.x, dv.y}, dot[3][0]); pair_fma(cx.w, Pair<T>{dv.z, dv.w}, dot[3][1]);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int j = 2 * q + u;
-                Pair<T> gv = {T(0), T(0)}, dold = {T(0), T(0)};
+            for (int u = 0; u < 4; ++u) {
+                const int j = 4 * aq + u;
+                Quad<T> gv, dold;
+                gv.x = gv.y = gv.z = gv.w = dold.x = dold.y = dold.z = dold.w = T(0);
                 if (j < mb) {
                     const T ca = caa[j], rc = rcaa[j];
-                    const Pair<T> dot = u ? dot1 : dot0;
-                    dold = *reinterpret_cast<const Pair<T> *>(Ds + ord_s[b * BB_M + j] * ncp + 2 * pr);
-                    const Pair<T> bv = *reinterpret_cast<const Pair<T> *>(Brow + j * ncp + 2 * pr);
-                    const T gx = (bv.x - dot.x) + ca * dold.x, gy = (bv.y - dot.y) + ca * dold.y;   // [ref: :679-683]
-                    T qx = gx * rc, qy = gy * rc;
-                    qx = fma(fma(-qx, ca, gx), rc, qx);                            // grad / caa, Newton-corrected
-                    qy = fma(fma(-qy, ca, gy), rc, qy);
                     const bool upd = ca > T(1e-20);                                // else do not update [ref: :681-683]
-                    gv.x = upd ? qx : dold.x; gv.y = upd ? qy : dold.y;
+                    dold = *reinterpret_cast<const Quad<T> *>(Ds + ord_s[b * BB_M + j] * ncp + 4 * cq);
+                    const Quad<T> bv = *reinterpret_cast<const Quad<T> *>(Brow + j * ncp + 4 * cq);
+                    auto cand = [&](T bvv, T dotv, T dv) {
+                        const T gr = (bvv - dotv) + ca * dv;                       // [ref: :679-683]
+                        T qv = gr * rc;
+                        qv = fma(fma(-qv, ca, gr), rc, qv);                        // grad / caa, Newton-corrected
+                        return upd ? qv : dv;
+                    };
+                    gv.x = cand(bv.x, dot[u][0].x, dold.x); gv.y = cand(bv.y, dot[u][0].y, dold.y);
+                    gv.z = cand(bv.z, dot[u][1].x, dold.z); gv.w = cand(bv.w, dot[u][1].y, dold.w);
                 }
-                *reinterpret_cast<Pair<T> *>(basis + j * ncp + 2 * pr) = gv;
-                *reinterpret_cast<Pair<T> *>(basis + (BB_M + j) * ncp + 2 * pr) = dold;
+                *reinterpret_cast<Quad<T> *>(basis + j * ncp + 4 * cq) = gv;
+                *reinterpret_cast<Quad<T> *>(basis + (BB_M + j) * ncp + 4 * cq) = dold;
             }
         }
-        if (tid < BB_M * BB_M) {
-            const int t = tid / BB_M, j = tid % BB_M;
+        if (tid >= 128) {
+            const int e = tid - 128, t = e / BB_M, j = e % BB_M;
             T l = T(0);
             if (j < t && t < mb && caa[t] > T(1e-20)) {
                 const T c1 = Cblk[t * kp + ord_s[b * BB_M + j]], ca = caa[t], rc = rcaa[t];   // C[a_t, a_j]
                 l = c1 * rc;
                 l = fma(fma(-l, ca, c1), rc, l);
             }
-            Lblk[tid] = l;
+            LT[j * BB_M + t] = l;
+        }
+        if (tid == 127) {   // arm this block's two exchanges (bytes this CTA will receive)
+            mbar_expect_tx(bar1, (unsigned)(n_owned * nblk * 16 * (int)sizeof(T)));
+            mbar_expect_tx(bar2, (unsigned)(BB_GRAM * (int)sizeof(T)));
         }
         __syncthreads();
         BB_STAMP(b, 2);
         if (b + 1 < nbk) issue_loads(b + 1);        // Cblk / Brow of block b are consumed
-        // ---- S1: partial Gram of the 32 basis vectors over my columns (4x4 register tiles, 8 column parts) ----
+        // ---- S1: partial Gram of the 32 basis vectors over my columns (4x4 register tiles, 8 column parts), pushed
+        //          tile by tile into the CTA that sums the tile (reduce-scatter over distributed shared memory) ----
         if (wid < BB_TILES / 4) {
             const int ti = 4 * wid + (lane >> 3), part = lane & 7;
             const int I = tile_i[ti], J = tile_j[ti];
@@ -396,112 +487,98 @@ bcd_blocked_kernel(BcdParams<T> P)
                     v += __shfl_xor_sync(kFullMask, v, 4);
                     out[a][bb] = v;
                 }
-            if (part == 0) {
-                T *dst = stage + par * BB_GRAM + ti * 16;
+            if (part < 4) {         // lane `part` of the tile's group sends row `part` of the tile
+                T q0 = out[0][0], q1 = out[0][1], q2 = out[0][2], q3 = out[0][3];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    Quad<T> o;
-                    o.x = out[a][0]; o.y = out[a][1]; o.z = out[a][2]; o.w = out[a][3];
-                    *reinterpret_cast<Quad<T> *>(dst + 4 * a) = o;
-                }
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // visible to the bulk copies below
+                for (int a = 1; a < 4; ++a)
+                    if (part == a) { q0 = out[a][0]; q1 = out[a][1]; q2 = out[a][2]; q3 = out[a][3]; }
+                const int owner = ti % nblk, slot = ti / nblk;
+                const unsigned local = (unsigned)__cvta_generic_to_shared(rsrecv + par * (BB_RS_SLOTS * 16) + ((slot * nblk + g) * 16 + 4 * part));
+                st_async_quad(mapa_u32(local, (unsigned)owner), mapa_u32(bar1, (unsigned)owner), q0, q1, q2, q3);
             }
         }
-        __syncthreads();
         BB_STAMP(b, 3);
-        // every peer has consumed the previous exchange (and finished the scratch use of its receive area)
-        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-        BB_STAMP(b, 4);
-        // ---- S2: all-to-all of the partial Grams ----
-        if (tid == 0) mbar_expect_tx(xbar_addr, (unsigned)nblk * kGramBytes);
-        if (tid < nblk) {
-            const unsigned src = (unsigned)__cvta_generic_to_shared(stage + par * BB_GRAM);
-            const unsigned dst = mapa_u32((unsigned)__cvta_generic_to_shared(recv + (size_t)g * BB_GRAM), (unsigned)tid);
-            const unsigned bar = mapa_u32(xbar_addr, (unsigned)tid);
-            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                         ::"r"(dst), "r"(src), "r"(kGramBytes), "r"(bar) : "memory");
+        // ---- S2: the owner of a tile sums its 16 partials (fixed order) and pushes the sums to every CTA (all-gather).
+        //          thread = (row of an owned tile, destination CTA): each sums its four values itself, no hand-over ----
+        if (tid < n_owned * 4 * nblk) {
+            const int qd = tid / nblk, pe = tid % nblk;
+            const int slot = qd >> 2, a = qd & 3;
+            mbar_wait(bar1, par);
+            const T *rsb = rsrecv + par * (BB_RS_SLOTS * 16);
+            Quad<T> sum = *reinterpret_cast<const Quad<T> *>(rsb + ((slot * nblk + 0) * 16 + 4 * a));
+            for (int q = 1; q < nblk; ++q) {
+                const Quad<T> v = *reinterpret_cast<const Quad<T> *>(rsb + ((slot * nblk + q) * 16 + 4 * a));
+                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            }
+            const int ti = slot * nblk + g;
+            const unsigned local = (unsigned)__cvta_generic_to_shared(Mflat + ti * 16 + 4 * a);
+            st_async_quad(mapa_u32(local, (unsigned)pe), mapa_u32(bar2, (unsigned)pe), sum.x, sum.y, sum.z, sum.w);
         }
-        mbar_wait(xbar_addr, (unsigned)par);
+        BB_STAMP(b, 4);
+        mbar_wait(bar2, par);
         BB_STAMP(b, 5);
-        // ---- S3: G = sum of the partials, in CTA order ----
+        // ---- S3: unpack the tiles into the symmetric matrix ----
         for (int v = tid; v < BB_GRAM; v += BB_THREADS) {
-            T part[BCD_MAX_CLUSTER];
-#pragma unroll
-            for (int q = 0; q < BCD_MAX_CLUSTER; ++q) part[q] = q < nblk ? recv[(size_t)q * BB_GRAM + v] : T(0);
-            T a0 = (part[0] + part[1]) + (part[2] + part[3]), a1 = (part[4] + part[5]) + (part[6] + part[7]);
-            T a2 = (part[8] + part[9]) + (part[10] + part[11]), a3 = (part[12] + part[13]) + (part[14] + part[15]);
-            const T sum = (a0 + a1) + (a2 + a3);
+            const T val = Mflat[v];
             const int ti = v >> 4, a = (v >> 2) & 3, bb = v & 3;
             const int r = 4 * tile_i[ti] + a, c = 4 * tile_j[ti] + bb;
-            Mfull[r * BB_MLD + c] = sum;
-            if (tile_i[ti] != tile_j[ti]) Mfull[c * BB_MLD + r] = sum;
+            Mfull[r * BB_MLD + c] = val;
+            if (tile_i[ti] != tile_j[ti]) Mfull[c * BB_MLD + r] = val;
         }
         cp_async_wait_all();
         __syncthreads();
         BB_STAMP(b, 6);
         // ---- S4: warp 0 solves the block's scalars; the other warps run the look-ahead product of the next block ----
-        if (wid == 0) {
+        if (wid == BB_SOLVER) {
             T Mrow[BB_NB];
 #pragma unroll
             for (int c = 0; c < BB_NB; ++c) Mrow[c] = Mfull[lane * BB_MLD + c];
-            T dl[BB_M], zz[BB_M];
+            // radius of atom t (lane t):  comp_norm_[k] += enet_norm(old row)  [ref: :676-678]; |d_t|^2 is a Gram diagonal
+            const int a_l = ord_s[b * BB_M + (lane & (BB_M - 1))];
+            const T rad_l = cnorm[a_l] + Mfull[(BB_M + (lane & (BB_M - 1))) * BB_MLD + BB_M + (lane & (BB_M - 1))];
+            const T rinv_l = rad_l != T(0) ? T(1) / rad_l : T(0);
+            T wacc[BB_M], yacc[BB_M];      // lane r's component of w_t and of G w_t, accumulated right-looking
+#pragma unroll
+            for (int t = 0; t < BB_M; ++t) { wacc[t] = (lane == t) ? T(1) : T(0); yacc[t] = Mrow[t]; }
 #pragma unroll
             for (int t = 0; t < BB_M; ++t) {
-                if (t < mb) {
-                    T w = (lane == t) ? T(1) : T(0);
-                    T y = Mrow[t];
+                const T w = wacc[t], y = yacc[t];
+                T n2 = w * y;                                       // |v_t|^2 = w^T G w
 #pragma unroll
-                    for (int j = 0; j < t; ++j) {
-                        const T l = Lblk[t * BB_M + j];
-                        w = fma(-l, dl[j], w);
-                        y = fma(-l, zz[j], y);
-                    }
-                    T n2 = w * y;
+                for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(kFullMask, n2, o);
+                n2 = n2 > T(0) ? n2 : T(0);
+                const T radius = __shfl_sync(kFullMask, rad_l, t), rinv = __shfl_sync(kFullMask, rinv_l, t);
+                const T x = n2 * rinv;
+                const T rs = bcd_rsqrt(x > T(1) ? x : T(1));
+                T rn = x > T(1) ? rs : T(1);                        // v / sqrt(|v|^2 / radius) outside the ball [ref: enet.pyx:62-70]
+                rn = radius == T(0) ? T(0) : rn;                    // [ref: enet.pyx:56-58]
+                const T cf = rn * w;
+                const T dlv = cf - ((lane == BB_M + t) ? T(1) : T(0));       // delta_t = n_t - d_t
+                const T zv = fma(rn, y, -Mrow[BB_M + t]);                    // G delta_t
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(kFullMask, n2, o);
-                    n2 = n2 > T(0) ? n2 : T(0);
-                    const int a = ord_s[b * BB_M + t];
-                    const T radius = cnorm[a] + Mfull[(BB_M + t) * BB_MLD + BB_M + t];   // comp_norm_[k] += enet_norm(old row) [ref: :676-678]
-                    if (lane == 0) rad[a] = radius;
-                    T rn = T(1);
-                    if (radius == T(0)) {
-                        rn = T(0);                                                  // [ref: enet.pyx:56-58]
-                    } else {
-                        const T x = n2 / radius;
-                        if (x > T(1)) rn = bcd_rsqrt(x);                            // v / sqrt(|v|^2 / radius) [ref: enet.pyx:62-70]
-                    }
-                    const T cf = rn * w;
-                    coef[t * BB_NB + lane] = cf;
-                    dl[t] = cf - ((lane == BB_M + t) ? T(1) : T(0));
-                    zz[t] = fma(rn, y, -Mrow[BB_M + t]);
-                } else {
-                    coef[t * BB_NB + lane] = T(0);
-                    dl[t] = zz[t] = T(0);
+                for (int t2 = t + 1; t2 < BB_M; ++t2) {
+                    const T l = LT[t * BB_M + t2];                           // L_{t2, t}
+                    wacc[t2] = fma(-l, dlv, wacc[t2]);
+                    yacc[t2] = fma(-l, zv, yacc[t2]);
                 }
+                coef[t * BB_NB + lane] = cf;
+                // comp_norm_[k] -= enet_norm(new row) [ref: :690-692]: |n_t|^2 = rn^2 |v_t|^2 (the same value in every CTA)
+                if (g == 0 && lane == 0 && t < mb) P.comp_norm[ord_s[b * BB_M + t]] = radius - (rn * rn) * n2;
             }
-            BB_STAMP(b, 7);
+            if (sstamp) sstamp[(int64_t)b * 8 + 7] = clock64();
         } else if (b + 1 < nbk) {
             if (wstamp) wstamp[2 * b] = clock64();
             lookahead();
             if (wstamp) wstamp[2 * b + 1] = clock64();
         }
         __syncthreads();
-        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     }
-    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     if (stamp) stamp[(int64_t)8 * k + 3] = clock64();
     apply_block(nbk - 1);
     __syncthreads();
     if (stamp) stamp[(int64_t)8 * k + 4] = clock64();
 
-    // ---- epilogue: norms of the new atoms, write-back (as in bcd_pilot_kernel) ----
-    T *napart = P.part;                                        // [nblk][k]
-    for (int i = wid; i < k; i += BB_THREADS / 32) {
-        T acc = T(0);
-        for (int c = lane; c < nc; c += 32) acc += enet_term(Ds[i * ncp + c], P.l1_ratio);
-        acc = warp_sum(acc);
-        if (lane == 0) napart[(int64_t)g * k + i] = acc;
-    }
+    // ---- epilogue: write the slice back ----
     if (p_vec) {
         const int nv = ncp / VE;
         for (int e = tid; e < k * nv; e += BB_THREADS) {
@@ -520,22 +597,10 @@ bcd_blocked_kernel(BcdParams<T> P)
         }
     }
     if (stamp) stamp[(int64_t)8 * k + 5] = clock64();
-    __threadfence();
+    // nobody leaves while a peer may still address its shared memory
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-    if (stamp) stamp[(int64_t)8 * k + 6] = clock64();
-    if (g == 0) {
-        for (int i = tid; i < k; i += BB_THREADS) {
-            T part[BCD_MAX_CLUSTER];
-#pragma unroll
-            for (int q = 0; q < BCD_MAX_CLUSTER; ++q) part[q] = q < nblk ? __ldcg(napart + (int64_t)q * k + i) : T(0);   // all in flight
-            T na = T(0);
-#pragma unroll
-            for (int q = 0; q < BCD_MAX_CLUSTER; ++q) na += part[q];                     // fixed order
-            P.comp_norm[i] = rad[i] - na;                                                // [ref: :690-692]
-        }
-    }
-    if (stamp) stamp[(int64_t)8 * k + 7] = clock64();
+    if (stamp) stamp[(int64_t)8 * k + 7] = stamp[(int64_t)8 * k + 6] = clock64();
 #undef BB_STAMP
 }
 

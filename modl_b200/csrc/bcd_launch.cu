@@ -64,7 +64,7 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
             for (int pilot = blocked_ok ? 2 : (ctx->opt_bcd_pilot ? 1 : 0); pilot >= 0 && !nblk; --pilot) {
                 size_t need;
                 if (pilot == 2) {
-                    if (bcd_blocked_red_elems(ncp) > (int64_t)BCD_MAX_CLUSTER * BB_GRAM) continue;
+                    if (!bcd_blocked_fits(ncp)) continue;
                     need = bcd_blocked_smem_bytes<T>(k, ncp);
                 } else if (pilot == 1 && !ctx->opt_bcd_pilot) {
                     continue;

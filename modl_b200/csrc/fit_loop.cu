@@ -422,6 +422,7 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
         q.sweeps = io->sweeps;
         q.global_batch = sharded ? b_global : 0;
         q.slot = slot;
+        q.h_inputs_mapped = 1;          // subset and order live in the pinned ring slot of this step
         const int64_t off = contiguous ? base : 0;
         q.n_samples = e->n_samples - off;
         q.code = static_cast<T *>(e->code) + off * k;

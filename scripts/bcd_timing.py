@@ -39,8 +39,8 @@ for name, blocked, pipe in (("blocked", 1, 1), ("pipelined pilot", 0, 1), ("pilo
         ph = np.array([[st[8 * b + i] for i in range(8)] for b in range(nbk)], dtype=np.int64)
         nxt = np.concatenate([ph[1:, 0], [g[3]]])              # start of the next block = end of S4 (after its barrier)
         iv = np.column_stack([np.diff(ph[:, :8], axis=1), nxt - ph[:, 6]])[1:-1]     # blocks 1 .. nbk-2
-        names = ["S0a tables+apply", "S0b repair+basis", "S1 loads+gram", "cluster wait", "S2 exchange", "S3 sum",
-                 "S4 solver alone", "S4 whole (solver | look-ahead)"]
+        names = ["S0a tables+apply", "S0b repair+basis", "S1 loads+gram+push", "S2a reduce-scatter wait+sum+push",
+                 "S2b all-gather wait", "S3 unpack", "S4 solver alone", "S4 whole (solver | look-ahead)"]
         la = np.array([st[8 * K + 16 + 2 * b + 1] - st[8 * K + 16 + 2 * b] for b in range(1, nbk - 1)])
         print(name, "| kernel %d cycles: loads %d, first product %d, blocks %d, last apply %d, norms+write-back %d, "
               "fence+cluster barrier %d, comp_norm %d" % (g[7] - g[0], g[1] - g[0], g[2] - g[1], g[3] - g[2], g[4] - g[3],
