@@ -44,6 +44,16 @@ constexpr int BB_RS_SLOTS = 52;          // (owned tile, sender) slots of the re
 constexpr int BB_RED_CAP = 9216;         // scratch of the look-ahead product (elements)
 enum { BB_BAR_WORKERS = 1 };
 constexpr int BB_SOLVER = BB_THREADS / 32 - 1;   // the solver warp: the HIGHEST warp id (the issue arbiter favours high ids)
+constexpr int BB_NWORK = 256;            // warps 0..7: the look-ahead product (two per scheduler), behind the solver
+constexpr int BB_NPH = BB_THREADS;       // every thread takes part in the per-block phases
+// 1 / sqrt(x) for x >= 1: approximation + one Newton step, no denormal handling
+__device__ __forceinline__ float bb_rsqrt(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return fmaf(0.5f * y, fmaf(-x * y, y, 1.f), y);
+}
+__device__ __forceinline__ double bb_rsqrt(double x) { return 1.0 / sqrt(x); }
 
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src)
 {
@@ -81,8 +91,8 @@ __host__ __device__ inline size_t bcd_blocked_smem_bytes(int64_t k, int64_t ncp)
 {
     const int64_t kp = round_up(k, 32);
     const int64_t elems = k * ncp                 // Ds
-                          + kp * BB_M             // Cblk
-                          + 2 * BB_M * ncp        // Rraw, Brow
+                          + 2 * kp * BB_M         // Cblk (two blocks)
+                          + 3 * BB_M * ncp        // Rraw (two blocks), Brow
                           + BB_NB * ncp           // basis
                           + BB_M * ncp            // dlt
                           + BB_M * BB_NB          // coef
@@ -113,24 +123,26 @@ bcd_blocked_kernel(BcdParams<T> P)
     const int kp = (int)round_up(k, 32);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nbk = (k + BB_M - 1) / BB_M;
-    const int NP = ncp >> 1;                                 // column pairs of the slice
+    const int NQ = ncp >> 2;                                 // groups of 4 columns of the slice
+    const bool worker = tid < BB_NWORK;
+    const int pt = tid;                                      // index among the phase threads (all of them)
 
     // ---- shared memory carve-up (see bcd_blocked_smem_bytes) ----
-    T *Ds = reinterpret_cast<T *>(bb_smem_raw);              // [k][ncp]   the CTA's slice of D_sub
-    T *Cblk = Ds + (size_t)k * ncp;                          // [M][kp]    C[a_j, :] of the block in flight / ahead
-    T *Rraw = Cblk + kp * BB_M;                              // [M][ncp]   look-ahead product C[a_j,:] . D_sub (previous block not applied)
-    T *Brow = Rraw + BB_M * ncp;                             // [M][ncp]   B_sub rows of the block
-    T *basis = Brow + BB_M * ncp;                            // [2M][ncp]  g_1..g_M, d_1..d_M
-    T *dlt = basis + BB_NB * ncp;                            // [M][ncp]   deltas of the block just applied
-    T *coef = dlt + BB_M * ncp;                              // [M][2M]    n_t = sum_r coef[t][r] basis_r
-    T *LT = coef + BB_M * BB_NB;                             // [M][M]     L_tj at [j*M + t] (j < t), zero elsewhere
-    T *Cx = LT + BB_M * BB_M;                                // [M][M]     C[a_j, a_i(previous block)] at [i*M + j]
-    T *Mfull = Cx + BB_M * BB_M;                             // [2M][2M+1] Gram matrix of the basis
-    T *cnorm = Mfull + BB_NB * BB_MLD + 32;                  // [kp]       comp_norm_ on entry
-    T *caa = cnorm + kp;                                     // [M]        C[a_t, a_t]
-    T *rcaa = caa + BB_M;                                    // [M]        1 / C[a_t, a_t]
-    T *Mflat = rcaa + BB_M;                                  // [36][16]   the summed Gram, tile-packed (all-gather target)
-    T *rsrecv = Mflat + BB_GRAM;                             // [2][slot][sender][16] partial tiles this CTA sums (reduce-scatter target, by block parity)
+    T *Ds = reinterpret_cast<T *>(bb_smem_raw);              // [k][ncp]     the CTA's slice of D_sub
+    T *Cblk = Ds + (size_t)k * ncp;                          // [2][M][kp]   C[a_j, :] by block parity
+    T *Rraw = Cblk + 2 * kp * BB_M;                          // [2][M][ncp]  look-ahead product C[a_j,:] . D_sub, by block parity
+    T *Brow = Rraw + 2 * BB_M * ncp;                         // [M][ncp]     B_sub rows of the block
+    T *basis = Brow + BB_M * ncp;                            // [2M][ncp]    g_1..g_M, d_1..d_M
+    T *dlt = basis + BB_NB * ncp;                            // [M][ncp]     deltas of the block just applied
+    T *coef = dlt + BB_M * ncp;                              // [M][2M]      n_t = sum_r coef[t][r] basis_r
+    T *LT = coef + BB_M * BB_NB;                             // [M][M]       L_tj at [j*M + t] (j < t), zero elsewhere
+    T *Cx = LT + BB_M * BB_M;                                // [M][M]       C[a_j, a_i(previous block)] at [i*M + j]
+    T *Mfull = Cx + BB_M * BB_M;                             // [2M][2M+1]   Gram matrix of the basis
+    T *cnorm = Mfull + BB_NB * BB_MLD + 32;                  // [kp]         comp_norm_ on entry
+    T *caa = cnorm + kp;                                     // [M]          C[a_t, a_t]
+    T *rcaa = caa + BB_M;                                    // [M]          1 / C[a_t, a_t]
+    T *Mflat = rcaa + BB_M;                                  // [36][16]     the summed Gram, tile-packed (all-gather target)
+    T *rsrecv = Mflat + BB_GRAM;                             // [2][slot][sender][16] partial tiles this CTA sums, by block parity
     T *red = rsrecv + 2 * BB_RS_SLOTS * 16;                  // scratch of the look-ahead product
     int *ord_s = reinterpret_cast<int *>(red + BB_RED_CAP);  // [kp] update order
     __shared__ __align__(8) unsigned long long xbar[2];      // [0] reduce-scatter arrivals, [1] all-gather arrivals
@@ -139,12 +151,16 @@ bcd_blocked_kernel(BcdParams<T> P)
     const unsigned bar2 = bar1 + 8;
     const int n_owned = (BB_TILES - g + nblk - 1) / nblk;    // tiles ti with ti % nblk == g  (g < nblk <= 16 < 36)
 
-    // debug stamps of CTA 0: thread 0 [b][0..6] phase starts and the look-ahead, lane 0 of the solver warp [b][7] = solver done;
-    // start / end per block at 8k + 16 + 2b, kernel-level stamps at 8k .. 8k + 7
+    // debug stamps of CTA 0.  First phase thread: [b][0..6]; lane 0 of the solver warp: [b][7] = solver done;
+    // thread 0 (a worker): look-ahead start / end per block at 8k + 16 + 4b; kernel-level stamps at 8k .. 8k + 7
     long long *stamp = (P.timing && g == 0 && tid == 0) ? P.timing : nullptr;
-    long long *wstamp = (P.timing && g == 0 && tid == 0) ? P.timing + (int64_t)8 * k + 16 : nullptr;
+    long long *wstamp = (P.timing && g == 0 && tid == 32) ? P.timing + (int64_t)8 * k + 16 : nullptr;
     long long *sstamp = (P.timing && g == 0 && tid == 32 * BB_SOLVER) ? P.timing : nullptr;
 #define BB_STAMP(b_, slot_) do { if (stamp) stamp[(int64_t)(b_) * 8 + (slot_)] = clock64(); } while (0)
+    // a stamp right after a barrier records when the warp ARRIVED (the barrier blocks at the next dependent access), so
+    // the release time is taken after a volatile shared load
+#define BB_REL_STAMP(b_, slot_) do { if (stamp) { const int v_ = *reinterpret_cast<volatile int *>(ord_s); \
+        stamp[(int64_t)(b_) * 8 + (slot_)] = clock64() + (v_ & 0); } } while (0)
     if (stamp) stamp[(int64_t)8 * k] = clock64();
 
     constexpr int VE = 16 / (int)sizeof(T);                  // elements per 16-byte copy
@@ -152,36 +168,39 @@ bcd_blocked_kernel(BcdParams<T> P)
     const bool p_vec = (lds % VE == 0) && (c0 % VE == 0) && ((reinterpret_cast<uintptr_t>(P.Dp) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(P.Bp) & 15) == 0);
 
-    // operands of block b: C[a_j, :] and B_sub[a_j, my columns]; every copy asynchronous and in flight at once
-    auto issue_loads = [&](int b) {
-        const int mb = min(BB_M, k - b * BB_M);
+    // asynchronous operand copies, spread over `nth` threads (index `t`): C[a_j, :] of block bc, B_sub rows of block bb
+    auto load_C = [&](int bc, int t, int nth) {
+        const int mb = min(BB_M, k - bc * BB_M);
+        T *dstC = Cblk + (bc & 1) * kp * BB_M;
         if (c_vec) {
             const int nv = k / VE;
-            for (int e = tid; e < BB_M * nv; e += BB_THREADS) {
+            for (int e = t; e < BB_M * nv; e += nth) {
                 const int j = e / nv, iv = (e % nv) * VE;
-                if (j < mb) cp_async_16(Cblk + j * kp + iv, P.C + (int64_t)ord_s[b * BB_M + j] * k + iv);
+                if (j < mb) cp_async_16(dstC + j * kp + iv, P.C + (int64_t)ord_s[bc * BB_M + j] * k + iv);
             }
         } else {
-            for (int e = tid; e < BB_M * k; e += BB_THREADS) {
+            for (int e = t; e < BB_M * k; e += nth) {
                 const int j = e / k, i = e % k;
-                if (j < mb) cp_async_elem(Cblk + j * kp + i, P.C + (int64_t)ord_s[b * BB_M + j] * k + i);
+                if (j < mb) cp_async_elem(dstC + j * kp + i, P.C + (int64_t)ord_s[bc * BB_M + j] * k + i);
             }
         }
+    };
+    auto load_B = [&](int bb, int t, int nth) {
+        const int mb = min(BB_M, k - bb * BB_M);
         const int nvb = ncp / VE;
-        for (int e = tid; e < BB_M * nvb; e += BB_THREADS) {
+        for (int e = t; e < BB_M * nvb; e += nth) {
             const int j = e / nvb, cv = (e % nvb) * VE;
             T *dst = Brow + j * ncp + cv;
             if (j < mb && p_vec && cv + VE <= nc) {
-                cp_async_16(dst, P.Bp + (int64_t)ord_s[b * BB_M + j] * lds + c0 + cv);
+                cp_async_16(dst, P.Bp + (int64_t)ord_s[bb * BB_M + j] * lds + c0 + cv);
             } else {
 #pragma unroll
                 for (int u = 0; u < VE; ++u) {
-                    if (j < mb && cv + u < nc) cp_async_elem(dst + u, P.Bp + (int64_t)ord_s[b * BB_M + j] * lds + c0 + cv + u);
+                    if (j < mb && cv + u < nc) cp_async_elem(dst + u, P.Bp + (int64_t)ord_s[bb * BB_M + j] * lds + c0 + cv + u);
                     else dst[u] = T(0);
                 }
             }
         }
-        cp_async_commit();
     };
 
     // ---- prologue: D slice (asynchronous copies), norms, order, tables ----
@@ -206,7 +225,7 @@ bcd_blocked_kernel(BcdParams<T> P)
             }
         }
     }
-    for (int e = tid; e < BB_M * kp; e += BB_THREADS) Cblk[e] = T(0);       // rows of a short last block stay zero
+    for (int e = tid; e < 2 * BB_M * kp; e += BB_THREADS) Cblk[e] = T(0);   // rows of a short last block stay zero
     for (int e = tid; e < BB_M * ncp; e += BB_THREADS) dlt[e] = T(0);
     for (int e = tid; e < BB_M * BB_NB; e += BB_THREADS) coef[e] = T(0);
     for (int e = tid; e < BB_M * BB_M; e += BB_THREADS) Cx[e] = T(0);
@@ -222,7 +241,10 @@ bcd_blocked_kernel(BcdParams<T> P)
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();                        // ord_s, zeroed Cblk
-    issue_loads(0);
+    load_C(0, tid, BB_THREADS);
+    if (nbk > 1) load_C(1, tid, BB_THREADS);
+    load_B(0, tid, BB_THREADS);
+    cp_async_commit();
     // every peer is resident and its mbarriers initialised before anybody sends
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
@@ -231,15 +253,18 @@ bcd_blocked_kernel(BcdParams<T> P)
     __syncthreads();
     if (stamp) stamp[(int64_t)8 * k + 1] = clock64();
 
-    // look-ahead product of the block whose C rows are in Cblk, against the shared slice as it is now (warps 0..10;
-    // warp 11 is the solver): Rraw[j] = C[a_j,:] . D_sub.  The shared-memory port bounds this loop (a broadcast load
-    // costs one port cycle per 4 bytes), so a thread owns FOUR columns x all 16 atoms x a group of rows: per 4 rows
-    // 4 + 16 128-bit loads feed 128 FFMA2.  Row groups are combined through a scratch that holds half of them: the
-    // first half stores, the second half adds in place, then the halves' sums are added in group order (fixed order).
-    auto lookahead = [&]() {
-        constexpr int NW = BB_THREADS - 32;
+    // Look-ahead product of block bl (worker warps): Rraw[bl & 1][j] = C[a_j,:] . D_sub against the shared slice as
+    // it is now.  A thread owns FOUR columns x all 16 atoms x a group of rows: per 4 rows 4 + 16 128-bit shared loads
+    // feed 128 FFMA2 (the fma pipe issues one FFMA2 per ~2.5 cycles and scheduler, a broadcast 128-bit load costs ~2.5
+    // cycles of the shared-memory port: the loop is fma-bound).  Row groups are combined through a scratch that holds
+    // half of them: the first half stores, the second half adds in place, then the sums are added in group order.
+    auto lookahead = [&](int bl) {
+        constexpr int NW = BB_NWORK;
+        const T *Cb = Cblk + (bl & 1) * kp * BB_M;
+        T *Rb = Rraw + (bl & 1) * BB_M * ncp;
         if constexpr (sizeof(T) == 8) {
             // double: two columns per thread (the four-column tile would not fit the register file), one round
+            const int NP = ncp >> 1;
             const int IGW = max(1, min(NW / NP, BB_RED_CAP / (BB_M * ncp)));
             const int pr = tid % NP, ig = tid / NP;
             const int RB = (((k + IGW - 1) / IGW) + 3) & ~3;
@@ -252,7 +277,7 @@ bcd_blocked_kernel(BcdParams<T> P)
                 for (int i = r0; i < r1; ++i) {
                     const Pair<T> d = dcol[i * NP];
 #pragma unroll
-                    for (int j = 0; j < BB_M; ++j) pair_fma(Cblk[j * kp + i], d, acc[j]);
+                    for (int j = 0; j < BB_M; ++j) pair_fma(Cb[j * kp + i], d, acc[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < BB_M; ++j)
@@ -262,11 +287,79 @@ bcd_blocked_kernel(BcdParams<T> P)
             for (int e = tid; e < BB_M * ncp; e += NW) {
                 T sum = T(0);
                 for (int gi = 0; gi < IGW; ++gi) sum += red[(size_t)gi * BB_M * ncp + e];   // fixed order
-                Rraw[e] = sum;
+                Rb[e] = sum;
             }
+            named_sync(BB_BAR_WORKERS, NW);
             return;
         }
-        const int NQ = ncp >> 2;
+        if (ncp == 96) {
+            // The benchmark width (k x 1250 over 16 CTAs).  One WARP per group of rows; lane = (half of the atoms, six
+            // columns): 8 atoms x 3 column pairs per thread, so that the eight warps carry exactly equal shares, two per
+            // scheduler (the fma pipe issues one FFMA2 per ~2.5 cycles and scheduler: 6144 warp-FFMA2 per block).
+            const int ig = wid, ah = lane >> 4, sx = lane & 15;
+            const int RB = (((k + 7) / 8) + 3) & ~3;
+            const int r0 = min(k, ig * RB), r1 = min(k, r0 + RB);
+            const T *dcol = Ds + 6 * sx;
+            const T *Ca = Cb + (8 * ah) * kp;
+            Pair<T> acc[8][3];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[j][c].x = acc[j][c].y = T(0);
+            int i = r0;
+            for (; i + 4 <= r1; i += 4) {
+                Pair<T> d[4][3];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) d[u][c] = *reinterpret_cast<const Pair<T> *>(dcol + (i + u) * ncp + 2 * c);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const Quad<T> c4 = *reinterpret_cast<const Quad<T> *>(Ca + j * kp + i);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        pair_fma(c4.x, d[0][c], acc[j][c]); pair_fma(c4.y, d[1][c], acc[j][c]);
+                        pair_fma(c4.z, d[2][c], acc[j][c]); pair_fma(c4.w, d[3][c], acc[j][c]);
+                    }
+                }
+            }
+            for (; i < r1; ++i) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const Pair<T> dv = *reinterpret_cast<const Pair<T> *>(dcol + i * ncp + 2 * c);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pair_fma(Ca[j * kp + i], dv, acc[j][c]);
+                }
+            }
+            // row groups 0..3 store, 4..7 add in place, then the four sums are added in group order (fixed order)
+            T *slot = red + ((size_t)(ig & 3) * BB_M + 8 * ah) * ncp + 6 * sx;
+            if (ig < 4) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) *reinterpret_cast<Pair<T> *>(slot + j * ncp + 2 * c) = acc[j][c];
+            }
+            named_sync(BB_BAR_WORKERS, NW);
+            if (ig >= 4) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        Pair<T> o = *reinterpret_cast<Pair<T> *>(slot + j * ncp + 2 * c);
+                        o.x += acc[j][c].x; o.y += acc[j][c].y;
+                        *reinterpret_cast<Pair<T> *>(slot + j * ncp + 2 * c) = o;
+                    }
+            }
+            named_sync(BB_BAR_WORKERS, NW);
+            for (int e = tid; e < BB_M * ncp; e += NW) {
+                T sum = red[e];
+#pragma unroll
+                for (int gi = 1; gi < 4; ++gi) sum += red[(size_t)gi * BB_M * ncp + e];
+                Rb[e] = sum;
+            }
+            named_sync(BB_BAR_WORKERS, NW);
+            return;
+        }
         const int half = max(1, BB_RED_CAP / (BB_M * ncp));
         const int IGW = max(1, min(NW / NQ, 2 * half));
         const int cq = tid % NQ, ig = tid / NQ;
@@ -285,7 +378,7 @@ bcd_blocked_kernel(BcdParams<T> P)
                 for (int h = 0; h < BB_M; h += 8) {
                     Quad<T> c4[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) c4[j] = *reinterpret_cast<const Quad<T> *>(Cblk + (h + j) * kp + i);
+                    for (int j = 0; j < 8; ++j) c4[j] = *reinterpret_cast<const Quad<T> *>(Cb + (h + j) * kp + i);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         pair_fma(c4[j].x, Pair<T>{d0.x, d0.y}, acc[h + j][0]); pair_fma(c4[j].x, Pair<T>{d0.z, d0.w}, acc[h + j][1]);
@@ -299,7 +392,7 @@ bcd_blocked_kernel(BcdParams<T> P)
                 const Quad<T> d = dcol[i * NQ];
 #pragma unroll
                 for (int j = 0; j < BB_M; ++j) {
-                    const T c = Cblk[j * kp + i];
+                    const T c = Cb[j * kp + i];
                     pair_fma(c, Pair<T>{d.x, d.y}, acc[j][0]); pair_fma(c, Pair<T>{d.z, d.w}, acc[j][1]);
                 }
             }
@@ -326,20 +419,20 @@ bcd_blocked_kernel(BcdParams<T> P)
         for (int e = tid; e < BB_M * ncp; e += NW) {
             T sum = T(0);
             for (int gi = 0; gi < nsum; ++gi) sum += red[(size_t)gi * BB_M * ncp + e];   // fixed order
-            Rraw[e] = sum;
+            Rb[e] = sum;
         }
+        named_sync(BB_BAR_WORKERS, NW);        // the scratch may be reused
     };
 
-    if (wid != BB_SOLVER) lookahead();
+    if (worker) lookahead(0);
     __syncthreads();
     if (stamp) stamp[(int64_t)8 * k + 2] = clock64();
 
     // new rows and deltas of block pb on my columns, from the coefficients the solver left:  n_j = sum_r coef[j][r] basis_r.
-    // item = (4 columns, 4 atoms): 8 128-bit loads feed 32 FFMA2 (the shared-memory port bounds this phase too).
+    // item = (4 columns, 4 atoms): 8 128-bit loads feed 32 FFMA2.  Phase threads.
     auto apply_block = [&](int pb) {
         const int mbp = min(BB_M, k - pb * BB_M);
-        const int NQ = ncp >> 2;
-        for (int e = tid; e < 4 * NQ; e += BB_THREADS) {
+        for (int e = pt; e < 4 * NQ; e += BB_NPH) {
             const int aq = e / NQ, cq = e % NQ;
             const Quad<T> *bcol = reinterpret_cast<const Quad<T> *>(basis) + cq;
             Pair<T> acc[4][2];
@@ -375,29 +468,35 @@ bcd_blocked_kernel(BcdParams<T> P)
     for (int b = 0; b < nbk; ++b) {
         const int mb = min(BB_M, k - b * BB_M);
         const unsigned par = (unsigned)(b & 1);
-        BB_STAMP(b, 0);
-        // ---- S0a: small tables of this block (its C rows are resident); apply the previous block ----
-        if (tid >= BB_THREADS - BB_M) {                      // (the low threads carry the apply below)
-            const int t = tid - (BB_THREADS - BB_M);
-            const T d = (t < mb) ? Cblk[t * kp + ord_s[b * BB_M + t]] : T(1);
-            caa[t] = d;
-            rcaa[t] = T(1) / d;
-        } else if (b > 0 && tid >= 96 && tid < 96 + BB_M * BB_M) {
-            const int e = tid - 96, i = e / BB_M, j = e % BB_M;
-            Cx[e] = Cblk[j * kp + ord_s[(b - 1) * BB_M + i]];                   // C[a_j, a_i(prev)]
+        const T *Cb = Cblk + (b & 1) * kp * BB_M;
+        BB_REL_STAMP(b, 0);
+        // ---- S0a: small tables of this block, apply the previous block ----
+        {
+            if (pt >= BB_NPH - BB_M) {
+                const int t = pt - (BB_NPH - BB_M);
+                const T d = (t < mb) ? Cb[t * kp + ord_s[b * BB_M + t]] : T(1);
+                caa[t] = d;
+                rcaa[t] = T(1) / d;
+            }
+            if (b > 0) {
+                for (int e = pt; e < BB_M * BB_M; e += BB_NPH) {
+                    const int i = e / BB_M, j = e % BB_M;
+                    Cx[e] = Cb[j * kp + ord_s[(b - 1) * BB_M + i]];              // C[a_j, a_i(prev)]
+                }
+                apply_block(b - 1);
+            }
         }
-        if (b > 0) apply_block(b - 1);
-        __syncthreads();
-        BB_STAMP(b, 1);
+        __syncthreads();                    // the shared slice now holds every block before b
+        BB_REL_STAMP(b, 1);
         // ---- S0b: repair the look-ahead product with the previous block's deltas; basis of this block.
         //      item = (4 columns, 4 atoms) ----
-        for (int e = tid; e < 4 * (ncp >> 2); e += BB_THREADS) {
-            const int NQ = ncp >> 2;
+        const T *Rb = Rraw + (b & 1) * BB_M * ncp;
+        for (int e = pt; e < 4 * NQ; e += BB_NPH) {
             const int aq = e / NQ, cq = e % NQ;
             Pair<T> dot[4][2];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const Quad<T> rr = *reinterpret_cast<const Quad<T> *>(Rraw + (4 * aq + u) * ncp + 4 * cq);
+                const Quad<T> rr = *reinterpret_cast<const Quad<T> *>(Rb + (4 * aq + u) * ncp + 4 * cq);
                 dot[u][0].x = rr.x; dot[u][0].y = rr.y; dot[u][1].x = rr.z; dot[u][1].y = rr.w;
             }
             if (b > 0) {
@@ -434,40 +533,45 @@ bcd_blocked_kernel(BcdParams<T> P)
                 *reinterpret_cast<Quad<T> *>(basis + (BB_M + j) * ncp + 4 * cq) = dold;
             }
         }
-        if (tid >= 128) {
-            const int e = tid - 128, t = e / BB_M, j = e % BB_M;
+        for (int e = pt; e < BB_M * BB_M; e += BB_NPH) {
+            const int t = e / BB_M, j = e % BB_M;
             T l = T(0);
             if (j < t && t < mb && caa[t] > T(1e-20)) {
-                const T c1 = Cblk[t * kp + ord_s[b * BB_M + j]], ca = caa[t], rc = rcaa[t];   // C[a_t, a_j]
+                const T c1 = Cb[t * kp + ord_s[b * BB_M + j]], ca = caa[t], rc = rcaa[t];   // C[a_t, a_j]
                 l = c1 * rc;
                 l = fma(fma(-l, ca, c1), rc, l);
             }
             LT[j * BB_M + t] = l;
         }
-        if (tid == 127) {   // arm this block's two exchanges (bytes this CTA will receive)
+        if (pt == BB_NPH - 1) {     // arm this block's two exchanges (bytes this CTA will receive)
             mbar_expect_tx(bar1, (unsigned)(n_owned * nblk * 16 * (int)sizeof(T)));
             mbar_expect_tx(bar2, (unsigned)(BB_GRAM * (int)sizeof(T)));
         }
         __syncthreads();
-        BB_STAMP(b, 2);
-        if (b + 1 < nbk) issue_loads(b + 1);        // Cblk / Brow of block b are consumed
-        // ---- S1: partial Gram of the 32 basis vectors over my columns (4x4 register tiles, 8 column parts), pushed
-        //          tile by tile into the CTA that sums the tile (reduce-scatter over distributed shared memory) ----
+        BB_REL_STAMP(b, 2);
+        // operands ahead: this block's C rows and B rows are consumed
+        if (b + 2 < nbk) load_C(b + 2, pt, BB_NPH);
+        if (b + 1 < nbk) load_B(b + 1, pt, BB_NPH);
+        cp_async_commit();
+        // ---- S1: partial Gram of the 32 basis vectors over my columns: 4x4 register tiles x 8 column parts (288 threads),
+        //          parts combined through shared memory (a warp shuffle costs as much of the shared-memory port as a load,
+        //          and 48 of them per thread were the most expensive part of this phase), then every row of a tile is
+        //          pushed into the CTA that sums the tile (reduce-scatter over distributed shared memory) ----
+        T *gpart = red;                                                         // [8 parts][36 tiles][16]; the scratch is free here
         if (wid < BB_TILES / 4) {
             const int ti = 4 * wid + (lane >> 3), part = lane & 7;
             const int I = tile_i[ti], J = tile_j[ti];
             const Quad<T> *ri = reinterpret_cast<const Quad<T> *>(basis + (4 * I) * ncp);
             const Quad<T> *rj = reinterpret_cast<const Quad<T> *>(basis + (4 * J) * ncp);
-            const int nq = ncp >> 2;                                            // float4 groups per row
             Pair<T> acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int bb = 0; bb < 4; ++bb) acc[a][bb].x = acc[a][bb].y = T(0);
-            for (int f = part; f < nq; f += 8) {
+            for (int f = part; f < NQ; f += 8) {
                 Quad<T> x[4], y[4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) { x[a] = ri[a * nq + f]; y[a] = rj[a * nq + f]; }
+                for (int a = 0; a < 4; ++a) { x[a] = ri[a * NQ + f]; y[a] = rj[a * NQ + f]; }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -476,32 +580,33 @@ bcd_blocked_kernel(BcdParams<T> P)
                         pair_mul_fma(Pair<T>{x[a].z, x[a].w}, Pair<T>{y[bb].z, y[bb].w}, acc[a][bb]);
                     }
             }
-            T out[4][4];
+            T *dst = gpart + ((size_t)part * BB_TILES + ti) * 16;
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int bb = 0; bb < 4; ++bb) {
-                    T v = acc[a][bb].x + acc[a][bb].y;
-                    v += __shfl_xor_sync(kFullMask, v, 1);
-                    v += __shfl_xor_sync(kFullMask, v, 2);
-                    v += __shfl_xor_sync(kFullMask, v, 4);
-                    out[a][bb] = v;
-                }
-            if (part < 4) {         // lane `part` of the tile's group sends row `part` of the tile
-                T q0 = out[0][0], q1 = out[0][1], q2 = out[0][2], q3 = out[0][3];
-#pragma unroll
-                for (int a = 1; a < 4; ++a)
-                    if (part == a) { q0 = out[a][0]; q1 = out[a][1]; q2 = out[a][2]; q3 = out[a][3]; }
-                const int owner = ti % nblk, slot = ti / nblk;
-                const unsigned local = (unsigned)__cvta_generic_to_shared(rsrecv + par * (BB_RS_SLOTS * 16) + ((slot * nblk + g) * 16 + 4 * part));
-                st_async_quad(mapa_u32(local, (unsigned)owner), mapa_u32(bar1, (unsigned)owner), q0, q1, q2, q3);
+            for (int a = 0; a < 4; ++a) {
+                Quad<T> o;
+                o.x = acc[a][0].x + acc[a][0].y; o.y = acc[a][1].x + acc[a][1].y;
+                o.z = acc[a][2].x + acc[a][2].y; o.w = acc[a][3].x + acc[a][3].y;
+                *reinterpret_cast<Quad<T> *>(dst + 4 * a) = o;
             }
+        }
+        __syncthreads();
+        if (tid < BB_TILES * 4) {       // one thread per row of a tile: the eight parts in order, then the push
+            const int ti = tid >> 2, a = tid & 3;
+            Quad<T> sum = *reinterpret_cast<const Quad<T> *>(gpart + (size_t)ti * 16 + 4 * a);
+#pragma unroll
+            for (int part = 1; part < 8; ++part) {
+                const Quad<T> v = *reinterpret_cast<const Quad<T> *>(gpart + ((size_t)part * BB_TILES + ti) * 16 + 4 * a);
+                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            }
+            const int owner = ti % nblk, slot = ti / nblk;
+            const unsigned local = (unsigned)__cvta_generic_to_shared(rsrecv + par * (BB_RS_SLOTS * 16) + ((slot * nblk + g) * 16 + 4 * a));
+            st_async_quad(mapa_u32(local, (unsigned)owner), mapa_u32(bar1, (unsigned)owner), sum.x, sum.y, sum.z, sum.w);
         }
         BB_STAMP(b, 3);
         // ---- S2: the owner of a tile sums its 16 partials (fixed order) and pushes the sums to every CTA (all-gather).
-        //          thread = (row of an owned tile, destination CTA): each sums its four values itself, no hand-over ----
-        if (tid < n_owned * 4 * nblk) {
-            const int qd = tid / nblk, pe = tid % nblk;
+        //          item = (row of an owned tile, destination CTA): each sums its four values itself, no hand-over ----
+        if (pt < n_owned * 4 * nblk) {
+            const int qd = pt / nblk, pe = pt % nblk;
             const int slot = qd >> 2, a = qd & 3;
             mbar_wait(bar1, par);
             const T *rsb = rsrecv + par * (BB_RS_SLOTS * 16);
@@ -518,7 +623,7 @@ bcd_blocked_kernel(BcdParams<T> P)
         mbar_wait(bar2, par);
         BB_STAMP(b, 5);
         // ---- S3: unpack the tiles into the symmetric matrix ----
-        for (int v = tid; v < BB_GRAM; v += BB_THREADS) {
+        for (int v = pt; v < BB_GRAM; v += BB_NPH) {
             const T val = Mflat[v];
             const int ti = v >> 4, a = (v >> 2) & 3, bb = v & 3;
             const int r = 4 * tile_i[ti] + a, c = 4 * tile_j[ti] + bb;
@@ -527,51 +632,92 @@ bcd_blocked_kernel(BcdParams<T> P)
         }
         cp_async_wait_all();
         __syncthreads();
-        BB_STAMP(b, 6);
-        // ---- S4: warp 0 solves the block's scalars; the other warps run the look-ahead product of the next block ----
+        BB_REL_STAMP(b, 6);
+        // ---- S4: the solver warp runs the block's scalar recurrence; warps 0..7 run the look-ahead product of the next
+        //          block meanwhile (the shared slice holds every block before b: what the product wants) ----
+        if (worker && b + 1 < nbk) {
+            if (wstamp) wstamp[4 * b] = clock64();
+            lookahead(b + 1);
+            if (wstamp) wstamp[4 * b + 1] = clock64();
+        }
         if (wid == BB_SOLVER) {
+            // Lane r holds component r of the coefficient vectors.  w_t = A_t - h_t w_{t-1} with h_t = L_{t,t-1} rn_{t-1} and
+            // A_t free of rn_{t-1}, so  |v_t|^2 = <A,GA> - 2 h <A, G w_{t-1}> + h^2 |v_{t-1}|^2 : the two warp reductions of
+            // atom t+1 are issued while the scalar chain of atom t (clamp, rsqrt, Newton) runs, and the per-atom period is
+            // about half of (reduction latency + scalar chain) instead of their sum.
             T Mrow[BB_NB];
 #pragma unroll
             for (int c = 0; c < BB_NB; ++c) Mrow[c] = Mfull[lane * BB_MLD + c];
             // radius of atom t (lane t):  comp_norm_[k] += enet_norm(old row)  [ref: :676-678]; |d_t|^2 is a Gram diagonal
-            const int a_l = ord_s[b * BB_M + (lane & (BB_M - 1))];
-            const T rad_l = cnorm[a_l] + Mfull[(BB_M + (lane & (BB_M - 1))) * BB_MLD + BB_M + (lane & (BB_M - 1))];
+            const int tl = lane & (BB_M - 1);
+            const T rad_l = cnorm[ord_s[b * BB_M + tl]] + Mfull[(BB_M + tl) * BB_MLD + BB_M + tl];
             const T rinv_l = rad_l != T(0) ? T(1) / rad_l : T(0);
-            T wacc[BB_M], yacc[BB_M];      // lane r's component of w_t and of G w_t, accumulated right-looking
+            T wacc[BB_M], yacc[BB_M];      // lane r's component of the pending w_t / G w_t (updates of atoms <= t-2 applied)
 #pragma unroll
             for (int t = 0; t < BB_M; ++t) { wacc[t] = (lane == t) ? T(1) : T(0); yacc[t] = Mrow[t]; }
+            auto bfly2 = [&](T &a, T &c) {
 #pragma unroll
-            for (int t = 0; t < BB_M; ++t) {
-                const T w = wacc[t], y = yacc[t];
-                T n2 = w * y;                                       // |v_t|^2 = w^T G w
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(kFullMask, n2, o);
-                n2 = n2 > T(0) ? n2 : T(0);
-                const T radius = __shfl_sync(kFullMask, rad_l, t), rinv = __shfl_sync(kFullMask, rinv_l, t);
-                const T x = n2 * rinv;
-                const T rs = bcd_rsqrt(x > T(1) ? x : T(1));
+                for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(kFullMask, a, o); c += __shfl_xor_sync(kFullMask, c, o); }
+            };
+            auto scale_of = [&](T n2, int t, T &radius) {
+                radius = __shfl_sync(kFullMask, rad_l, t);
+                const T rinv = __shfl_sync(kFullMask, rinv_l, t);
+                const T n2c = n2 > T(0) ? n2 : T(0);
+                const T x = n2c * rinv;
+                const T rs = bb_rsqrt(x > T(1) ? x : T(1));
                 T rn = x > T(1) ? rs : T(1);                        // v / sqrt(|v|^2 / radius) outside the ball [ref: enet.pyx:62-70]
-                rn = radius == T(0) ? T(0) : rn;                    // [ref: enet.pyx:56-58]
-                const T cf = rn * w;
-                const T dlv = cf - ((lane == BB_M + t) ? T(1) : T(0));       // delta_t = n_t - d_t
-                const T zv = fma(rn, y, -Mrow[BB_M + t]);                    // G delta_t
+                return radius == T(0) ? T(0) : rn;                  // [ref: enet.pyx:56-58]
+            };
+            // atom 0
+            T wp = wacc[0], yp = yacc[0];                           // w_{t-1}, G w_{t-1}
+            T n2p, dummy = T(0);
+            n2p = wp * yp;
+            bfly2(n2p, dummy);
+            T radius;
+            T rnp = scale_of(n2p, 0, radius);
+            if (g == 0 && lane == 0 && 0 < mb) P.comp_norm[ord_s[b * BB_M]] = radius - (rnp * rnp) * (n2p > T(0) ? n2p : T(0));
+            T lnext = LT[0 * BB_M + 1];                             // L_{1,0}
+            T A = wacc[1] + ((lane == BB_M + 0) ? lnext : T(0));
+            T Ay = fma(lnext, Mrow[BB_M + 0], yacc[1]);
+            T S0 = A * Ay, S1 = A * yp;
+            bfly2(S0, S1);
 #pragma unroll
-                for (int t2 = t + 1; t2 < BB_M; ++t2) {
-                    const T l = LT[t * BB_M + t2];                           // L_{t2, t}
+            for (int t = 1; t < BB_M; ++t) {
+                const T h = lnext * rnp;                            // L_{t,t-1} rn_{t-1}
+                const T n2 = fma(h, fma(h, n2p, T(-2) * S1), S0);   // |v_t|^2
+                const T w = fma(-h, wp, A), y = fma(-h, yp, Ay);    // w_t, G w_t
+                // the previous atom is final: its coefficients, its delta, and the lagging right-looking update
+                const T cfp = rnp * wp;
+                coef[(t - 1) * BB_NB + lane] = cfp;
+                const T dlv = cfp - ((lane == BB_M + t - 1) ? T(1) : T(0));      // delta_{t-1} = n_{t-1} - d_{t-1}
+                const T zv = fma(rnp, yp, -Mrow[BB_M + t - 1]);                  // G delta_{t-1}
+                T An = T(0), Ayn = T(0), ln = T(0);
+                if (t + 1 < BB_M) {
+                    const T l2 = LT[(t - 1) * BB_M + t + 1];                     // L_{t+1,t-1}
+                    wacc[t + 1] = fma(-l2, dlv, wacc[t + 1]);
+                    yacc[t + 1] = fma(-l2, zv, yacc[t + 1]);
+                    ln = LT[t * BB_M + t + 1];                                   // L_{t+1,t}
+                    An = wacc[t + 1] + ((lane == BB_M + t) ? ln : T(0));
+                    Ayn = fma(ln, Mrow[BB_M + t], yacc[t + 1]);
+                    S0 = An * Ayn; S1 = An * y;
+                    bfly2(S0, S1);                                               // reductions of atom t+1, in flight
+                }
+                T radius_t;
+                const T rn = scale_of(n2, t, radius_t);
+                if (g == 0 && lane == 0 && t < mb)                               // comp_norm_[k] -= enet_norm(new row) [ref: :690-692]
+                    P.comp_norm[ord_s[b * BB_M + t]] = radius_t - (rn * rn) * (n2 > T(0) ? n2 : T(0));
+#pragma unroll
+                for (int t2 = t + 2; t2 < BB_M; ++t2) {
+                    const T l = LT[(t - 1) * BB_M + t2];                         // L_{t2, t-1}
                     wacc[t2] = fma(-l, dlv, wacc[t2]);
                     yacc[t2] = fma(-l, zv, yacc[t2]);
                 }
-                coef[t * BB_NB + lane] = cf;
-                // comp_norm_[k] -= enet_norm(new row) [ref: :690-692]: |n_t|^2 = rn^2 |v_t|^2 (the same value in every CTA)
-                if (g == 0 && lane == 0 && t < mb) P.comp_norm[ord_s[b * BB_M + t]] = radius - (rn * rn) * n2;
+                wp = w; yp = y; n2p = n2; rnp = rn; A = An; Ay = Ayn; lnext = ln;
             }
+            coef[(BB_M - 1) * BB_NB + lane] = rnp * wp;
             if (sstamp) sstamp[(int64_t)b * 8 + 7] = clock64();
-        } else if (b + 1 < nbk) {
-            if (wstamp) wstamp[2 * b] = clock64();
-            lookahead();
-            if (wstamp) wstamp[2 * b + 1] = clock64();
         }
-        __syncthreads();
+        __syncthreads();                    // coefficients, look-ahead product of block b+1, operands of blocks b+1 / b+2
     }
     if (stamp) stamp[(int64_t)8 * k + 3] = clock64();
     apply_block(nbk - 1);
@@ -602,6 +748,7 @@ bcd_blocked_kernel(BcdParams<T> P)
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     if (stamp) stamp[(int64_t)8 * k + 7] = stamp[(int64_t)8 * k + 6] = clock64();
 #undef BB_STAMP
+#undef BB_REL_STAMP
 }
 
 }  // namespace modl

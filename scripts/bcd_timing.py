@@ -40,15 +40,16 @@ for name, blocked, pipe in (("blocked", 1, 1), ("pipelined pilot", 0, 1), ("pilo
         nxt = np.concatenate([ph[1:, 0], [g[3]]])              # start of the next block = end of S4 (after its barrier)
         iv = np.column_stack([np.diff(ph[:, :8], axis=1), nxt - ph[:, 6]])[1:-1]     # blocks 1 .. nbk-2
         names = ["S0a tables+apply", "S0b repair+basis", "S1 loads+gram+push", "S2a reduce-scatter wait+sum+push",
-                 "S2b all-gather wait", "S3 unpack", "S4 solver alone", "S4 whole (solver | look-ahead)"]
-        la = np.array([st[8 * K + 16 + 2 * b + 1] - st[8 * K + 16 + 2 * b] for b in range(1, nbk - 1)])
+                 "S2b all-gather wait", "S3 unpack", "S4 solver", "S4 + wait for the workers"]
+        W = 8 * K + 16
+        la = np.array([st[W + 4 * b + 1] - st[W + 4 * b] for b in range(1, nbk - 1)])
         print(name, "| kernel %d cycles: loads %d, first product %d, blocks %d, last apply %d, norms+write-back %d, "
               "fence+cluster barrier %d, comp_norm %d" % (g[7] - g[0], g[1] - g[0], g[2] - g[1], g[3] - g[2], g[4] - g[3],
                                                           g[5] - g[4], g[6] - g[5], g[7] - g[6]))
         per_block = (ph[-1, 0] - ph[1, 0]) / (nbk - 2)
         print("   cycles per block of 16: %.0f  (%.0f per atom)" % (per_block, per_block / 16))
         print("   phases (mean over blocks 1..%d):" % (nbk - 2), {n: int(round(v)) for n, v in zip(names, list(iv.mean(axis=0)))},
-              "look-ahead (warp 1) %d" % la.mean())
+              "look-ahead of the next block (worker warps) %d" % la.mean())
     else:
         t0 = [st[8 * t] for t in range(K)]
         per = (t0[K - 1] - t0[8]) / (K - 9)
