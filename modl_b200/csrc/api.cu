@@ -57,6 +57,7 @@ static int ctx_init(modl_ctx *c, int device)
     MODL_CUDA_TRY(cudaDeviceGetAttribute(&c->cluster_ok, cudaDevAttrClusterLaunch, device));
     if (const char *e = getenv("MODL_BCD_CLUSTER")) c->opt_bcd_cluster = atoi(e);
     if (const char *e = getenv("MODL_BCD_BLOCKED")) c->opt_bcd_blocked = atoi(e);
+    if (const char *e = getenv("MODL_TC_RAW_B")) c->opt_tc_raw_b = atoi(e);
     if (const char *e = getenv("MODL_BCD_PIPELINE")) c->opt_bcd_pipeline = atoi(e);
     if (const char *e = getenv("MODL_CD_WARPS")) c->opt_cd_warps = atoi(e);
     if (const char *e = getenv("MODL_FORCE_GLOBAL_GRAM")) c->opt_force_global_gram = atoi(e);
@@ -112,6 +113,7 @@ int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "bcd_pilot")) ctx->opt_bcd_pilot = value;
     else if (!strcmp(name, "bcd_pipeline")) ctx->opt_bcd_pipeline = value;
     else if (!strcmp(name, "bcd_blocked")) ctx->opt_bcd_blocked = value;
+    else if (!strcmp(name, "tc_raw_b")) ctx->opt_tc_raw_b = value;
     else if (!strcmp(name, "bcd_coop_min_cols")) ctx->opt_bcd_coop_min_cols = value;
     else if (!strcmp(name, "bcd_flag_barrier")) ctx->opt_bcd_flag_barrier = value;
     else { set_error("unknown option %s", name); return MODL_EINVAL; }
@@ -581,6 +583,11 @@ static int stats_b_impl(modl_ctx *ctx, const T *cb, const T *X, int64_t ldx, T *
                 codeP = cp;
             }
             const int bn = tc_pick_bn(ctx, p, ceil_div(k, 128), sm_avail);
+            if (ctx->opt_tc_raw_b) {
+                // X straight from its rows: the GEMM's own warps split it into the TF32 hi / lo operand in shared memory
+                (void)XP;
+                return tc_gemm(ctx, codeP, nullptr, k, p, b, a, be, out, ldo, bn, st, WS_GEMM_PART2, nullptr, 0, 0, 0, X, ldx);
+            }
             MODL_TRY(ws<float>(ctx, WS_TC_X, tc_packed_elems(p, b, bn), &XP));
             MODL_TRY(tc_pack_cols(ctx, X, ldx, b, p, XP, bn, st));
             return tc_gemm(ctx, codeP, XP, k, p, b, a, be, out, ldo, bn, st, WS_GEMM_PART2);

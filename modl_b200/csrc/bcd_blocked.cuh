@@ -70,6 +70,18 @@ __device__ __forceinline__ void pair_mul_fma(const Pair<double> &a, const Pair<d
 {
     acc.x = fma(a.x, b.x, acc.x); acc.y = fma(a.y, b.y, acc.y);
 }
+// TMA bulk copies: global -> shared (completes bytes on an mbarrier), shared -> global (bulk group)
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned bar)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, unsigned bytes)
+{
+    const unsigned src = (unsigned)__cvta_generic_to_shared(smem_src);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(src), "r"(bytes) : "memory");
+}
 // four values into a peer's shared memory, completing their bytes on the PEER's mbarrier (one-way, no fences)
 __device__ __forceinline__ void st_async_quad(unsigned remote, unsigned remote_mbar, float a, float b, float c, float d)
 {
@@ -145,10 +157,12 @@ bcd_blocked_kernel(BcdParams<T> P)
     T *rsrecv = Mflat + BB_GRAM;                             // [2][slot][sender][16] partial tiles this CTA sums, by block parity
     T *red = rsrecv + 2 * BB_RS_SLOTS * 16;                  // scratch of the look-ahead product
     int *ord_s = reinterpret_cast<int *>(red + BB_RED_CAP);  // [kp] update order
-    __shared__ __align__(8) unsigned long long xbar[2];      // [0] reduce-scatter arrivals, [1] all-gather arrivals
+    __shared__ __align__(8) unsigned long long xbar[3];      // [0] reduce-scatter arrivals, [1] all-gather arrivals, [2] operand copies
     __shared__ unsigned char tile_i[BB_TILES], tile_j[BB_TILES];
     const unsigned bar1 = (unsigned)__cvta_generic_to_shared(&xbar[0]);
     const unsigned bar2 = bar1 + 8;
+    const unsigned ldbar = bar1 + 16;
+    unsigned ld_batches = 0;                                  // operand batches issued so far (phase of ldbar)
     const int n_owned = (BB_TILES - g + nblk - 1) / nblk;    // tiles ti with ti % nblk == g  (g < nblk <= 16 < 36)
 
     // debug stamps of CTA 0.  First phase thread: [b][0..6]; lane 0 of the solver warp: [b][7] = solver done;
@@ -167,12 +181,17 @@ bcd_blocked_kernel(BcdParams<T> P)
     const bool c_vec = (k % VE == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
     const bool p_vec = (lds % VE == 0) && (c0 % VE == 0) && ((reinterpret_cast<uintptr_t>(P.Dp) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(P.Bp) & 15) == 0);
+    // whole rows move with TMA bulk copies (one instruction per row) when every row start and length is 16-byte aligned
+    const bool bulk = c_vec && p_vec && nc > 0 && (nc % VE == 0);
+    const unsigned row_bytes = (unsigned)nc * (unsigned)sizeof(T), crow_bytes = (unsigned)k * (unsigned)sizeof(T);
 
     // asynchronous operand copies, spread over `nth` threads (index `t`): C[a_j, :] of block bc, B_sub rows of block bb
     auto load_C = [&](int bc, int t, int nth) {
         const int mb = min(BB_M, k - bc * BB_M);
         T *dstC = Cblk + (bc & 1) * kp * BB_M;
-        if (c_vec) {
+        if (bulk) {
+            if (t < mb) bulk_g2s(dstC + t * kp, P.C + (int64_t)ord_s[bc * BB_M + t] * k, crow_bytes, ldbar);
+        } else if (c_vec) {
             const int nv = k / VE;
             for (int e = t; e < BB_M * nv; e += nth) {
                 const int j = e / nv, iv = (e % nv) * VE;
@@ -188,6 +207,11 @@ bcd_blocked_kernel(BcdParams<T> P)
     auto load_B = [&](int bb, int t, int nth) {
         const int mb = min(BB_M, k - bb * BB_M);
         const int nvb = ncp / VE;
+        if (bulk) {         // (the padding columns were zeroed once in the prologue)
+            const int j = t - 32;
+            if (j >= 0 && j < mb) bulk_g2s(Brow + j * ncp, P.Bp + (int64_t)ord_s[bb * BB_M + j] * lds + c0, row_bytes, ldbar);
+            return;
+        }
         for (int e = t; e < BB_M * nvb; e += nth) {
             const int j = e / nvb, cv = (e % nvb) * VE;
             T *dst = Brow + j * ncp + cv;
@@ -203,12 +227,28 @@ bcd_blocked_kernel(BcdParams<T> P)
         }
     };
 
+    // one batch of operand copies = one phase of ldbar (bulk mode) or one cp.async group (otherwise)
+    auto arm_batch = [&](unsigned bytes) {
+        if (bulk && tid == 0) mbar_expect_tx(ldbar, bytes);
+    };
+    auto wait_batch = [&]() {
+        if (bulk) { mbar_wait(ldbar, ld_batches & 1u); }
+        else cp_async_wait_all();
+        ld_batches += 1;
+    };
+
     // ---- prologue: D slice (asynchronous copies), norms, order, tables ----
     for (int i = tid; i < kp; i += BB_THREADS) {
         cnorm[i] = i < k ? P.comp_norm[i] : T(0);
         ord_s[i] = i < k ? P.order[i] : 0;
     }
-    {
+    if (bulk) {
+        for (int e = tid; e < k * (ncp - nc); e += BB_THREADS) {                // padding columns of the slice and of the B rows
+            const int i = e / (ncp - nc), c = nc + e % (ncp - nc);
+            Ds[i * ncp + c] = T(0);
+            if (i < BB_M) Brow[i * ncp + c] = T(0);
+        }
+    } else {
         const T *Dg = P.Dp + c0;
         const int nv = ncp / VE;
         for (int e = tid; e < k * nv; e += BB_THREADS) {
@@ -238,9 +278,17 @@ bcd_blocked_kernel(BcdParams<T> P)
     if (tid == 0) {
         mbar_init(bar1, 1);
         mbar_init(bar2, 1);
+        mbar_init(ldbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the zero fills above precede the bulk copies below
     __syncthreads();                        // ord_s, zeroed Cblk
+    {
+        const int mb0 = min(BB_M, k), mb1 = nbk > 1 ? min(BB_M, k - BB_M) : 0;
+        arm_batch((unsigned)k * row_bytes + (unsigned)(mb0 + mb1) * crow_bytes + (unsigned)mb0 * row_bytes);
+        if (bulk)
+            for (int i = tid; i < k; i += BB_THREADS) bulk_g2s(Ds + i * ncp, P.Dp + (int64_t)i * lds + c0, row_bytes, ldbar);
+    }
     load_C(0, tid, BB_THREADS);
     if (nbk > 1) load_C(1, tid, BB_THREADS);
     load_B(0, tid, BB_THREADS);
@@ -249,7 +297,7 @@ bcd_blocked_kernel(BcdParams<T> P)
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     if (g == 0 && tid == 0) bcd_signal_start(P);
-    cp_async_wait_all();
+    wait_batch();
     __syncthreads();
     if (stamp) stamp[(int64_t)8 * k + 1] = clock64();
 
@@ -550,9 +598,14 @@ bcd_blocked_kernel(BcdParams<T> P)
         __syncthreads();
         BB_REL_STAMP(b, 2);
         // operands ahead: this block's C rows and B rows are consumed
-        if (b + 2 < nbk) load_C(b + 2, pt, BB_NPH);
-        if (b + 1 < nbk) load_B(b + 1, pt, BB_NPH);
-        cp_async_commit();
+        const bool batch = b + 1 < nbk;
+        if (batch) {
+            arm_batch((b + 2 < nbk ? (unsigned)min(BB_M, k - (b + 2) * BB_M) * crow_bytes : 0u) +
+                      (unsigned)min(BB_M, k - (b + 1) * BB_M) * row_bytes);
+            if (b + 2 < nbk) load_C(b + 2, pt, BB_NPH);
+            load_B(b + 1, pt, BB_NPH);
+            cp_async_commit();
+        }
         // ---- S1: partial Gram of the 32 basis vectors over my columns: 4x4 register tiles x 8 column parts (288 threads),
         //          parts combined through shared memory (a warp shuffle costs as much of the shared-memory port as a load,
         //          and 48 of them per thread were the most expensive part of this phase), then every row of a tile is
@@ -630,7 +683,7 @@ bcd_blocked_kernel(BcdParams<T> P)
             Mfull[r * BB_MLD + c] = val;
             if (tile_i[ti] != tile_j[ti]) Mfull[c * BB_MLD + r] = val;
         }
-        cp_async_wait_all();
+        if (batch) wait_batch();
         __syncthreads();
         BB_REL_STAMP(b, 6);
         // ---- S4: the solver warp runs the block's scalar recurrence; warps 0..7 run the look-ahead product of the next
@@ -721,11 +774,16 @@ bcd_blocked_kernel(BcdParams<T> P)
     }
     if (stamp) stamp[(int64_t)8 * k + 3] = clock64();
     apply_block(nbk - 1);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the rows written above are read by the bulk stores
     __syncthreads();
     if (stamp) stamp[(int64_t)8 * k + 4] = clock64();
 
     // ---- epilogue: write the slice back ----
-    if (p_vec) {
+    if (bulk) {
+        for (int i = tid; i < k; i += BB_THREADS) bulk_s2g(P.Dp + (int64_t)i * lds + c0, Ds + i * ncp, row_bytes);
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+    } else if (p_vec) {
         const int nv = ncp / VE;
         for (int e = tid; e < k * nv; e += BB_THREADS) {
             const int i = e / nv, cv = (e % nv) * VE;

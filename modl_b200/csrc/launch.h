@@ -57,6 +57,7 @@ int tc_pack_cols(modl_ctx *ctx, const float *src, int64_t ld, int64_t kd, int64_
 // bn = accumulator tile width = rows per block of the packed B operand (multiple of 16, <= 256)
 int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M, int64_t N, int64_t Kd, float alpha,
             float beta, float *C, int64_t ldc, int bn, cudaStream_t st, WsSlot part_slot = WS_GEMM_PART,
-            float *C2 = nullptr, int64_t ldc2 = 0, int64_t n_split = 0, int64_t N1 = 0);
+            float *C2 = nullptr, int64_t ldc2 = 0, int64_t n_split = 0, int64_t N1 = 0, const float *Braw = nullptr,
+            int64_t ldb_raw = 0);
 
 }  // namespace modl

@@ -50,13 +50,15 @@ int tc_pack_cols(modl_ctx *ctx, const float *src, int64_t ld, int64_t kd, int64_
 
 int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M, int64_t N, int64_t Kd, float alpha,
             float beta, float *C, int64_t ldc, int bn, cudaStream_t st, WsSlot part_slot, float *C2, int64_t ldc2,
-            int64_t n_split, int64_t N1)
+            int64_t n_split, int64_t N1, const float *Braw, int64_t ldb_raw)
 {
     if (M <= 0 || N <= 0) return MODL_OK;
     MODL_REQUIRE(Kd >= 1, "tc_gemm needs a non-empty contraction");
     MODL_REQUIRE(bn >= 16 && bn <= TC_MAX_BN && bn % 16 == 0, "tc_gemm tile width");
     TcGemmParams P;
     P.A = Apacked; P.B = Bpacked; P.C = C; P.ldc = ldc; P.M = (int)M; P.N = (int)N;
+    MODL_REQUIRE((Bpacked != nullptr) != (Braw != nullptr), "tc_gemm takes the B operand packed or raw");
+    P.Braw = Braw; P.ldb_raw = ldb_raw; P.Kd = (int)Kd;
     P.nkb = (int)tc_k_blocks(Kd);
     P.alpha = alpha; P.beta = beta;
     P.sbo = 128u;

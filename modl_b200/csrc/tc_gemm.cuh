@@ -274,13 +274,21 @@ struct TcGemmParams {
     float *C2;
     int64_t ldc2;
     int n_split, N1, N2;
+    // optional RAW B operand (B == NULL): Braw is the row-major source whose COLUMNS are the operand rows,
+    // op[n, kk] = Braw[kk * ldb_raw + n] (kk < Kd, n < N) -- e.g. the batch X of  B_ += code^T X.  The four epilogue
+    // warps then build every B block in shared memory themselves (coalesced loads along n, hi/lo TF32 split in
+    // registers, the same 16-byte units the pack kernel writes), so the 8-byte-per-element packed copy of X never
+    // goes through HBM.
+    const float *Braw;
+    int64_t ldb_raw;
+    int Kd;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(TcGemmParams P)
 {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
-    __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_STAGES + 1];
+    __shared__ __align__(8) unsigned long long bars[3 * TC_MAX_STAGES + 1];
     __shared__ unsigned tmem_base_s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(tc_smem) + 1023u) & ~1023u;
@@ -288,6 +296,8 @@ tc_gemm_kernel(TcGemmParams P)
     auto full_bar = [&](int s) { return bar0 + 8u * (unsigned)s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (unsigned)(TC_MAX_STAGES + s); };
     const unsigned done_bar = bar0 + 8u * (unsigned)(2 * TC_MAX_STAGES);
+    auto fullb_bar = [&](int s) { return bar0 + 8u * (unsigned)(2 * TC_MAX_STAGES + 1 + s); };   // raw-B blocks converted
+    const bool rawB = P.Braw != nullptr;
     const int STAGES = P.stages;
     const unsigned a_bytes = TC_BLOCK_BYTES, b_half = (unsigned)P.bn * TC_BK * 4u, b_bytes = 2u * b_half;
     const unsigned stage_bytes = a_bytes + b_bytes;
@@ -299,7 +309,9 @@ tc_gemm_kernel(TcGemmParams P)
     const int nk = kb1 - kb0;                 // >= 1 by construction of the grid
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { tc_mbar_init(full_bar(s), 1); tc_mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < STAGES; ++s) {
+            tc_mbar_init(full_bar(s), 1); tc_mbar_init(empty_bar(s), 1); tc_mbar_init(fullb_bar(s), TC_THREADS - 64);
+        }
         tc_mbar_init(done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -318,10 +330,10 @@ tc_gemm_kernel(TcGemmParams P)
                 const int s = i % STAGES;
                 const unsigned ph = (unsigned)(i / STAGES) & 1u;
                 tc_mbar_wait(empty_bar(s), ph ^ 1u);                 // slot free (first pass: immediately)
-                tc_mbar_expect_tx(full_bar(s), stage_bytes);
+                tc_mbar_expect_tx(full_bar(s), rawB ? a_bytes : stage_bytes);
                 const unsigned sa = smem0 + (unsigned)s * stage_bytes;
                 tc_bulk_g2s(sa, Ab + (size_t)i * TC_BLOCK_FLOATS, a_bytes, full_bar(s));
-                tc_bulk_g2s(sa + a_bytes, Bb + (size_t)i * b_block_floats, b_bytes, full_bar(s));
+                if (!rawB) tc_bulk_g2s(sa + a_bytes, Bb + (size_t)i * b_block_floats, b_bytes, full_bar(s));
             }
         }
     } else if (warp == 1) {
@@ -333,6 +345,7 @@ tc_gemm_kernel(TcGemmParams P)
                 const int s = i % STAGES;
                 const unsigned ph = (unsigned)(i / STAGES) & 1u;
                 tc_mbar_wait(full_bar(s), ph);
+                if (rawB) tc_mbar_wait(fullb_bar(s), ph);
                 tc_fence_after();
                 const unsigned sa = smem0 + (unsigned)s * stage_bytes;            // A: hi | lo
                 const unsigned sb = sa + a_bytes;                                 // B: hi | lo
@@ -359,6 +372,48 @@ tc_gemm_kernel(TcGemmParams P)
         // touch 32 different rows per warp instruction.  The operand stages are free once the
         // last MMA has completed, so the tile is staged there and written out row by row, one
         // 512-byte segment per warp instruction (and C is read the same way when beta != 0).
+        if (rawB) {
+            // ===== converters: the B block of every stage, straight from the raw source =====
+            // unit (n, c) = the four contraction elements 4c..4c+3 of operand row n; consecutive threads take consecutive n
+            // (128-byte coalesced loads of four source rows, conflict-free 16-byte shared stores)
+            const int ct = (int)threadIdx.x - 64, bn = P.bn;
+            const int n_base = nb * bn;
+            const int nunits = bn * TC_CHUNKS;
+            constexpr int NCT = TC_THREADS - 64;
+            constexpr int UMAX = (TC_MAX_BN * TC_CHUNKS + NCT - 1) / NCT;      // units per thread at the widest tile
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % STAGES;
+                const unsigned ph = (unsigned)(i / STAGES) & 1u;
+                const int kk0 = (kb0 + i) * TC_BK;
+                float v[UMAX][4];
+                // every load of the block in flight before the first conversion
+#pragma unroll
+                for (int u = 0; u < UMAX; ++u) {
+                    const int e = ct + u * NCT;
+                    const int c = e / bn, n = e - c * bn;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const int kk = kk0 + 4 * c + w;
+                        v[u][w] = (e < nunits && n_base + n < P.N && kk < P.Kd) ? __ldg(P.Braw + (int64_t)kk * P.ldb_raw + n_base + n) : 0.f;
+                    }
+                }
+                tc_mbar_wait(empty_bar(s), ph ^ 1u);                 // the MMAs that read this slot are done
+                const unsigned sb = smem0 + (unsigned)s * stage_bytes + a_bytes;
+#pragma unroll
+                for (int u = 0; u < UMAX; ++u) {
+                    const int e = ct + u * NCT;
+                    if (e < nunits) {
+                        float4 h, l;
+                        tc_split(v[u][0], h.x, l.x); tc_split(v[u][1], h.y, l.y); tc_split(v[u][2], h.z, l.z); tc_split(v[u][3], h.w, l.w);
+                        const unsigned dst = sb + 16u * (unsigned)e;             // (c * bn + n) * 16 bytes
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + b_half), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic stores -> visible to the tensor core
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(fullb_bar(s)) : "memory");
+            }
+        }
         tc_mbar_wait(done_bar, 0);
         tc_fence_after();
         const int q = warp & 3;                        // TMEM lane quadrant this warp may read
