@@ -607,24 +607,24 @@ bcd_blocked_kernel(BcdParams<T> P)
             cp_async_commit();
         }
         // ---- S1: partial Gram of the 32 basis vectors over my columns: 4x4 register tiles x 8 column parts (288 threads),
-        //          parts combined through shared memory (a warp shuffle costs as much of the shared-memory port as a load,
-        //          and 48 of them per thread were the most expensive part of this phase), then every row of a tile is
-        //          pushed into the CTA that sums the tile (reduce-scatter over distributed shared memory) ----
-        T *gpart = red;                                                         // [8 parts][36 tiles][16]; the scratch is free here
+        //          parts combined with three shuffle levels (measured against a shared-memory combine + block barrier on the
+        //          same box: 2 980 vs 3 670 cycles for the phase), then lane `part` of a tile's group pushes row `part` of
+        //          the tile into the CTA that sums the tile (reduce-scatter over distributed shared memory) ----
         if (wid < BB_TILES / 4) {
             const int ti = 4 * wid + (lane >> 3), part = lane & 7;
             const int I = tile_i[ti], J = tile_j[ti];
             const Quad<T> *ri = reinterpret_cast<const Quad<T> *>(basis + (4 * I) * ncp);
             const Quad<T> *rj = reinterpret_cast<const Quad<T> *>(basis + (4 * J) * ncp);
+            const int nq = ncp >> 2;                                            // float4 groups per row
             Pair<T> acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int bb = 0; bb < 4; ++bb) acc[a][bb].x = acc[a][bb].y = T(0);
-            for (int f = part; f < NQ; f += 8) {
+            for (int f = part; f < nq; f += 8) {
                 Quad<T> x[4], y[4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) { x[a] = ri[a * NQ + f]; y[a] = rj[a * NQ + f]; }
+                for (int a = 0; a < 4; ++a) { x[a] = ri[a * nq + f]; y[a] = rj[a * nq + f]; }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -633,27 +633,26 @@ bcd_blocked_kernel(BcdParams<T> P)
                         pair_mul_fma(Pair<T>{x[a].z, x[a].w}, Pair<T>{y[bb].z, y[bb].w}, acc[a][bb]);
                     }
             }
-            T *dst = gpart + ((size_t)part * BB_TILES + ti) * 16;
+            T out[4][4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                Quad<T> o;
-                o.x = acc[a][0].x + acc[a][0].y; o.y = acc[a][1].x + acc[a][1].y;
-                o.z = acc[a][2].x + acc[a][2].y; o.w = acc[a][3].x + acc[a][3].y;
-                *reinterpret_cast<Quad<T> *>(dst + 4 * a) = o;
-            }
-        }
-        __syncthreads();
-        if (tid < BB_TILES * 4) {       // one thread per row of a tile: the eight parts in order, then the push
-            const int ti = tid >> 2, a = tid & 3;
-            Quad<T> sum = *reinterpret_cast<const Quad<T> *>(gpart + (size_t)ti * 16 + 4 * a);
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int part = 1; part < 8; ++part) {
-                const Quad<T> v = *reinterpret_cast<const Quad<T> *>(gpart + ((size_t)part * BB_TILES + ti) * 16 + 4 * a);
-                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                for (int bb = 0; bb < 4; ++bb) {
+                    T v = acc[a][bb].x + acc[a][bb].y;
+                    v += __shfl_xor_sync(kFullMask, v, 1);
+                    v += __shfl_xor_sync(kFullMask, v, 2);
+                    v += __shfl_xor_sync(kFullMask, v, 4);
+                    out[a][bb] = v;
+                }
+            if (part < 4) {         // lane `part` of the tile's group sends row `part` of the tile
+                T q0 = out[0][0], q1 = out[0][1], q2 = out[0][2], q3 = out[0][3];
+#pragma unroll
+                for (int a = 1; a < 4; ++a)
+                    if (part == a) { q0 = out[a][0]; q1 = out[a][1]; q2 = out[a][2]; q3 = out[a][3]; }
+                const int owner = ti % nblk, slot = ti / nblk;
+                const unsigned local = (unsigned)__cvta_generic_to_shared(rsrecv + par * (BB_RS_SLOTS * 16) + ((slot * nblk + g) * 16 + 4 * part));
+                st_async_quad(mapa_u32(local, (unsigned)owner), mapa_u32(bar1, (unsigned)owner), q0, q1, q2, q3);
             }
-            const int owner = ti % nblk, slot = ti / nblk;
-            const unsigned local = (unsigned)__cvta_generic_to_shared(rsrecv + par * (BB_RS_SLOTS * 16) + ((slot * nblk + g) * 16 + 4 * a));
-            st_async_quad(mapa_u32(local, (unsigned)owner), mapa_u32(bar1, (unsigned)owner), sum.x, sum.y, sum.z, sum.w);
         }
         BB_STAMP(b, 3);
         // ---- S2: the owner of a tile sums its 16 partials (fixed order) and pushes the sums to every CTA (all-gather).
@@ -687,87 +686,54 @@ bcd_blocked_kernel(BcdParams<T> P)
         __syncthreads();
         BB_REL_STAMP(b, 6);
         // ---- S4: the solver warp runs the block's scalar recurrence; warps 0..7 run the look-ahead product of the next
-        //          block meanwhile (the shared slice holds every block before b: what the product wants) ----
+        //          block meanwhile (the shared slice holds every block before b: what the product wants).
+        //          Solver: lane r holds component r of the coefficient vectors; w_t and G w_t are kept up to date for every
+        //          pending atom by a right-looking rank-1 update, so the dependent chain of an atom is one warp reduction
+        //          (five shuffle levels), the clamp, one rsqrt + Newton step and two FMAs.  (A variant that moved the
+        //          reduction off the chain with the three-term expansion of |v_t|^2 -- two reductions in flight, as in the
+        //          pilot kernel -- was slower in place: 8 650 vs 7 370 cycles per block; a warp issues in order, so the
+        //          second reduction's shuffles queue in front of the scalar chain instead of beside it.) ----
         if (worker && b + 1 < nbk) {
             if (wstamp) wstamp[4 * b] = clock64();
             lookahead(b + 1);
             if (wstamp) wstamp[4 * b + 1] = clock64();
         }
         if (wid == BB_SOLVER) {
-            // Lane r holds component r of the coefficient vectors.  w_t = A_t - h_t w_{t-1} with h_t = L_{t,t-1} rn_{t-1} and
-            // A_t free of rn_{t-1}, so  |v_t|^2 = <A,GA> - 2 h <A, G w_{t-1}> + h^2 |v_{t-1}|^2 : the two warp reductions of
-            // atom t+1 are issued while the scalar chain of atom t (clamp, rsqrt, Newton) runs, and the per-atom period is
-            // about half of (reduction latency + scalar chain) instead of their sum.
             T Mrow[BB_NB];
 #pragma unroll
             for (int c = 0; c < BB_NB; ++c) Mrow[c] = Mfull[lane * BB_MLD + c];
             // radius of atom t (lane t):  comp_norm_[k] += enet_norm(old row)  [ref: :676-678]; |d_t|^2 is a Gram diagonal
-            const int tl = lane & (BB_M - 1);
-            const T rad_l = cnorm[ord_s[b * BB_M + tl]] + Mfull[(BB_M + tl) * BB_MLD + BB_M + tl];
+            const int a_l = ord_s[b * BB_M + (lane & (BB_M - 1))];
+            const T rad_l = cnorm[a_l] + Mfull[(BB_M + (lane & (BB_M - 1))) * BB_MLD + BB_M + (lane & (BB_M - 1))];
             const T rinv_l = rad_l != T(0) ? T(1) / rad_l : T(0);
-            T wacc[BB_M], yacc[BB_M];      // lane r's component of the pending w_t / G w_t (updates of atoms <= t-2 applied)
+            T wacc[BB_M], yacc[BB_M];      // lane r's component of w_t and of G w_t, accumulated right-looking
 #pragma unroll
             for (int t = 0; t < BB_M; ++t) { wacc[t] = (lane == t) ? T(1) : T(0); yacc[t] = Mrow[t]; }
-            auto bfly2 = [&](T &a, T &c) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(kFullMask, a, o); c += __shfl_xor_sync(kFullMask, c, o); }
-            };
-            auto scale_of = [&](T n2, int t, T &radius) {
-                radius = __shfl_sync(kFullMask, rad_l, t);
-                const T rinv = __shfl_sync(kFullMask, rinv_l, t);
-                const T n2c = n2 > T(0) ? n2 : T(0);
-                const T x = n2c * rinv;
+            for (int t = 0; t < BB_M; ++t) {
+                const T w = wacc[t], y = yacc[t];
+                T n2 = w * y;                                       // |v_t|^2 = w^T G w
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(kFullMask, n2, o);
+                n2 = n2 > T(0) ? n2 : T(0);
+                const T radius = __shfl_sync(kFullMask, rad_l, t), rinv = __shfl_sync(kFullMask, rinv_l, t);
+                const T x = n2 * rinv;
                 const T rs = bb_rsqrt(x > T(1) ? x : T(1));
                 T rn = x > T(1) ? rs : T(1);                        // v / sqrt(|v|^2 / radius) outside the ball [ref: enet.pyx:62-70]
-                return radius == T(0) ? T(0) : rn;                  // [ref: enet.pyx:56-58]
-            };
-            // atom 0
-            T wp = wacc[0], yp = yacc[0];                           // w_{t-1}, G w_{t-1}
-            T n2p, dummy = T(0);
-            n2p = wp * yp;
-            bfly2(n2p, dummy);
-            T radius;
-            T rnp = scale_of(n2p, 0, radius);
-            if (g == 0 && lane == 0 && 0 < mb) P.comp_norm[ord_s[b * BB_M]] = radius - (rnp * rnp) * (n2p > T(0) ? n2p : T(0));
-            T lnext = LT[0 * BB_M + 1];                             // L_{1,0}
-            T A = wacc[1] + ((lane == BB_M + 0) ? lnext : T(0));
-            T Ay = fma(lnext, Mrow[BB_M + 0], yacc[1]);
-            T S0 = A * Ay, S1 = A * yp;
-            bfly2(S0, S1);
+                rn = radius == T(0) ? T(0) : rn;                    // [ref: enet.pyx:56-58]
+                const T cf = rn * w;
+                const T dlv = cf - ((lane == BB_M + t) ? T(1) : T(0));       // delta_t = n_t - d_t
+                const T zv = fma(rn, y, -Mrow[BB_M + t]);                    // G delta_t
 #pragma unroll
-            for (int t = 1; t < BB_M; ++t) {
-                const T h = lnext * rnp;                            // L_{t,t-1} rn_{t-1}
-                const T n2 = fma(h, fma(h, n2p, T(-2) * S1), S0);   // |v_t|^2
-                const T w = fma(-h, wp, A), y = fma(-h, yp, Ay);    // w_t, G w_t
-                // the previous atom is final: its coefficients, its delta, and the lagging right-looking update
-                const T cfp = rnp * wp;
-                coef[(t - 1) * BB_NB + lane] = cfp;
-                const T dlv = cfp - ((lane == BB_M + t - 1) ? T(1) : T(0));      // delta_{t-1} = n_{t-1} - d_{t-1}
-                const T zv = fma(rnp, yp, -Mrow[BB_M + t - 1]);                  // G delta_{t-1}
-                T An = T(0), Ayn = T(0), ln = T(0);
-                if (t + 1 < BB_M) {
-                    const T l2 = LT[(t - 1) * BB_M + t + 1];                     // L_{t+1,t-1}
-                    wacc[t + 1] = fma(-l2, dlv, wacc[t + 1]);
-                    yacc[t + 1] = fma(-l2, zv, yacc[t + 1]);
-                    ln = LT[t * BB_M + t + 1];                                   // L_{t+1,t}
-                    An = wacc[t + 1] + ((lane == BB_M + t) ? ln : T(0));
-                    Ayn = fma(ln, Mrow[BB_M + t], yacc[t + 1]);
-                    S0 = An * Ayn; S1 = An * y;
-                    bfly2(S0, S1);                                               // reductions of atom t+1, in flight
-                }
-                T radius_t;
-                const T rn = scale_of(n2, t, radius_t);
-                if (g == 0 && lane == 0 && t < mb)                               // comp_norm_[k] -= enet_norm(new row) [ref: :690-692]
-                    P.comp_norm[ord_s[b * BB_M + t]] = radius_t - (rn * rn) * (n2 > T(0) ? n2 : T(0));
-#pragma unroll
-                for (int t2 = t + 2; t2 < BB_M; ++t2) {
-                    const T l = LT[(t - 1) * BB_M + t2];                         // L_{t2, t-1}
+                for (int t2 = t + 1; t2 < BB_M; ++t2) {
+                    const T l = LT[t * BB_M + t2];                           // L_{t2, t}
                     wacc[t2] = fma(-l, dlv, wacc[t2]);
                     yacc[t2] = fma(-l, zv, yacc[t2]);
                 }
-                wp = w; yp = y; n2p = n2; rnp = rn; A = An; Ay = Ayn; lnext = ln;
+                coef[t * BB_NB + lane] = cf;
+                // comp_norm_[k] -= enet_norm(new row) [ref: :690-692]: |n_t|^2 = rn^2 |v_t|^2 (the same value in every CTA)
+                if (g == 0 && lane == 0 && t < mb) P.comp_norm[ord_s[b * BB_M + t]] = radius - (rn * rn) * n2;
             }
-            coef[(BB_M - 1) * BB_NB + lane] = rnp * wp;
             if (sstamp) sstamp[(int64_t)b * 8 + 7] = clock64();
         }
         __syncthreads();                    // coefficients, look-ahead product of block b+1, operands of blocks b+1 / b+2

@@ -59,6 +59,7 @@ int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M
     P.A = Apacked; P.B = Bpacked; P.C = C; P.ldc = ldc; P.M = (int)M; P.N = (int)N;
     MODL_REQUIRE((Bpacked != nullptr) != (Braw != nullptr), "tc_gemm takes the B operand packed or raw");
     P.Braw = Braw; P.ldb_raw = ldb_raw; P.Kd = (int)Kd;
+    MODL_REQUIRE(Braw == nullptr || bn <= 160, "tc_gemm: the raw-B form converts tiles of at most 160 columns");
     P.nkb = (int)tc_k_blocks(Kd);
     P.alpha = alpha; P.beta = beta;
     P.sbo = 128u;

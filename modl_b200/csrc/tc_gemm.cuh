@@ -380,13 +380,13 @@ tc_gemm_kernel(TcGemmParams P)
             const int n_base = nb * bn;
             const int nunits = bn * TC_CHUNKS;
             constexpr int NCT = TC_THREADS - 64;
-            constexpr int UMAX = (TC_MAX_BN * TC_CHUNKS + NCT - 1) / NCT;      // units per thread at the widest tile
-            for (int i = 0; i < nk; ++i) {
-                const int s = i % STAGES;
-                const unsigned ph = (unsigned)(i / STAGES) & 1u;
+            constexpr int TC_RAW_MAX_BN = 160;                                  // widest tile of the raw-B form (launcher checks)
+            constexpr int UMAX = (TC_RAW_MAX_BN * TC_CHUNKS + NCT - 1) / NCT;   // units per thread
+            float v[2][UMAX][4];
+            // loads of block i into v[i & 1]; every load of a block is in flight at once, and the loads of block i + 1 are
+            // issued BEFORE block i is converted and stored: the global latency hides behind the conversion of the previous block
+            auto issue = [&](int i, float (&vv)[UMAX][4]) {
                 const int kk0 = (kb0 + i) * TC_BK;
-                float v[UMAX][4];
-                // every load of the block in flight before the first conversion
 #pragma unroll
                 for (int u = 0; u < UMAX; ++u) {
                     const int e = ct + u * NCT;
@@ -394,9 +394,13 @@ tc_gemm_kernel(TcGemmParams P)
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {
                         const int kk = kk0 + 4 * c + w;
-                        v[u][w] = (e < nunits && n_base + n < P.N && kk < P.Kd) ? __ldg(P.Braw + (int64_t)kk * P.ldb_raw + n_base + n) : 0.f;
+                        vv[u][w] = (e < nunits && n_base + n < P.N && kk < P.Kd) ? __ldg(P.Braw + (int64_t)kk * P.ldb_raw + n_base + n) : 0.f;
                     }
                 }
+            };
+            auto convert = [&](int i, const float (&vv)[UMAX][4]) {
+                const int s = i % STAGES;
+                const unsigned ph = (unsigned)(i / STAGES) & 1u;
                 tc_mbar_wait(empty_bar(s), ph ^ 1u);                 // the MMAs that read this slot are done
                 const unsigned sb = smem0 + (unsigned)s * stage_bytes + a_bytes;
 #pragma unroll
@@ -404,7 +408,7 @@ tc_gemm_kernel(TcGemmParams P)
                     const int e = ct + u * NCT;
                     if (e < nunits) {
                         float4 h, l;
-                        tc_split(v[u][0], h.x, l.x); tc_split(v[u][1], h.y, l.y); tc_split(v[u][2], h.z, l.z); tc_split(v[u][3], h.w, l.w);
+                        tc_split(vv[u][0], h.x, l.x); tc_split(vv[u][1], h.y, l.y); tc_split(vv[u][2], h.z, l.z); tc_split(vv[u][3], h.w, l.w);
                         const unsigned dst = sb + 16u * (unsigned)e;             // (c * bn + n) * 16 bytes
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst + b_half), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
@@ -412,6 +416,15 @@ tc_gemm_kernel(TcGemmParams P)
                 }
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic stores -> visible to the tensor core
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(fullb_bar(s)) : "memory");
+            };
+            issue(0, v[0]);
+            for (int i = 0; i < nk; i += 2) {
+                if (i + 1 < nk) issue(i + 1, v[1]);
+                convert(i, v[0]);
+                if (i + 1 < nk) {
+                    if (i + 2 < nk) issue(i + 2, v[0]);
+                    convert(i + 1, v[1]);
+                }
             }
         }
         tc_mbar_wait(done_bar, 0);

@@ -66,8 +66,9 @@ for f in ("bench.json", "bench_ref.json"):
         shutil.copy(os.path.join(src, f), os.path.join(dst, tag + "_" + f))
 # per-phase DRAM traffic of one step (bytes), summed over the captured launches of the phase's kernels
 import json
-PHASE_OF = [("bcd_pilot", "dict_bcd"), ("cd_regression", "code"), ("tc_pack_rows", "gather"),
-            ("tc_pack_cols", "stats"), ("tc_gemm", None)]
+PHASE_OF = [("bcd_blocked", "dict_bcd"), ("bcd_pilot", "dict_bcd"), ("cd_regression", "code"), ("tc_pack_rows", "gather"),
+            ("tc_pack_cols", "stats_sub"), ("tc_gemm", None)]
+GEMM_ORDER = ["gram", "stats_sub", "stats"]     # launches of one step of the two-stream loop, in host order
 traffic, gemm_seen = {}, 0
 for f in sorted(os.listdir(src)):
     if not f.endswith(".raw.csv"):
@@ -87,8 +88,8 @@ for f in sorted(os.listdir(src)):
         byt = val('dram__bytes_read.sum') + val('dram__bytes_write.sum')
         for key, ph in PHASE_OF:
             if key in name:
-                if key == "tc_gemm":      # launches of one step in order: [G ; Dx], then [B_ | C_]
-                    ph = "gram" if gemm_seen % 2 == 0 else "stats"
+                if key == "tc_gemm":      # [G ; Dx], [B_[:, subset] | C_] (critical path), B_ full width (second stream)
+                    ph = GEMM_ORDER[gemm_seen % 3]
                     gemm_seen += 1
                 traffic[ph] = traffic.get(ph, 0) + byt
                 break
