@@ -58,6 +58,7 @@ static int ctx_init(modl_ctx *c, int device)
     if (const char *e = getenv("MODL_BCD_CLUSTER")) c->opt_bcd_cluster = atoi(e);
     if (const char *e = getenv("MODL_BCD_BLOCKED")) c->opt_bcd_blocked = atoi(e);
     if (const char *e = getenv("MODL_TC_RAW_B")) c->opt_tc_raw_b = atoi(e);
+    if (const char *e = getenv("MODL_TC_SPLIT2")) c->opt_tc_split2 = atoi(e);
     if (const char *e = getenv("MODL_BCD_PIPELINE")) c->opt_bcd_pipeline = atoi(e);
     if (const char *e = getenv("MODL_CD_WARPS")) c->opt_cd_warps = atoi(e);
     if (const char *e = getenv("MODL_FORCE_GLOBAL_GRAM")) c->opt_force_global_gram = atoi(e);
@@ -114,6 +115,7 @@ int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "bcd_pipeline")) ctx->opt_bcd_pipeline = value;
     else if (!strcmp(name, "bcd_blocked")) ctx->opt_bcd_blocked = value;
     else if (!strcmp(name, "tc_raw_b")) ctx->opt_tc_raw_b = value;
+    else if (!strcmp(name, "tc_split2")) ctx->opt_tc_split2 = value;
     else if (!strcmp(name, "bcd_coop_min_cols")) ctx->opt_bcd_coop_min_cols = value;
     else if (!strcmp(name, "bcd_flag_barrier")) ctx->opt_bcd_flag_barrier = value;
     else { set_error("unknown option %s", name); return MODL_EINVAL; }

@@ -96,7 +96,9 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
                     cudaGetLastError();
                     continue;
                 }
-                if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess) {
+                // always the whole opt-in budget: the attribute is per FUNCTION, and a later, smaller request (another
+                // cluster size of the same kernel) would otherwise lower it under a cached larger one
+                if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
                     cudaGetLastError();
                     continue;
                 }
@@ -132,7 +134,7 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
         size_t need = base_smem(ncp) + (size_t)k * ncp * sizeof(T);
         d_in_smem = need <= budget && ncp <= 2 * BCD_THREADS;
         if (!d_in_smem) need = base_smem(ncp);
-        MODL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        MODL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));   // per function: never lower it
         int per_sm = 0;
         MODL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BCD_THREADS, need));
         MODL_REQUIRE(per_sm >= 1, "dictionary-update kernel does not fit on an SM");

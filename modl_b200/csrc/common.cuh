@@ -104,6 +104,7 @@ struct modl_ctx {
                                     // measured r02_a: image shape 8.3 -> 5.5 us/atom at 128, worse again at 256)
     int opt_bcd_timing = 0;       // debug: record clock64 stamps inside the dictionary update
     int bcd_timing_k = 0;
+    int opt_tc_split2 = 1;        // split the contraction of the two-destination GEMM ([B_[:, subset] | C_]: 26 tiles on 148 SMs otherwise)
     int opt_tc_raw_b = 1;         // full-width B_ product: the GEMM converts raw X rows itself (no packed X^T panel through HBM)
     int opt_bcd_blocked = 1;      // L2 ball without positivity, panel fits one cluster: block-wise coefficient-space solve (bcd_blocked.cuh)
     int opt_bcd_pipeline = 1;     // pilot kernel, L2 ball without positivity: keep two norm exchanges in flight (bcd_pilot.cuh)

@@ -5,6 +5,27 @@
 
 namespace modl {
 
+// split-K reduction of the two-destination form: columns [0, N1) of the N-wide product go to C, columns
+// [n_split, n_split + N2) to C2; fixed summation order over the slices
+__global__ void tc_splitk_reduce2_kernel(int M, int N, int splits, float alpha, const float *__restrict__ part, float beta,
+                                         float *__restrict__ C, int64_t ldc, int N1, float *__restrict__ C2, int64_t ldc2,
+                                         int n_split, int N2)
+{
+    const int64_t total = (int64_t)M * N;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(e / N), n = (int)(e % N);
+        float *c = nullptr;
+        if (n < N1) c = C + (int64_t)m * ldc + n;
+        else if (n >= n_split && n < n_split + N2) c = C2 + (int64_t)m * ldc2 + (n - n_split);
+        if (c == nullptr) continue;
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += part[(int64_t)z * total + e];
+        float r = alpha * s;
+        if (beta != 0.f) r = fmaf(beta, *c, r);
+        *c = r;
+    }
+}
+
 size_t tc_packed_elems(int64_t rows, int64_t kd, int64_t rpb) { return tc_packed_floats(rows, kd, rpb); }
 
 // Accumulator tile width for an N-column output produced by `mtiles` row tiles: the multiple of 16
@@ -87,7 +108,7 @@ int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M
     int64_t splits = (int64_t)ctx->sm_count / tiles;            // never more CTAs than SMs: a second wave costs a whole tile time
     if (splits > P.nkb) splits = P.nkb;
     if (splits > 32) splits = 32;
-    if (splits < 1 || C2 != nullptr) splits = 1;        // the two-destination form is never split
+    if (splits < 1 || (C2 != nullptr && !ctx->opt_tc_split2)) splits = 1;
     P.kb_per_split = (int)ceil_div(P.nkb, splits);
     splits = ceil_div(P.nkb, P.kb_per_split);
     P.part = nullptr;
@@ -98,7 +119,11 @@ int tc_gemm(modl_ctx *ctx, const float *Apacked, const float *Bpacked, int64_t M
     if (splits > 1) {
         const int64_t total = M * N;
         int blocks = (int)(ceil_div(total, 256) < 4 * ctx->sm_count ? ceil_div(total, 256) : 4 * ctx->sm_count);
-        gemm_splitk_reduce_kernel<float><<<blocks, 256, 0, st>>>((int)M, (int)N, (int)splits, alpha, P.part, beta, C, ldc);
+        if (C2 == nullptr)
+            gemm_splitk_reduce_kernel<float><<<blocks, 256, 0, st>>>((int)M, (int)N, (int)splits, alpha, P.part, beta, C, ldc);
+        else
+            tc_splitk_reduce2_kernel<<<blocks, 256, 0, st>>>((int)M, (int)N, (int)splits, alpha, P.part, beta, C, ldc, P.N1, C2, ldc2,
+                                                             P.n_split, P.N2);
         MODL_LAUNCH_CHECK(ctx);
     }
     return MODL_OK;

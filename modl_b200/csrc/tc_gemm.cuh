@@ -454,12 +454,12 @@ tc_gemm_kernel(TcGemmParams P)
         }
         asm volatile("bar.sync 2, 128;\n" ::: "memory");        // the four epilogue warps
         const int ew = warp - 2;
-        const bool second = P.C2 != nullptr && nb * P.bn >= P.n_split;
+        const bool raw = P.part != nullptr;            // split-K: raw partial tiles, at their column in the N-wide product
+        const bool second = !raw && P.C2 != nullptr && nb * P.bn >= P.n_split;
         const int n_tile = second ? nb * P.bn - P.n_split : nb * P.bn;     // first column of the tile in its destination
-        const int n_lim = second ? P.N2 : P.N1;
+        const int n_lim = raw ? P.N : (second ? P.N2 : P.N1);
         float *const c_base = second ? P.C2 : P.C;
         const int64_t c_ld = second ? P.ldc2 : P.ldc;
-        const bool raw = P.part != nullptr;
         const bool use_c = !raw && P.beta != 0.f;
         // 8 rows per batch (r0, r0 + 4, ..., r0 + 28): their C reads are all in flight before the first is consumed
         for (int r0 = ew; r0 < TC_ROWS; r0 += 32) {
