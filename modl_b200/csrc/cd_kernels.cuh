@@ -58,6 +58,29 @@ __global__ void __launch_bounds__(256)
 cd_pack_gram_kernel(const T *__restrict__ G, int k, int tiles, T *__restrict__ packed)
 {
     const int t = blockIdx.x;
+    if (t == cd_tri(tiles)) {
+        // one extra CTA: H for the all-ones warm start of a first visit [ref: dict_fact.py:470, code_ = ones], i.e. the
+        // rows of G added in coordinate order -- bit for bit what the solver's  H += w_c G[c,:]  loop produces for w = 1
+        // (fma(1, g, h) rounds once, like the add), so that warps whose sample still carries the warm start skip k
+        // dependent row loads
+        T *h_ones = packed + (int64_t)cd_tri(tiles) * CD_TILE_ELEMS;
+        for (int j = threadIdx.x; j < tiles * CD_TILE; j += blockDim.x) {
+            T acc = T(0);
+            if (j < k) {
+                int c = 0;
+                for (; c + 32 <= k; c += 32) {          // 32 loads in flight, added in coordinate order
+                    T v[32];
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) v[u] = G[(int64_t)(c + u) * k + j];
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) acc = acc + v[u];
+                }
+                for (; c < k; ++c) acc = acc + G[(int64_t)c * k + j];
+            }
+            h_ones[j] = acc;
+        }
+        return;
+    }
     int I = 0;
     while (cd_tri(I + 1) <= t) ++I;
     const int J = t - cd_tri(I);
@@ -161,7 +184,7 @@ __device__ __forceinline__ void cd_axpy_tiles(double (&h)[TILES], const double (
 template <typename T, int TILES, bool PACKED>
 __device__ __forceinline__ int cd_solve_warp(unsigned sbase, const T *__restrict__ Gs, int k, int lane,
                                              T (&w)[TILES], const T (&q)[TILES], T ynorm2, T alpha,
-                                             T beta, T tol, int max_iter, bool positive)
+                                             T beta, T tol, int max_iter, bool positive, const T *__restrict__ h_ones = nullptr)
 {
     T h[TILES], r[TILES], inv[TILES];
     unsigned dead = 0;      // bit J: my coordinate 32 J + lane has a zero diagonal (or is padding)
@@ -180,9 +203,17 @@ __device__ __forceinline__ int cd_solve_warp(unsigned sbase, const T *__restrict
         h[J] = T(0);
     }
     // ---- H = Q w accumulated column by column (Q symmetric)  [ref: :340-347] ----
+    bool ones = h_ones != nullptr;
+#pragma unroll
+    for (int J = 0; J < TILES; ++J) ones = ones && (w[J] == ((J * CD_TILE + lane) < k ? T(1) : T(0)));
+    ones = __all_sync(kFullMask, ones);
+    if (ones) {     // the warm start of a first visit: H precomputed once per Gram matrix (cd_pack_gram_kernel), same bits
+#pragma unroll
+        for (int J = 0; J < TILES; ++J) h[J] = h_ones[J * CD_TILE + lane];
+    }
 #pragma unroll
     for (int J = 0; J < TILES; ++J) {
-        const int lmax = min(CD_TILE, k - J * CD_TILE);
+        const int lmax = ones ? 0 : min(CD_TILE, k - J * CD_TILE);
         for (int l = 0; l < lmax; ++l) {
             const T wc = __shfl_sync(kFullMask, w[J], l);
             if (wc != T(0)) {
@@ -212,15 +243,8 @@ __device__ __forceinline__ int cd_solve_warp(unsigned sbase, const T *__restrict
             // then jumps to the first coordinate that does something, executes it exactly like the
             // sequential loop would, and re-tests the lanes after it.  Sparse codes (a few percent
             // of non-zeros) therefore cost a few dependent steps per tile instead of 32.
-            unsigned todo = kFullMask;
-            while (true) {
-                const T tmp0 = q[J] - h[J];
-                const T mag0 = t_abs(tmp0) - alpha;
-                const bool moves = mag0 > T(0) && !(positive && tmp0 < T(0));
-                const unsigned act = __ballot_sync(kFullMask, my_live && (w[J] != T(0) || moves)) & todo;
-                if (act == 0u) break;
-                const int l = __ffs(act) - 1;
-                todo = (l == 31) ? 0u : (kFullMask << (l + 1));
+            // one coordinate step, exactly the sequential loop's  [ref: :356-377]
+            auto step = [&](int l) {
                 if (PACKED) cd_row_packed<T, TILES>(sbase, J, l, lane, r);
                 else        cd_row_global<T, TILES>(Gs, k, J * CD_TILE + l, lane, r);
                 const T w_old = __shfl_sync(kFullMask, w[J], l);
@@ -237,6 +261,27 @@ __device__ __forceinline__ int cd_solve_warp(unsigned sbase, const T *__restrict
                 const T w_new = __shfl_sync(kFullMask, cand, l);
                 w[J] = (lane == l) ? w_new : w[J];
                 cd_axpy_tiles<TILES>(h, r, w_new);
+            };
+            // A tile whose live coordinates all carry a non-zero weight (the first sweep from the all-ones warm start):
+            // every coordinate is active whatever H becomes, so the walk is the plain sequential loop -- no test, ballot
+            // and find-first on the dependent chain.
+            const unsigned live_mask = __ballot_sync(kFullMask, my_live);
+            const unsigned nz_mask = __ballot_sync(kFullMask, my_live && w[J] != T(0));
+            if (nz_mask == live_mask) {
+                for (int l = 0; l < lmax; ++l)
+                    if ((live_mask >> l) & 1u) step(l);
+                continue;
+            }
+            unsigned todo = kFullMask;
+            while (true) {
+                const T tmp0 = q[J] - h[J];
+                const T mag0 = t_abs(tmp0) - alpha;
+                const bool moves = mag0 > T(0) && !(positive && tmp0 < T(0));
+                const unsigned act = __ballot_sync(kFullMask, my_live && (w[J] != T(0) || moves)) & todo;
+                if (act == 0u) break;
+                const int l = __ffs(act) - 1;
+                todo = (l == 31) ? 0u : (kFullMask << (l + 1));
+                step(l);
             }
         }
         // max |w| and max |delta w| of this sweep over the visited coordinates [ref: :379-386]
@@ -319,7 +364,8 @@ __global__ void cd_regression_kernel(const T *__restrict__ G, int64_t g_stride, 
         }
         const T *Gs = G + (int64_t)ii * g_stride;
         const int sw = cd_solve_warp<T, TILES, PACKED>((unsigned)__cvta_generic_to_shared(sG), Gs, k, lane, w, q,
-                                                       xnorm2[ii], alpha, beta, tol, max_iter, positive != 0);
+                                                       xnorm2[ii], alpha, beta, tol, max_iter, positive != 0,
+                                                       PACKED ? G + cd_packed_elems(TILES) : (const T *)nullptr);
 #pragma unroll
         for (int J = 0; J < TILES; ++J) {
             const int c = J * CD_TILE + lane;

@@ -28,8 +28,8 @@ static int cd_launch_inst(modl_ctx *ctx, const T *G, int64_t g_stride, const T *
         }
         // tile-packed lower triangle of G in global memory, pulled by TMA bulk copies
         T *packed = nullptr;
-        MODL_TRY(ws<T>(ctx, WS_GPACK, cd_packed_elems(TILES), &packed));
-        cd_pack_gram_kernel<T><<<cd_tri(TILES), 256, 0, st>>>(G, (int)k, TILES, packed);
+        MODL_TRY(ws<T>(ctx, WS_GPACK, cd_packed_elems(TILES) + (size_t)TILES * CD_TILE, &packed));    // image | H of the all-ones start
+        cd_pack_gram_kernel<T><<<cd_tri(TILES) + 1, 256, 0, st>>>(G, (int)k, TILES, packed);
         MODL_LAUNCH_CHECK(ctx);
         G = packed;
     } else {
