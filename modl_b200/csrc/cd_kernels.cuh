@@ -243,8 +243,15 @@ __device__ __forceinline__ int cd_solve_warp(unsigned sbase, const T *__restrict
             // then jumps to the first coordinate that does something, executes it exactly like the
             // sequential loop would, and re-tests the lanes after it.  Sparse codes (a few percent
             // of non-zeros) therefore cost a few dependent steps per tile instead of 32.
-            // one coordinate step, exactly the sequential loop's  [ref: :356-377]
-            auto step = [&](int l) {
+            unsigned todo = kFullMask;
+            while (true) {
+                const T tmp0 = q[J] - h[J];
+                const T mag0 = t_abs(tmp0) - alpha;
+                const bool moves = mag0 > T(0) && !(positive && tmp0 < T(0));
+                const unsigned act = __ballot_sync(kFullMask, my_live && (w[J] != T(0) || moves)) & todo;
+                if (act == 0u) break;
+                const int l = __ffs(act) - 1;
+                todo = (l == 31) ? 0u : (kFullMask << (l + 1));
                 if (PACKED) cd_row_packed<T, TILES>(sbase, J, l, lane, r);
                 else        cd_row_global<T, TILES>(Gs, k, J * CD_TILE + l, lane, r);
                 const T w_old = __shfl_sync(kFullMask, w[J], l);
@@ -261,27 +268,6 @@ __device__ __forceinline__ int cd_solve_warp(unsigned sbase, const T *__restrict
                 const T w_new = __shfl_sync(kFullMask, cand, l);
                 w[J] = (lane == l) ? w_new : w[J];
                 cd_axpy_tiles<TILES>(h, r, w_new);
-            };
-            // A tile whose live coordinates all carry a non-zero weight (the first sweep from the all-ones warm start):
-            // every coordinate is active whatever H becomes, so the walk is the plain sequential loop -- no test, ballot
-            // and find-first on the dependent chain.
-            const unsigned live_mask = __ballot_sync(kFullMask, my_live);
-            const unsigned nz_mask = __ballot_sync(kFullMask, my_live && w[J] != T(0));
-            if (nz_mask == live_mask) {
-                for (int l = 0; l < lmax; ++l)
-                    if ((live_mask >> l) & 1u) step(l);
-                continue;
-            }
-            unsigned todo = kFullMask;
-            while (true) {
-                const T tmp0 = q[J] - h[J];
-                const T mag0 = t_abs(tmp0) - alpha;
-                const bool moves = mag0 > T(0) && !(positive && tmp0 < T(0));
-                const unsigned act = __ballot_sync(kFullMask, my_live && (w[J] != T(0) || moves)) & todo;
-                if (act == 0u) break;
-                const int l = __ffs(act) - 1;
-                todo = (l == 31) ? 0u : (kFullMask << (l + 1));
-                step(l);
             }
         }
         // max |w| and max |delta w| of this sweep over the visited coordinates [ref: :379-386]

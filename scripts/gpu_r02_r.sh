@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round-2 call R: dense-tile walk of the CD kernel: whole GPU suite + bench.
+TAG=${1:-r02_r}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+export PYTHONUNBUFFERED=1
+timeout 1200 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log; tail -3 $OUT/pytest_gpu.log
+timeout 600 python bench.py --no-cpu > $OUT/bench.json 2> $OUT/bench.err
+python - <<PY
+import json
+d=json.load(open("$OUT/bench.json"))
+print("bench value %.0f ms/step %.4f (min %.4f max %.4f) host %.3f  e2e %.0f (%.4f ms)" % (d["value"], d["ms_per_step"], d["run"]["ms_per_step_min"], d["run"]["ms_per_step_max"], d["host_enqueue_ms_per_step"], d["e2e"]["value"], d["e2e"]["ms_per_step"]))
+print({k: round(v["ms"]*1e3,1) for k,v in d["roofline"]["phases"].items()}, "dense", d["extra"]["dense_codes"]["ms_per_step"])
+PY
+timeout 120 python scripts/loop_trace.py device 4 2>&1 | tail -2
+ls $OUT
