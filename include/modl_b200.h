@@ -42,6 +42,9 @@ typedef struct modl_sampler modl_sampler; /* host feature-subset sampler        
 
 int modl_version(void);
 const char *modl_last_error(void);
+/* sizeof(modl_step_params), sizeof(modl_fit_params), sizeof(modl_fit_batches) as this library was compiled: a binding
+ * that mirrors the structs (ctypes, cgo, JNA ...) checks its own layout against them before the first call. */
+void modl_struct_sizes(int64_t *h_out3);
 
 /* ------------------------------------------------------------------------------------
  * Host-side bookkeeping: bit-exact with the reference (integer streams).

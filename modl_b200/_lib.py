@@ -75,6 +75,7 @@ def _declare(L):
         return f
 
     fn("modl_version", ci, [])
+    fn("modl_struct_sizes", None, [vp])
     fn("modl_last_error", C.c_char_p, [])
     fn("modl_rs_create", vp, [u64])
     fn("modl_rs_destroy", None, [vp])
@@ -127,7 +128,7 @@ def _declare(L):
 
 # every symbol include/modl_b200.h declares (tests check the library exports them all)
 EXPORTED = (
-    ["modl_version", "modl_last_error", "modl_rs_create", "modl_rs_destroy", "modl_rs_seed",
+    ["modl_version", "modl_struct_sizes", "modl_last_error", "modl_rs_create", "modl_rs_destroy", "modl_rs_seed",
      "modl_rs_randint", "modl_rs_binomial", "modl_rs_permutation", "modl_rs_shuffle",
      "modl_rs_shuffle_with_trace", "modl_sampler_create", "modl_sampler_destroy",
      "modl_sampler_yield_subset", "modl_batch_weight", "modl_ctx_create", "modl_ctx_destroy",

@@ -47,6 +47,14 @@ int modl_ctx::reserve(WsSlot slot, size_t bytes, void **out)
 extern "C" {
 
 int modl_version(void) { return 100; }
+
+void modl_struct_sizes(int64_t *h_out3)
+{
+    if (!h_out3) return;
+    h_out3[0] = (int64_t)sizeof(modl_step_params);
+    h_out3[1] = (int64_t)sizeof(modl_fit_params);
+    h_out3[2] = (int64_t)sizeof(modl_fit_batches);
+}
 const char *modl_last_error(void) { return modl::g_err; }
 
 static int ctx_init(modl_ctx *c, int device)

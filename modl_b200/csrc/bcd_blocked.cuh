@@ -477,21 +477,21 @@ bcd_blocked_kernel(BcdParams<T> P)
     if (stamp) stamp[(int64_t)8 * k + 2] = clock64();
 
     // new rows and deltas of block pb on my columns, from the coefficients the solver left:  n_j = sum_r coef[j][r] basis_r.
-    // item = (4 columns, 4 atoms): 8 128-bit loads feed 32 FFMA2.  Phase threads.
+    // item = (4 columns, 2 atoms): 192 threads; 6 128-bit loads feed 16 FFMA2.
     auto apply_block = [&](int pb) {
         const int mbp = min(BB_M, k - pb * BB_M);
-        for (int e = pt; e < 4 * NQ; e += BB_NPH) {
-            const int aq = e / NQ, cq = e % NQ;
+        for (int e = pt; e < 8 * NQ; e += BB_NPH) {
+            const int ap = e / NQ, cq = e % NQ;
             const Quad<T> *bcol = reinterpret_cast<const Quad<T> *>(basis) + cq;
-            Pair<T> acc[4][2];
+            Pair<T> acc[2][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) acc[u][0].x = acc[u][0].y = acc[u][1].x = acc[u][1].y = T(0);
+            for (int u = 0; u < 2; ++u) acc[u][0].x = acc[u][0].y = acc[u][1].x = acc[u][1].y = T(0);
 #pragma unroll
             for (int r = 0; r < BB_NB; r += 4) {
                 const Quad<T> b0 = bcol[(r + 0) * NQ], b1 = bcol[(r + 1) * NQ], b2 = bcol[(r + 2) * NQ], b3 = bcol[(r + 3) * NQ];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const Quad<T> f = *reinterpret_cast<const Quad<T> *>(coef + (4 * aq + u) * BB_NB + r);
+                for (int u = 0; u < 2; ++u) {
+                    const Quad<T> f = *reinterpret_cast<const Quad<T> *>(coef + (2 * ap + u) * BB_NB + r);
                     pair_fma(f.x, Pair<T>{b0.x, b0.y}, acc[u][0]); pair_fma(f.x, Pair<T>{b0.z, b0.w}, acc[u][1]);
                     pair_fma(f.y, Pair<T>{b1.x, b1.y}, acc[u][0]); pair_fma(f.y, Pair<T>{b1.z, b1.w}, acc[u][1]);
                     pair_fma(f.z, Pair<T>{b2.x, b2.y}, acc[u][0]); pair_fma(f.z, Pair<T>{b2.z, b2.w}, acc[u][1]);
@@ -499,8 +499,8 @@ bcd_blocked_kernel(BcdParams<T> P)
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = 4 * aq + u;
+            for (int u = 0; u < 2; ++u) {
+                const int j = 2 * ap + u;
                 Quad<T> nv; nv.x = acc[u][0].x; nv.y = acc[u][0].y; nv.z = acc[u][1].x; nv.w = acc[u][1].y;
                 Quad<T> dv; dv.x = dv.y = dv.z = dv.w = T(0);
                 if (j < mbp) {
@@ -537,30 +537,28 @@ bcd_blocked_kernel(BcdParams<T> P)
         __syncthreads();                    // the shared slice now holds every block before b
         BB_REL_STAMP(b, 1);
         // ---- S0b: repair the look-ahead product with the previous block's deltas; basis of this block.
-        //      item = (4 columns, 4 atoms) ----
+        //      item = (4 columns, 2 atoms) ----
         const T *Rb = Rraw + (b & 1) * BB_M * ncp;
-        for (int e = pt; e < 4 * NQ; e += BB_NPH) {
-            const int aq = e / NQ, cq = e % NQ;
-            Pair<T> dot[4][2];
+        for (int e = pt; e < 8 * NQ; e += BB_NPH) {
+            const int ap = e / NQ, cq = e % NQ;
+            Pair<T> dot[2][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const Quad<T> rr = *reinterpret_cast<const Quad<T> *>(Rb + (4 * aq + u) * ncp + 4 * cq);
+            for (int u = 0; u < 2; ++u) {
+                const Quad<T> rr = *reinterpret_cast<const Quad<T> *>(Rb + (2 * ap + u) * ncp + 4 * cq);
                 dot[u][0].x = rr.x; dot[u][0].y = rr.y; dot[u][1].x = rr.z; dot[u][1].y = rr.w;
             }
             if (b > 0) {
 #pragma unroll
                 for (int i = 0; i < BB_M; ++i) {
                     const Quad<T> dv = *reinterpret_cast<const Quad<T> *>(dlt + i * ncp + 4 * cq);
-                    const Quad<T> cx = *reinterpret_cast<const Quad<T> *>(Cx + i * BB_M + 4 * aq);
+                    const Pair<T> cx = *reinterpret_cast<const Pair<T> *>(Cx + i * BB_M + 2 * ap);
                     pair_fma(cx.x, Pair<T>{dv.x, dv.y}, dot[0][0]); pair_fma(cx.x, Pair<T>{dv.z, dv.w}, dot[0][1]);
                     pair_fma(cx.y, Pair<T>{dv.x, dv.y}, dot[1][0]); pair_fma(cx.y, Pair<T>{dv.z, dv.w}, dot[1][1]);
-                    pair_fma(cx.z, Pair<T>{dv.x, dv.y}, dot[2][0]); pair_fma(cx.z, Pair<T>{dv.z, dv.w}, dot[2][1]);
-                    pair_fma(cx.w, Pair<T>{dv.x, dv.y}, dot[3][0]); pair_fma(cx.w, Pair<T>{dv.z, dv.w}, dot[3][1]);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = 4 * aq + u;
+            for (int u = 0; u < 2; ++u) {
+                const int j = 2 * ap + u;
                 Quad<T> gv, dold;
                 gv.x = gv.y = gv.z = gv.w = dold.x = dold.y = dold.z = dold.w = T(0);
                 if (j < mb) {

@@ -29,6 +29,14 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTED), declared ^ set(_lib.EXPORTED)
 
 
+def test_ctypes_structs_match_the_compiled_layout():
+    """The ctypes mirrors of the three parameter structs have the size the library was compiled with (a field added on one
+    side only would shift every later member silently)."""
+    sizes = (ctypes.c_int64 * 3)()
+    _lib.lib().modl_struct_sizes(sizes)
+    assert list(sizes) == [ctypes.sizeof(_lib.StepParams), ctypes.sizeof(_lib.FitParams), ctypes.sizeof(_lib.FitBatches)]
+
+
 def test_random_kat():
     rs = RandomState(seed=0)
     vals = [rs.randint(10) for _ in range(10000)]
