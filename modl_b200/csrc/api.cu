@@ -827,15 +827,12 @@ int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream)
     }
     if (phases & MODL_PHASE_APPLY_SUB) {
         prof_mark(ctx, st, MODL_PROF_STATS);
-        xpby_kernel<T><<<grid_for(ctx, ceil_div(k * k, 256), 4), 256, 0, st>>>(static_cast<T *>(q->C), inc_sub, k * k, keep);
-        MODL_LAUNCH_CHECK(ctx);
         T *Bp = nullptr;
         MODL_TRY(ws<T>(ctx, slot ? WS_PANEL_B2 : WS_PANEL_B, (size_t)(k * lds), &Bp));
-        if (s > 0) {
-            gather_axpby_kernel<T><<<grid_for(ctx, k, 16), 256, 0, st>>>(static_cast<const T *>(q->B), p, (int)k, d_subset, (int)s,
-                                                                          keep, inc_sub + k * k, lds, Bp, lds);
-            MODL_LAUNCH_CHECK(ctx);
-        }
+        // C_ and the B_[:, subset] panel in one launch (s == 0: the second loop is empty)
+        apply_sub_kernel<T><<<grid_for(ctx, k, 2), 256, 0, st>>>(static_cast<T *>(q->C), inc_sub, (int)k, static_cast<const T *>(q->B), p,
+                                                                 d_subset, (int)s, keep, inc_sub + k * k, lds, Bp, lds);
+        MODL_LAUNCH_CHECK(ctx);
         ctx->panel_b_ready = 1;
         if (q->ev_after_apply_sub) MODL_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(q->ev_after_apply_sub), st));
     }

@@ -66,6 +66,28 @@ gather_axpby_kernel(const T *__restrict__ B, int64_t ldb, int rows, const int64_
     }
 }
 
+// The two folds the sharded step does after its all-reduce, in ONE launch (it sits on the critical path of every rank):
+//   C_[r, :] = keep * C_[r, :] + incC[r, :]                      (same fma as xpby_kernel)
+//   out[r, j] = keep * B[r, subset[j]] + incB[r, j]              (same fma as gather_axpby_kernel)
+template <typename T>
+__global__ void __launch_bounds__(256)
+apply_sub_kernel(T *__restrict__ Cmat, const T *__restrict__ incC, int k, const T *__restrict__ B, int64_t ldb,
+                 const int64_t *__restrict__ subset, int s, T keep, const T *__restrict__ incB, int64_t ldi,
+                 T *__restrict__ out, int64_t ldo)
+{
+    for (int r = blockIdx.x; r < k; r += gridDim.x) {
+        for (int j = threadIdx.x; j < k; j += blockDim.x) {
+            const int64_t i = (int64_t)r * k + j;
+            Cmat[i] = (keep != T(0)) ? fma(keep, Cmat[i], incC[i]) : incC[i];
+        }
+        const T *row = B + (int64_t)r * ldb;
+        for (int j = threadIdx.x; j < s; j += blockDim.x) {
+            const T x = incB[(int64_t)r * ldi + j];
+            out[(int64_t)r * ldo + j] = (keep != T(0)) ? fma(keep, row[subset[j]], x) : x;
+        }
+    }
+}
+
 // dst[ii, :] = src[indices[ii], :]
 template <typename T>
 __global__ void gather_rows_kernel(const T *__restrict__ src, int64_t ld, const int64_t *__restrict__ indices,
