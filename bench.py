@@ -408,6 +408,8 @@ def run_b200(args, rank, world):
             sw = est.last_sweeps_
             diag["mean_cd_sweeps"] = float(sw[:b_local].mean()) if sw is not None else float("nan")
             diag["subset_len_last"] = float(est.last_subset_.shape[0])
+            if world == 1:
+                diag["cuda_graphs"] = est._fit_loop_handle().graph_stats()
             last = run.idx_of(warmup + reps * steps - 1)
             diag["code_density"] = float((est.code_dev[torch.as_tensor(last, device=dev)] != 0).float().mean().item())
             keep = (run, est, X, Xd)
@@ -425,6 +427,8 @@ def run_b200(args, rank, world):
         code_host = torch.empty((b_local, K), dtype=torch.float32).pin_memory()
         regions, host_ms2, _ = run.timed(est2, Xp, steps, warmup, REPEATS, ctx, code_out=code_host)
         e2e = summarize(regions, steps, b_global)
+        if world == 1:
+            e2e["cuda_graphs"] = est2._fit_loop_handle().graph_stats()
         e2e.update({"unit": "samples/s", "h2d_bytes_per_step": int(b_local * P * 4 + b_local * 8),
                     "d2h_bytes_per_step": int(b_local * K * 4), "host_enqueue_ms_per_step": host_ms2,
                     "api": "DictFact(async_host_copy=True).partial_fit(pinned host rows, sample_indices, code_out=pinned "

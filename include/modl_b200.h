@@ -334,7 +334,10 @@ enum { MODL_PHASE_CODE = 1, MODL_PHASE_STATS = 2, MODL_PHASE_APPLY = 4, MODL_PHA
        MODL_PHASE_INPUTS_READY = 1024,
        /* flag, one GPU: STATS_SUB folds its product straight into C_ and into the B_[:, subset] panel
         * ([panel | C_] = keep [panel | C_] + (w/b) code^T [X_sub | code], one tensor-core launch); no APPLY_SUB */
-       MODL_PHASE_FUSED_APPLY = 2048 };
+       MODL_PHASE_FUSED_APPLY = 2048,
+       /* flag, with FUSED_APPLY and INPUTS_READY: the B_[:, subset] panel is gathered by THIS call (the step's PREFETCH ran
+        * without FUSED_APPLY, while the previous step's full-width product could still be writing B_) */
+       MODL_PHASE_GATHER_B = 4096 };
 
 int modl_batch_fit_f32(modl_ctx *, const modl_step_params *prm, void *stream);
 int modl_batch_fit_f64(modl_ctx *, const modl_step_params *prm, void *stream);
@@ -391,8 +394,17 @@ typedef struct modl_fit_batches {      /* one partial_fit call */
 int modl_fit_create(modl_ctx *ctx, modl_fit **out);
 void modl_fit_destroy(modl_fit *fit);
 /* "overlap" (1 = the two-stream schedule above, 0 = one fused call per block on the caller's stream),
- * "gate" (1 = the second stream starts only once the dictionary-update kernel is resident). */
+ * "gate" (1 = the second stream starts only once the dictionary-update kernel is resident),
+ * "graph" (on one GPU, after the first four blocks, the launches of a block are stream-captured, folded into the previous
+ * block's executable CUDA graph with cudaGraphExecUpdate and launched as a graph -- same kernels, same results:
+ * 1 (default) = the three calls of the two-stream schedule as three graphs; 2 = one graph per block on the caller's
+ * stream, the full-width product forked inside it; 0 = plain stream launches). */
 int modl_fit_set_option(modl_fit *fit, const char *name, int value);
+/* h_out[0] = graph launches so far, h_out[1] = executable graphs rebuilt because the block's topology changed,
+ * h_out[2] = calls run with plain launches because they could not be captured (a workspace slot had to grow),
+ * h_out[3] = times the full-width product gave up waiting (20 ms) for the dictionary kernel to become resident
+ * (always 0 unless a dictionary kernel failed to start).  Synchronises the device. */
+int modl_fit_graph_stats(modl_fit *fit, int64_t *h_out4);
 /* Blocks until the loop's own streams (copies, second stream, code read-back) are idle. */
 int modl_fit_synchronize(modl_fit *fit);
 /* Debug: timeline of the next `steps` steps of the two-stream schedule (0 = off), then

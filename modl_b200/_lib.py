@@ -101,6 +101,7 @@ def _declare(L):
     fn("modl_fit_destroy", None, [vp])
     fn("modl_fit_set_option", ci, [vp, C.c_char_p, ci])
     fn("modl_fit_synchronize", ci, [vp])
+    fn("modl_fit_graph_stats", ci, [vp, vp])
     fn("modl_fit_trace", ci, [vp, ci])
     fn("modl_fit_trace_read", ci, [vp, vp, ci, vp])
     fn("modl_nccl_unique_id", ci, [vp, i64])
@@ -134,7 +135,7 @@ EXPORTED = (
      "modl_sampler_yield_subset", "modl_batch_weight", "modl_ctx_create", "modl_ctx_destroy",
      "modl_ctx_sm_count", "modl_ctx_launch_count", "modl_ctx_set_option", "modl_ctx_check_info",
      "modl_ctx_profile", "modl_ctx_profile_read", "modl_fit_create", "modl_fit_destroy", "modl_fit_set_option",
-     "modl_fit_synchronize", "modl_fit_trace", "modl_fit_trace_read", "modl_nccl_unique_id", "modl_fit_set_comm"]
+     "modl_fit_synchronize", "modl_fit_graph_stats", "modl_fit_trace", "modl_fit_trace_read", "modl_nccl_unique_id", "modl_fit_set_comm"]
     + [n + s for s in ("f32", "f64") for n in (
         "modl_enet_norm_", "modl_enet_projection_", "modl_enet_scale_", "modl_gram_dx_",
         "modl_enet_regression_single_gram_", "modl_enet_regression_multi_gram_",
@@ -227,6 +228,12 @@ class FitLoop(object):
 
     def synchronize(self):
         check(lib().modl_fit_synchronize(self.handle))
+
+    def graph_stats(self):
+        """-> {graph launches, executable graphs rebuilt (topology changed), calls that fell back to plain launches}."""
+        out = (C.c_int64 * 4)()
+        check(lib().modl_fit_graph_stats(self.handle, out))
+        return {"launches": int(out[0]), "rebuilt": int(out[1]), "fallbacks": int(out[2]), "gate_timeouts": int(out[3])}
 
     TRACE_POINTS = ("h2d_start", "h2d_end", "prefetch_start", "prefetch_end", "main_start", "codes_done", "dict_done",
                     "stats_b_start", "stats_b_end", "d2h_done")

@@ -32,6 +32,7 @@ int modl_ctx::reserve(WsSlot slot, size_t bytes, void **out)
 {
     if (bytes == 0) bytes = 16;
     if (slot_bytes[slot] < bytes) {
+        if (capturing) return MODL_EGROW;     // cudaFree / cudaMalloc are not capturable: the caller re-runs the step eagerly
         // grow-only; freeing is stream-ordered-safe because cudaFree synchronises the device
         if (slot_ptr[slot]) MODL_CUDA_TRY(cudaFree(slot_ptr[slot]));
         slot_ptr[slot] = nullptr;
@@ -103,6 +104,8 @@ void modl_ctx_destroy(modl_ctx *ctx)
         CtxGuard g_(ctx);
         for (int i = 0; i < WS_COUNT; ++i)
             if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
+        for (int i = 0; i < 2; ++i)
+            if (ctx->ev_fork[i]) cudaEventDestroy(ctx->ev_fork[i]);
     }
     delete ctx;
 }
@@ -265,12 +268,23 @@ fetch_step_inputs_kernel(const int64_t *__restrict__ h_subset, int64_t *__restri
     for (int i = t; i < k; i += n) d_order[i] = (int32_t)h_order[i];
 }
 
+// An event the step records in the middle of a call (other streams wait on it).  While the call is being captured into a
+// graph the record becomes an event-record NODE: the event fires when the graph's launch reaches it, and a
+// cudaStreamWaitEvent issued after cudaGraphLaunch waits for exactly that.
+static int record_step_event(modl_ctx *ctx, void *ev, cudaStream_t st)
+{
+    if (ctx->capturing == 1) MODL_CUDA_TRY(cudaEventRecordWithFlags(static_cast<cudaEvent_t>(ev), st, cudaEventRecordExternal));
+    else MODL_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(ev), st));
+    return MODL_OK;
+}
+
 // upload the atom order as int32 (two buffers: the step in flight and the one being prefetched)
 static int upload_order(modl_ctx *ctx, const int64_t *h_order, int64_t k, int32_t **d_order, cudaStream_t st, int slot = 0,
                         bool ready = false)
 {
     MODL_TRY(ws<int32_t>(ctx, slot ? WS_ORDER2 : WS_ORDER, (size_t)k, d_order));
     if (ready) return MODL_OK;          // uploaded by this step's MODL_PHASE_PREFETCH
+    if (ctx->capturing) return MODL_EGROW;   // a copy out of a temporary cannot live in a graph: run the step eagerly
     std::vector<int32_t> tmp((size_t)k);
     for (int64_t i = 0; i < k; ++i) {
         MODL_REQUIRE(h_order[i] >= 0 && h_order[i] < k, "order is not a permutation of range(k)");
@@ -540,9 +554,9 @@ static int update_stats_impl(modl_ctx *ctx, const T *code, const int64_t *indice
 // only, so MODL_PHASE_PREFETCH builds it ahead of time.  The packed code^T is appended at the next tile boundary.
 static inline int64_t xs_split(int64_t s) { return s > 0 ? round_up(s, 128) : 0; }
 static int pack_xsub(modl_ctx *ctx, const float *Xsub, int64_t lds, int64_t s, int64_t b, int64_t k, float **XsP, cudaStream_t st,
-                     bool do_pack)
+                     bool do_pack, int slot)
 {
-    MODL_TRY(ws<float>(ctx, WS_TC_XS, tc_packed_elems(xs_split(s) + k, b), XsP));
+    MODL_TRY(ws<float>(ctx, slot ? WS_TC_XS2 : WS_TC_XS, tc_packed_elems(xs_split(s) + k, b), XsP));
     if (do_pack && s > 0) MODL_TRY(tc_pack_cols(ctx, Xsub, lds, b, s, *XsP, 128, st));
     return MODL_OK;
 }
@@ -554,14 +568,14 @@ static int pack_xsub(modl_ctx *ctx, const float *Xsub, int64_t lds, int64_t s, i
 // Xsub is the plain b x lds panel of X[:, subset]; xs_packed says its packed transpose is already in WS_TC_XS.
 template <typename T>
 static int stats_sub_impl(modl_ctx *ctx, const T *cb, const T *Xsub, int64_t lds, int64_t s, T *inc_sub, T *Cmat, T *Bp, T a,
-                          T keep, int64_t b, int64_t k, cudaStream_t st, bool xs_packed)
+                          T keep, int64_t b, int64_t k, cudaStream_t st, bool xs_packed, int slot = 0)
 {
     T *outC = inc_sub ? inc_sub : Cmat, *outB = inc_sub ? inc_sub + k * k : Bp;
     const T be = inc_sub ? T(0) : keep;
     if constexpr (std::is_same<T, float>::value) {
         if (use_tc<T>(ctx)) {
             float *XsP = nullptr;
-            MODL_TRY(pack_xsub(ctx, Xsub, lds, s, b, k, &XsP, st, !xs_packed));
+            MODL_TRY(pack_xsub(ctx, Xsub, lds, s, b, k, &XsP, st, !xs_packed, slot));
             const int64_t nkb = ceil_div(b, 32);
             float *codeP = XsP + (size_t)(xs_split(s) / 128) * nkb * (2 * 128 * 32);
             MODL_TRY(tc_pack_cols(ctx, cb, k, b, k, codeP, 128, st));
@@ -642,7 +656,8 @@ int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream)
     T *D = static_cast<T *>(q->components);
     T *code = static_cast<T *>(q->code);
     const T r = (T)q->reduction;
-    const int flag_bits = MODL_PHASE_REUSE_SUBSET | MODL_PHASE_INPUTS_READY | MODL_PHASE_FUSED_APPLY;
+    const int flag_bits = MODL_PHASE_REUSE_SUBSET | MODL_PHASE_INPUTS_READY | MODL_PHASE_FUSED_APPLY | MODL_PHASE_GATHER_B;
+    const bool gather_b = (q->phases & MODL_PHASE_GATHER_B) != 0;
     const bool inputs_ready = (q->phases & MODL_PHASE_INPUTS_READY) != 0;     // this step's MODL_PHASE_PREFETCH has run
     const bool reuse_subset = (q->phases & MODL_PHASE_REUSE_SUBSET) != 0 || inputs_ready;
     const bool fused_apply = (q->phases & MODL_PHASE_FUSED_APPLY) != 0;
@@ -724,7 +739,7 @@ int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream)
                     float *XsP = nullptr;
                     float *Xs = nullptr;
                     MODL_TRY(ws<float>(ctx, WS_PANEL_X, (size_t)(b * lds), &Xs));
-                    MODL_TRY(pack_xsub(ctx, Xs, lds, s, b, k, &XsP, st, true));
+                    MODL_TRY(pack_xsub(ctx, Xs, lds, s, b, k, &XsP, st, true, slot));
                 }
             }
         }
@@ -738,7 +753,20 @@ int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream)
     }
 
     T *panel_keep = nullptr;
+    bool b_early = false;
     if (phases & MODL_PHASE_CODE) {
+    if (gather_b && fused_apply && (phases & MODL_PHASE_STATS_SUB) && ctx->fork_stream && s > 0) {
+        // B_[:, subset] on the forked stream, beside the Gram / code solve (B_ is final: the previous step has ended)
+        for (int i = 0; i < 2; ++i)
+            if (!ctx->ev_fork[i]) MODL_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork[i], cudaEventDisableTiming));
+        T *Bp = nullptr;
+        MODL_TRY(ws<T>(ctx, slot ? WS_PANEL_B2 : WS_PANEL_B, (size_t)(k * lds), &Bp));
+        MODL_CUDA_TRY(cudaEventRecord(ctx->ev_fork[0], st));
+        MODL_CUDA_TRY(cudaStreamWaitEvent(ctx->fork_stream, ctx->ev_fork[0], 0));
+        MODL_TRY(gather_cols<T>(ctx, static_cast<const T *>(q->B), p, k, p, d_subset, s, Bp, lds, nullptr, ctx->fork_stream));
+        MODL_CUDA_TRY(cudaEventRecord(ctx->ev_fork[1], ctx->fork_stream));
+        b_early = true;
+    }
     // ---- _compute_code [ref: :577-648] ----
     const int x_mode = (inputs_ready && x_ahead) ? 2 : 0;
     if (need_sub) {
@@ -791,14 +819,16 @@ int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream)
         T *Bp = nullptr;
         if (fused_apply) {
             MODL_TRY(ws<T>(ctx, slot ? WS_PANEL_B2 : WS_PANEL_B, (size_t)(k * lds), &Bp));
-            if (!inputs_ready && s > 0)
+            if (b_early)
+                MODL_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_fork[1], 0));
+            else if ((!inputs_ready || gather_b) && s > 0)
                 MODL_TRY(gather_cols<T>(ctx, static_cast<const T *>(q->B), p, k, p, d_subset, s, Bp, lds, nullptr, st));
         }
         MODL_TRY(stats_sub_impl<T>(ctx, cb, Xsub, lds, s, fused_apply ? (T *)nullptr : inc_sub, static_cast<T *>(q->C), Bp, av,
-                                   keep, b, k, st, inputs_ready && x_there));
+                                   keep, b, k, st, inputs_ready && x_there, slot));
         if (fused_apply) {
             ctx->panel_b_ready = 1;
-            if (q->ev_after_apply_sub) MODL_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(q->ev_after_apply_sub), st));
+            if (q->ev_after_apply_sub) MODL_TRY(record_step_event(ctx, q->ev_after_apply_sub, st));
         }
     }
     // ---- _update_C / _update_B [ref: :559-575] ----
@@ -834,7 +864,7 @@ int batch_fit_impl(modl_ctx *ctx, const modl_step_params *q, void *stream)
                                                                  d_subset, (int)s, keep, inc_sub + k * k, lds, Bp, lds);
         MODL_LAUNCH_CHECK(ctx);
         ctx->panel_b_ready = 1;
-        if (q->ev_after_apply_sub) MODL_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(q->ev_after_apply_sub), st));
+        if (q->ev_after_apply_sub) MODL_TRY(record_step_event(ctx, q->ev_after_apply_sub, st));
     }
     if (phases & MODL_PHASE_DICT) {
     // ---- _update_dict [ref: :650-715] ----

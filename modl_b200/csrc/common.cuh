@@ -39,6 +39,9 @@ void set_error(const char *fmt, ...);
         }                                                                       \
     } while (0)
 
+// internal status (never crosses the C ABI): a workspace slot must grow while the call is being stream-captured
+#define MODL_EGROW 100
+
 // check the launch that was just issued
 #define MODL_LAUNCH_CHECK(ctx)                \
     do {                                      \
@@ -82,6 +85,8 @@ enum WsSlot {
     WS_WSAMPLE,      // real[b] per-sample weights of the 'average' modes, two slots
     WS_WSAMPLE2,
     WS_PANEL_X,      // X_sub  b x s_pad
+    WS_TC_XS2,       // second packed X[:, subset]^T | code^T panel (slot 1): the full-width product of step t reads the code^T
+                     //   part of its panel while the prefetch of step t+1 packs the next one
     WS_COUNT
 };
 
@@ -110,6 +115,14 @@ struct modl_ctx {
     int opt_bcd_pipeline = 1;     // pilot kernel, L2 ball without positivity: keep two norm exchanges in flight (bcd_pilot.cuh)
     const float *code_packed = nullptr;   // packed code^T (A operand, 128-row blocks) of the current step, or NULL
     int panel_b_ready = 0;        // the B_[:, subset] panel of the current step is complete in WS_PANEL_B[slot]
+    int capturing = 0;            // the launches of this call are being captured into a CUDA graph (fit_loop.cu): a workspace
+                                  // slot that would have to grow returns MODL_EGROW instead (the step is then run eagerly).
+                                  // 1: the mid-call event is one other streams wait for (an event-record node); 2: it is
+                                  // the fork point of a second captured stream (a plain record)
+    // set by the minibatch loop around a fused-graph step: a second stream on which the call may run work that is
+    // independent of the dictionary (the B_[:, subset] gather) beside its critical path; ev_fork orders the two
+    cudaStream_t fork_stream = nullptr;
+    cudaEvent_t ev_fork[2] = {};
     // optional per-phase device timing of the fused step (modl_ctx_profile)
     int prof_on = 0;
     int prof_n = 0;                       // marks recorded in the current step

@@ -143,6 +143,27 @@ struct modl_fit {
     size_t inc_bytes = 0, inc_sub_bytes = 0;
 
     int overlap = 1;                     // 0: one stream, one fused call per step (the round-1 schedule)
+    // CUDA graphs (one GPU, two-stream schedule): the launches of each of the step's three calls are stream-captured on
+    // `cap` (nothing ever runs there), folded into last step's executable graph with cudaGraphExecUpdate (new pointers,
+    // subset length, weights: same topology) and launched on the stream the call belongs to.  Inside a graph a kernel
+    // follows its predecessor in ~1 us instead of ~3 us, and -- the reason this exists -- stays there while pinned host
+    // rows saturate PCIe (stream launches: 5-10 us each then, scripts/ubench/graph_update_ubench.cu).
+    //   graph = 1 (default): the three calls of the two-stream schedule as three graphs; the second stream and the code
+    //   read-back wait for the dictionary kernel's residency flag instead of an event in the middle of the critical path (an
+    //   event-record node cuts a graph into separately submitted pieces).
+    //   graph = 2 (opt-in, measured 1-2 % slower: profiles/r02_w4_*): ONE graph per step on the caller's stream holds the
+    //   critical path AND, forked inside the graph after the subset statistics, the full-width product (behind a one-thread
+    //   kernel that polls the residency flag), joined at the end; the B_[:, subset] panel is gathered by the graph itself on
+    //   the forked stream (B_ is final when the previous graph has ended), so the second stream only prepares the X side of
+    //   the next step and the cycle step t -> step t+1 crosses no stream.
+    int graph = 1;
+    static constexpr int GRAPH_WARM_STEPS = 4;      // eager steps first: they size the workspace of both slots
+    cudaStream_t cap = nullptr, cap2 = nullptr;
+    cudaEvent_t ev_gfork[2] = {}, ev_gjoin[2] = {}; // fork / join of the second captured stream (never waited on outside)
+    bool prev_fused = false;                        // the previous step ran as one fused graph (or its eager twin)
+    cudaGraphExec_t gexec[2][3] = {};               // [slot][0 prefetch, 1 critical path, 2 full-width product]
+    std::vector<cudaGraphExec_t> gexec_retired;     // replaced executables: destroyed once nothing can be in flight
+    int64_t graph_launches = 0, graph_updates_failed = 0, graph_fallbacks = 0;
     int gate = 1;                        // side stream waits for the dictionary kernel to be resident
     cudaEvent_t ev_call = nullptr;       // "the caller's stream has reached this partial_fit call"
     cudaEvent_t code_ev[2] = {};         // the event that marked ev_code of the last step on each slot (a trace event when tracing)
@@ -191,6 +212,13 @@ static int fit_init(modl_fit *f)
     MODL_CUDA_TRY(cudaMemset(f->d_flag, 0, 256));
     if (const char *e = getenv("MODL_FIT_OVERLAP")) f->overlap = atoi(e);
     if (const char *e = getenv("MODL_FIT_GATE")) f->gate = atoi(e);
+    if (const char *e = getenv("MODL_FIT_GRAPH")) f->graph = atoi(e);
+    MODL_CUDA_TRY(cudaStreamCreateWithFlags(&f->cap, cudaStreamNonBlocking));
+    MODL_CUDA_TRY(cudaStreamCreateWithFlags(&f->cap2, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        MODL_CUDA_TRY(cudaEventCreateWithFlags(&f->ev_gfork[i], cudaEventDisableTiming));
+        MODL_CUDA_TRY(cudaEventCreateWithFlags(&f->ev_gjoin[i], cudaEventDisableTiming));
+    }
     return MODL_OK;
 }
 
@@ -219,6 +247,15 @@ static void fit_free(modl_fit *f)
     if (f->ev_call) cudaEventDestroy(f->ev_call);
     if (f->trace_base) cudaEventDestroy(f->trace_base);
     for (cudaEvent_t e : f->trace_ev) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 3; ++j) if (f->gexec[i][j]) cudaGraphExecDestroy(f->gexec[i][j]);
+    for (cudaGraphExec_t e : f->gexec_retired) cudaGraphExecDestroy(e);
+    if (f->cap) cudaStreamDestroy(f->cap);
+    if (f->cap2) cudaStreamDestroy(f->cap2);
+    for (int i = 0; i < 2; ++i) {
+        if (f->ev_gfork[i]) cudaEventDestroy(f->ev_gfork[i]);
+        if (f->ev_gjoin[i]) cudaEventDestroy(f->ev_gjoin[i]);
+    }
     if (f->d_flag) cudaFree(f->d_flag);
     if (f->inc) cudaFree(f->inc);
     if (f->inc_sub) cudaFree(f->inc_sub);
@@ -299,6 +336,110 @@ static int stage_batch(modl_fit *f, const T *h_rows, int64_t ldx, int64_t rows, 
     return MODL_OK;
 }
 
+// One thread polls the residency flag of the dictionary kernel (first node of the full-width product's branch inside the
+// fused graph: a one-CTA-per-SM GEMM that starts first leaves no room for the 16-CTA cluster).  Bounded: a dictionary
+// kernel that never started must not hang the device.
+__global__ void wait_flag_kernel(unsigned *flag, unsigned serial)
+{
+    const long long t0 = clock64();
+    while ((int)(*reinterpret_cast<const volatile unsigned *>(flag) - serial) < 0) {
+        if (clock64() - t0 > 40000000LL) {          // ~20 ms: give up (counted: modl_fit_graph_stats)
+            atomicAdd(flag + 1, 1u);
+            break;
+        }
+        __nanosleep(100);
+    }
+}
+
+// The fused step on streams (a, b2): critical path on a; after the subset statistics b2 forks, waits for the dictionary
+// kernel to be resident and runs the full-width product; a waits for b2 at the end.  Captured (a = cap, b2 = cap2) this is
+// the step's graph; on real streams it is the same step with plain launches.
+template <typename T>
+static int enqueue_fused(modl_fit *f, const modl_step_params *q0, int slot, cudaStream_t a, cudaStream_t b2)
+{
+    modl_ctx *ctx = f->ctx;
+    modl_step_params q = *q0;
+    q.phases = MODL_PHASE_CODE | MODL_PHASE_STATS_SUB | MODL_PHASE_DICT | MODL_PHASE_INPUTS_READY | MODL_PHASE_FUSED_APPLY |
+               MODL_PHASE_GATHER_B;
+    q.ev_after_apply_sub = f->ev_gfork[slot];
+    ctx->fork_stream = b2;                          // the B_[:, subset] gather runs there, beside the Gram and the code solve
+    const int status = batch_fit_impl<T>(ctx, &q, a);
+    ctx->fork_stream = nullptr;
+    MODL_TRY(status);
+    MODL_CUDA_TRY(cudaStreamWaitEvent(b2, f->ev_gfork[slot], 0));
+    if (q.subset_len > 0) {                         // a dictionary kernel was launched: it raises the flag
+        wait_flag_kernel<<<1, 1, 0, b2>>>(f->d_flag, f->serial);
+        MODL_LAUNCH_CHECK(ctx);
+    }
+    q.phases = MODL_PHASE_STATS_B;
+    q.inc_sub = nullptr;
+    q.ev_after_apply_sub = nullptr;
+    q.sm_avail = ctx->sm_count - 16;
+    MODL_TRY(batch_fit_impl<T>(ctx, &q, b2));
+    MODL_CUDA_TRY(cudaEventRecord(f->ev_gjoin[slot], b2));
+    MODL_CUDA_TRY(cudaStreamWaitEvent(a, f->ev_gjoin[slot], 0));
+    return MODL_OK;
+}
+
+// One call of the step (`which`: 0 prefetch, 1 critical path, 2 full-width product) on `st`: launched directly, or --
+// `use_graph` -- captured, folded into the slot's executable graph and launched as one.  A call that cannot be captured
+// (a workspace slot has to grow, an option took a path with a pageable upload) is run eagerly instead.
+template <typename T>
+static int run_call(modl_fit *f, bool use_graph, int which, int slot, const modl_step_params *q, cudaStream_t st, bool fused = false)
+{
+    modl_ctx *ctx = f->ctx;
+    // fused: the whole step (two captured streams); its eager twin runs the branch on the loop's second stream
+    auto eager = [&]() { return fused ? enqueue_fused<T>(f, q, slot, st, f->side) : batch_fit_impl<T>(ctx, q, st); };
+    if (!use_graph) return eager();
+    const float *code_packed = ctx->code_packed;
+    const int panel_b_ready = ctx->panel_b_ready;
+    const int64_t launches = ctx->launches;
+    if (cudaStreamBeginCapture(f->cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        f->graph = 0;
+        return eager();
+    }
+    ctx->capturing = fused ? 2 : 1;
+    const int status = fused ? enqueue_fused<T>(f, q, slot, f->cap, f->cap2) : batch_fit_impl<T>(ctx, q, f->cap);
+    ctx->capturing = 0;
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(f->cap, &g);
+    if (status != MODL_OK || ce != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        if (status != MODL_OK && status != MODL_EGROW) return status;
+        if (status == MODL_OK) f->graph = 0;        // something on this path is not capturable: stop trying
+        ctx->code_packed = code_packed; ctx->panel_b_ready = panel_b_ready; ctx->launches = launches;
+        f->graph_fallbacks += 1;
+        return eager();
+    }
+    cudaGraphExec_t &ex = f->gexec[slot][which];
+    bool current = false;
+    if (ex) {
+        cudaGraphExecUpdateResultInfo info;
+        current = cudaGraphExecUpdate(ex, g, &info) == cudaSuccess;
+        if (!current) {                             // another topology (empty subset, another kernel variant): rebuild
+            cudaGetLastError();
+            f->gexec_retired.push_back(ex);         // a launch of it may still be running
+            ex = nullptr;
+            f->graph_updates_failed += 1;
+        }
+    }
+    if (!current && cudaGraphInstantiate(&ex, g, 0) != cudaSuccess) {
+        cudaGetLastError();
+        cudaGraphDestroy(g);
+        ex = nullptr;
+        f->graph = 0;
+        ctx->code_packed = code_packed; ctx->panel_b_ready = panel_b_ready; ctx->launches = launches;
+        f->graph_fallbacks += 1;
+        return eager();
+    }
+    cudaGraphDestroy(g);
+    MODL_CUDA_TRY(cudaGraphLaunch(ex, st));
+    f->graph_launches += 1;
+    return MODL_OK;
+}
+
 template <typename T>
 static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fit_batches *io, void *stream)
 {
@@ -320,6 +461,11 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
     const bool overlap = f->overlap && !e->optimizer_sgd && !ctx->prof_on;
     StreamMemOps *smo = stream_mem_ops();
     const bool gate = overlap && f->gate && smo->ok;
+    if (f->gexec_retired.size() > 64) {             // rare: topology changes pile up only with alternating empty subsets
+        MODL_CUDA_TRY(cudaDeviceSynchronize());
+        for (cudaGraphExec_t ex : f->gexec_retired) cudaGraphExecDestroy(ex);
+        f->gexec_retired.clear();
+    }
     const T *X = static_cast<const T *>(io->X);
 
     if (host_x) {
@@ -366,6 +512,7 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
     for (int64_t i = 0; i < nb; ++i) {
         const int64_t r0 = i * bs, b = (r0 + bs <= n ? bs : n - r0);
         const int slot = (int)(f->step & 1), prev = slot ^ 1;
+        const bool use_graph = overlap && !sharded && f->graph && f->step >= modl_fit::GRAPH_WARM_STEPS;
         // ---- host rows on their way ----
         if (host_x) {
             for (; issued < nb && issued <= i + ahead - 1; ++issued) {
@@ -432,7 +579,7 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
         if (overlap && f->side_pending[prev]) {
             // the buffers PREFETCH rewrites were last read before ev_code of the previous step; B_ (gathered below on one
             // GPU) is final once the previous step's full-width product has run -- same stream, in order
-            MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, f->code_ev[prev], 0));
+            if (f->code_ev[prev]) MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, f->code_ev[prev], 0));
         }
         if (!contiguous) {
             int64_t *d_idx = nullptr;
@@ -476,11 +623,72 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
             continue;
         }
 
+        if (use_graph && gate && f->graph >= 2) {
+            // ---- one graph per step (see modl_fit::graph) ----
+            // side: the X side of this step's inputs.  Its buffers were last read by the previous step's subset statistics:
+            // the dictionary kernel that follows them has raised the flag (an eager predecessor: its code event as well)
+            if (f->side_pending[prev] && f->code_ev[prev]) MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, f->code_ev[prev], 0));
+            if (f->serial > 0) smo->wait32((CUstream)f->side, (CUdeviceptr)(uintptr_t)f->d_flag, f->serial, CU_STREAM_WAIT_VALUE_GEQ);
+            if (host_x) MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, f->ev_copied[sj], 0));
+            trace_mark(f, 2, f->side);
+            q.phases = MODL_PHASE_PREFETCH;                 // without FUSED_APPLY: the graph gathers B_[:, subset] itself
+            MODL_TRY(run_call<T>(f, true, 0, slot, &q, f->side));
+            MODL_CUDA_TRY(cudaEventRecord(f->ev_pre[slot], f->side));
+            trace_mark(f, 3, f->side);
+            MODL_CUDA_TRY(cudaEventRecord(f->ev_ring[f->step % modl_fit::NRING], f->side));
+            f->ring_busy[f->step % modl_fit::NRING] = true;
+
+            // main: the step
+            MODL_CUDA_TRY(cudaStreamWaitEvent(main_st, f->ev_pre[slot], 0));
+            for (int j = 0; j < 2; ++j)
+                if (f->side_pending[j]) {                   // an eager predecessor's full-width product (second stream): B_ is final
+                    MODL_CUDA_TRY(cudaStreamWaitEvent(main_st, f->ev_side[j], 0));
+                    f->side_pending[j] = false;
+                }
+            if (f->d2h_pending[prev]) {                     // the previous batch code has been read back before CODE overwrites it
+                MODL_CUDA_TRY(cudaStreamWaitEvent(main_st, f->ev_d2h[prev], 0));
+                f->d2h_pending[prev] = false;
+            }
+            f->serial += 1;
+            q.start_flag = f->d_flag;
+            q.start_serial = f->serial;
+            trace_mark(f, 4, main_st);
+            f->code_ev[slot] = nullptr;
+            MODL_TRY(run_call<T>(f, true, 1, slot, &q, main_st, true));
+            if (s == 0)                                     // no dictionary kernel: the flag still reaches the serial
+                smo->write32((CUstream)main_st, (CUdeviceptr)(uintptr_t)f->d_flag, f->serial, CU_STREAM_WRITE_VALUE_DEFAULT);
+            trace_mark(f, 6, main_st);
+            if (io->h_code_out) {
+                smo->wait32((CUstream)f->d2h, (CUdeviceptr)(uintptr_t)f->d_flag, f->serial, CU_STREAM_WAIT_VALUE_GEQ);
+                trace_mark(f, 5, f->d2h);                   // "codes done", as the read-back stream sees it
+                MODL_CUDA_TRY(cudaMemcpyAsync(static_cast<T *>(io->h_code_out) + r0 * k, ctx->slot_ptr[WS_CODE_BATCH],
+                                              sizeof(T) * (size_t)(b * k), cudaMemcpyDeviceToHost, f->d2h));
+                MODL_CUDA_TRY(cudaEventRecord(f->ev_d2h[slot], f->d2h));
+                trace_mark(f, 9, f->d2h);
+                f->d2h_pending[slot] = true;
+            }
+            if (f->trace_n < f->trace_cap) f->trace_n += 1;
+            if (host_x) {                                   // the graph's full-width product was the last reader of the rows
+                MODL_CUDA_TRY(cudaEventRecord(f->ev_free[sj], main_st));
+                f->stage_busy[sj] = true;
+            }
+            f->prev_fused = true;
+            f->step += 1;
+            continue;
+        }
+        if (f->prev_fused) {
+            // back to plain launches (graphs switched off, or a sharded / profiled call): the second stream must see the
+            // end of the last fused graph (B_ final, its buffers read) before it prepares this step
+            MODL_CUDA_TRY(cudaEventRecord(f->ev_call, main_st));
+            MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, f->ev_call, 0));
+            f->prev_fused = false;
+        }
+
         // ---- side: everything of the step that does not depend on the dictionary ----
         if (host_x) MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, f->ev_copied[sj], 0));
         trace_mark(f, 2, f->side);
         q.phases = MODL_PHASE_PREFETCH | (sharded ? 0 : MODL_PHASE_FUSED_APPLY);
-        MODL_TRY(batch_fit_impl<T>(ctx, &q, f->side));
+        MODL_TRY(run_call<T>(f, use_graph, 0, slot, &q, f->side));
         MODL_CUDA_TRY(cudaEventRecord(f->ev_pre[slot], f->side));
         trace_mark(f, 3, f->side);
         MODL_CUDA_TRY(cudaEventRecord(f->ev_ring[f->step % modl_fit::NRING], f->side));
@@ -497,16 +705,21 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
         q.start_serial = f->serial;
         trace_mark(f, 4, main_st);
         // ev_code: the codes are solved, the subset statistics folded in; the dictionary update follows on this stream
-        cudaEvent_t evc = f->ev_code[slot];
-        if (f->trace_n < f->trace_cap) {
+        // Graph-replayed step with the residency flag: no event in the middle of the critical path (an event-record node
+        // cuts the graph into separately submitted pieces, each paying the launch latency PCIe traffic inflates).  The
+        // dictionary kernel follows the subset statistics in stream order, so "its cluster is resident" (the flag the
+        // second stream already waits for) implies "codes solved, subset statistics folded in".
+        const bool by_flag = use_graph && gate;
+        cudaEvent_t evc = by_flag ? nullptr : f->ev_code[slot];
+        if (!by_flag && f->trace_n < f->trace_cap) {
             evc = f->trace_ev[(size_t)f->trace_n * modl_fit::TRACE_POINTS + 5];
             f->trace_set[(size_t)f->trace_n * modl_fit::TRACE_POINTS + 5] = 1;
         }
-        f->code_ev[slot] = evc;
+        f->code_ev[slot] = evc;                             // NULL: the second stream has waited for the flag, in order
         if (!sharded) {
             q.phases = MODL_PHASE_CODE | MODL_PHASE_STATS_SUB | MODL_PHASE_DICT | MODL_PHASE_INPUTS_READY | MODL_PHASE_FUSED_APPLY;
             q.ev_after_apply_sub = evc;                     // recorded between the subset statistics and the dictionary update
-            MODL_TRY(batch_fit_impl<T>(ctx, &q, main_st));
+            MODL_TRY(run_call<T>(f, use_graph, 1, slot, &q, main_st));
         } else {
             q.stats_inc = f->inc;
             q.inc_sub = f->inc_sub;
@@ -519,13 +732,14 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
             q.ev_after_apply_sub = f->ev_sub[slot];         // B_[:, subset] has been read
             MODL_TRY(batch_fit_impl<T>(ctx, &q, main_st));
         }
-        if (gate)    // whatever the dictionary phase launched (or did not: empty subset), the flag reaches the serial
+        if (gate && !(by_flag && s > 0))    // whatever the dictionary phase launched (or did not: empty subset), the flag reaches
             smo->write32((CUstream)main_st, (CUdeviceptr)(uintptr_t)f->d_flag, f->serial, CU_STREAM_WRITE_VALUE_DEFAULT);
         trace_mark(f, 6, main_st);
 
         // ---- read-back of the batch code (optional), on its own stream ----
         if (io->h_code_out) {
-            MODL_CUDA_TRY(cudaStreamWaitEvent(f->d2h, evc, 0));
+            if (by_flag) smo->wait32((CUstream)f->d2h, (CUdeviceptr)(uintptr_t)f->d_flag, f->serial, CU_STREAM_WAIT_VALUE_GEQ);
+            else MODL_CUDA_TRY(cudaStreamWaitEvent(f->d2h, evc, 0));
             MODL_CUDA_TRY(cudaMemcpyAsync(static_cast<T *>(io->h_code_out) + r0 * k, ctx->slot_ptr[WS_CODE_BATCH],
                                           sizeof(T) * (size_t)(b * k), cudaMemcpyDeviceToHost, f->d2h));
             MODL_CUDA_TRY(cudaEventRecord(f->ev_d2h[slot], f->d2h));
@@ -534,14 +748,15 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
         }
 
         // ---- side: the full-width statistic, behind the dictionary update ----
-        MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, evc, 0));
+        if (!by_flag) MODL_CUDA_TRY(cudaStreamWaitEvent(f->side, evc, 0));
         if (gate) smo->wait32((CUstream)f->side, (CUdeviceptr)(uintptr_t)f->d_flag, f->serial, CU_STREAM_WAIT_VALUE_GEQ);
+        if (by_flag) trace_mark(f, 5, f->side);             // "codes done", as the second stream sees it
         trace_mark(f, 7, f->side);
         q.phases = MODL_PHASE_STATS_B;
         q.inc_sub = nullptr;
         q.ev_after_apply_sub = nullptr;
         q.sm_avail = ctx->sm_count - 16;
-        MODL_TRY(batch_fit_impl<T>(ctx, &q, f->side));
+        MODL_TRY(run_call<T>(f, use_graph, 2, slot, &q, f->side));
         if (sharded) {
             MODL_NCCL_TRY(nccl_api()->AllReduce(static_cast<T *>(f->inc) + k * k, static_cast<T *>(f->inc) + k * k, (size_t)(k * p),
                                                 sizeof(T) == 4 ? ncclFloat : ncclDouble, ncclSum, f->comm_side, f->side));
@@ -563,7 +778,7 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
     // the caller's stream sees the whole call: B_ is final, the batch code has been read back
     if (overlap) {
         const int last = (int)((f->step - 1) & 1);
-        MODL_CUDA_TRY(cudaStreamWaitEvent(main_st, f->ev_side[last], 0));
+        if (f->side_pending[last]) MODL_CUDA_TRY(cudaStreamWaitEvent(main_st, f->ev_side[last], 0));   // (a fused step joins inside its graph)
         if (f->d2h_pending[last]) MODL_CUDA_TRY(cudaStreamWaitEvent(main_st, f->ev_d2h[last], 0));
     }
     if (io->wait_host) {
@@ -617,7 +832,19 @@ int modl_fit_set_option(modl_fit *f, const char *name, int value)
     CtxGuard g_(f->ctx);
     if (!strcmp(name, "overlap")) f->overlap = value;
     else if (!strcmp(name, "gate")) f->gate = value;
+    else if (!strcmp(name, "graph")) f->graph = value;
     else { set_error("unknown option %s", name); return MODL_EINVAL; }
+    return MODL_OK;
+}
+
+int modl_fit_graph_stats(modl_fit *f, int64_t *h_out4)
+{
+    MODL_REQUIRE(f && h_out4, "null");
+    CtxGuard g_(f->ctx);
+    h_out4[0] = f->graph_launches; h_out4[1] = f->graph_updates_failed; h_out4[2] = f->graph_fallbacks;
+    unsigned timeouts = 0;
+    MODL_CUDA_TRY(cudaMemcpy(&timeouts, f->d_flag + 1, sizeof(unsigned), cudaMemcpyDeviceToHost));     // synchronises
+    h_out4[3] = (int64_t)timeouts;
     return MODL_OK;
 }
 

@@ -436,6 +436,43 @@ def test_c_loop_schedules_agree(option):
             assert rel_err(getattr(a, name), getattr(c, name)) < tol, name
 
 
+@pytest.mark.parametrize("mode", [2, 1])
+@pytest.mark.parametrize("rows", ["device", "pinned"])
+def test_c_loop_graph_replay_is_bit_identical(rows, mode):
+    """From its fifth block on the loop replays a block as CUDA graphs updated in place (modl_fit_set_option "graph":
+    2 = one graph per block with the full-width product forked inside it, 1 = the three calls of the two-stream
+    schedule as three graphs): same kernels, same inputs, so every state array, the codes read back and the bookkeeping
+    are bit-identical to plain stream launches -- across calls, ragged tails and host rows."""
+    from modl_b200 import DictFact
+    n, p, k, b = 1900, 2000, 64, 120                  # 16 blocks, the last one ragged
+    Xh = torch.from_numpy(_planted(n, p, k, seed=6))
+    X = Xh.cuda() if rows == "device" else Xh.pin_memory()
+    outs, codes, stats = [], [], []
+    for value in (mode, 0):
+        est = DictFact(n_components=k, batch_size=b, reduction=4, code_l1_ratio=1., code_alpha=0.4, random_state=0,
+                       async_host_copy=True)
+        est.prepare(n_samples=n, X=Xh[:k].numpy())
+        loop = est._fit_loop_handle()
+        loop.set_option("graph", value)
+        out = torch.empty((n, k), dtype=torch.float32).pin_memory()
+        cuts = [0, 120, 240, 360, 480, 600, 720, 1320, n]         # one block per call, then several, then the tail
+        for r0, r1 in zip(cuts[:-1], cuts[1:]):
+            est.partial_fit(X[r0:r1], np.arange(r0, r1), code_out=out[r0:r1])
+        est.synchronize()
+        outs.append(est)
+        codes.append(out.numpy().copy())
+        stats.append(loop.graph_stats())
+    assert stats[1]["launches"] == 0
+    assert stats[0]["gate_timeouts"] == 0, stats[0]
+    assert stats[0]["launches"] >= (4 - mode) * (16 - 4) - stats[0]["fallbacks"] > 0, stats[0]
+    a, c = outs
+    for name in ("components_", "code_", "C_", "B_", "comp_norm_", "sample_n_iter_", "last_subset_", "last_order_"):
+        np.testing.assert_array_equal(getattr(a, name), getattr(c, name), err_msg=name)
+    assert a.n_iter_ == c.n_iter_
+    np.testing.assert_array_equal(codes[0], codes[1])
+    np.testing.assert_array_equal(codes[0], a.code_)
+
+
 def test_refit_with_another_dtype():
     """prepare() drops every dtype- / device-bound cache: the same estimator fits float32 then float64 data."""
     from modl_b200 import DictFact
