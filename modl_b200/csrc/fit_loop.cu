@@ -161,7 +161,8 @@ struct modl_fit {
     cudaStream_t cap = nullptr, cap2 = nullptr;
     cudaEvent_t ev_gfork[2] = {}, ev_gjoin[2] = {}; // fork / join of the second captured stream (never waited on outside)
     bool prev_fused = false;                        // the previous step ran as one fused graph (or its eager twin)
-    cudaGraphExec_t gexec[2][3] = {};               // [slot][0 prefetch, 1 critical path, 2 full-width product]
+    cudaGraphExec_t gexec[2][4] = {};               // [slot][0 prefetch, 1 critical path (sharded: up to the all-reduce), 2 full-width
+                                                    //  product, 3 sharded: fold-in + dictionary update]
     std::vector<cudaGraphExec_t> gexec_retired;     // replaced executables: destroyed once nothing can be in flight
     int64_t graph_launches = 0, graph_updates_failed = 0, graph_fallbacks = 0;
     int gate = 1;                        // side stream waits for the dictionary kernel to be resident
@@ -248,7 +249,7 @@ static void fit_free(modl_fit *f)
     if (f->trace_base) cudaEventDestroy(f->trace_base);
     for (cudaEvent_t e : f->trace_ev) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i)
-        for (int j = 0; j < 3; ++j) if (f->gexec[i][j]) cudaGraphExecDestroy(f->gexec[i][j]);
+        for (int j = 0; j < 4; ++j) if (f->gexec[i][j]) cudaGraphExecDestroy(f->gexec[i][j]);
     for (cudaGraphExec_t e : f->gexec_retired) cudaGraphExecDestroy(e);
     if (f->cap) cudaStreamDestroy(f->cap);
     if (f->cap2) cudaStreamDestroy(f->cap2);
@@ -512,7 +513,7 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
     for (int64_t i = 0; i < nb; ++i) {
         const int64_t r0 = i * bs, b = (r0 + bs <= n ? bs : n - r0);
         const int slot = (int)(f->step & 1), prev = slot ^ 1;
-        const bool use_graph = overlap && !sharded && f->graph && f->step >= modl_fit::GRAPH_WARM_STEPS;
+        const bool use_graph = overlap && f->graph && f->step >= modl_fit::GRAPH_WARM_STEPS;
         // ---- host rows on their way ----
         if (host_x) {
             for (; issued < nb && issued <= i + ahead - 1; ++issued) {
@@ -623,7 +624,7 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
             continue;
         }
 
-        if (use_graph && gate && f->graph >= 2) {
+        if (use_graph && gate && !sharded && f->graph >= 2) {
             // ---- one graph per step (see modl_fit::graph) ----
             // side: the X side of this step's inputs.  Its buffers were last read by the previous step's subset statistics:
             // the dictionary kernel that follows them has raised the flag (an eager predecessor: its code event as well)
@@ -709,7 +710,7 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
         // cuts the graph into separately submitted pieces, each paying the launch latency PCIe traffic inflates).  The
         // dictionary kernel follows the subset statistics in stream order, so "its cluster is resident" (the flag the
         // second stream already waits for) implies "codes solved, subset statistics folded in".
-        const bool by_flag = use_graph && gate;
+        const bool by_flag = use_graph && gate && !sharded;
         cudaEvent_t evc = by_flag ? nullptr : f->ev_code[slot];
         if (!by_flag && f->trace_n < f->trace_cap) {
             evc = f->trace_ev[(size_t)f->trace_n * modl_fit::TRACE_POINTS + 5];
@@ -724,13 +725,13 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
             q.stats_inc = f->inc;
             q.inc_sub = f->inc_sub;
             q.phases = MODL_PHASE_CODE | MODL_PHASE_STATS_SUB | MODL_PHASE_INPUTS_READY;
-            MODL_TRY(batch_fit_impl<T>(ctx, &q, main_st));
+            MODL_TRY(run_call<T>(f, use_graph, 1, slot, &q, main_st));
             MODL_CUDA_TRY(cudaEventRecord(evc, main_st));
             MODL_NCCL_TRY(nccl_api()->AllReduce(f->inc_sub, f->inc_sub, (size_t)(k * k + k * panel_ld(s)),
                                                 sizeof(T) == 4 ? ncclFloat : ncclDouble, ncclSum, f->comm_main, main_st));
             q.phases = MODL_PHASE_APPLY_SUB | MODL_PHASE_DICT | MODL_PHASE_INPUTS_READY;
             q.ev_after_apply_sub = f->ev_sub[slot];         // B_[:, subset] has been read
-            MODL_TRY(batch_fit_impl<T>(ctx, &q, main_st));
+            MODL_TRY(run_call<T>(f, use_graph, 3, slot, &q, main_st));
         }
         if (gate && !(by_flag && s > 0))    // whatever the dictionary phase launched (or did not: empty subset), the flag reaches
             smo->write32((CUstream)main_st, (CUdeviceptr)(uintptr_t)f->d_flag, f->serial, CU_STREAM_WRITE_VALUE_DEFAULT);

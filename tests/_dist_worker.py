@@ -21,7 +21,7 @@ def main():
     from modl_b200.distributed import ShardedDictFact
 
     rng = np.random.RandomState(0)
-    k, p, b_local, steps = 64, 2000, 96, 3
+    k, p, b_local, steps = 64, 2000, 96, 8      # the C loop replays CUDA graphs from its fifth step on
     n = b_local * world * steps
     D0 = rng.randn(k, p)
     D0 /= np.linalg.norm(D0, axis=1, keepdims=True)
