@@ -49,6 +49,18 @@ def main():
             out[name] = {"spread": spread, "D": err(est.components_, ref.components_), "C": err(est.C_, ref.C_),
                          "B": err(est.B_, ref.B_), "code_rank0_rows": err(est.code_[mine], ref.code_[mine]),
                          "n_iter": [int(est.n_iter_), int(ref.n_iter_)]}
+            # ... and against the UNMODIFIED reference (oracle/_ref, compiled from /root/reference) on the same rows
+            ref_dir = os.path.join(ROOT, "oracle", "_ref")
+            if os.path.isdir(os.path.join(ref_dir, "modl")):
+                if ref_dir not in sys.path:
+                    sys.path.insert(0, ref_dir)
+                import modl.decomposition.dict_fact as ref_df
+                gold = ref_df.DictFact(batch_size=b_local * world, **base)
+                gold.prepare(n_samples=n, X=X[:k])
+                gold.partial_fit(X)
+                out[name].update({"ref_D": err(est.components_, gold.components_), "ref_C": err(est.C_, gold.C_),
+                                  "ref_B": err(est.B_, gold.B_), "ref_code_rank0_rows": err(est.code_[mine], gold.code_[mine]),
+                                  "ref_n_iter": int(gold.n_iter_)})
     if rank == 0:
         print("DIST_RESULT " + json.dumps(out))
     dist.destroy_process_group()

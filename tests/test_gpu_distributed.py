@@ -1,5 +1,6 @@
 """N-GPU parity of the sample-sharded step (NCCL all-reduce of the statistics increments): the
-replicas stay bit-identical and match the single-GPU estimator run on the concatenated batch.
+replicas stay bit-identical and match the single-GPU estimator run on the concatenated batch and the
+unmodified reference (oracle/_ref) run on the same rows.
 Needs >= 2 GPUs (gpurun --gpus 2); skipped otherwise."""
 import json
 import os
@@ -46,3 +47,8 @@ def test_sharded_matches_single_gpu():
         assert r["n_iter"][0] == r["n_iter"][1]
         for key in ("D", "C", "B", "code_rank0_rows"):
             assert r[key] < 2e-5, (name, key, r)
+        if "ref_D" in r:                                     # the unmodified reference on the same rows, 8 minibatches (f32)
+            assert r["ref_n_iter"] == r["n_iter"][0]
+            for key in ("ref_D", "ref_C", "ref_B", "ref_code_rank0_rows"):
+                assert r[key] < 2e-3, (name, key, r)
+        print("sharded vs single GPU / vs reference:", name, r)
