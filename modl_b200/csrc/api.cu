@@ -129,6 +129,19 @@ int modl_ctx_set_option(modl_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "tc_split2")) ctx->opt_tc_split2 = value;
     else if (!strcmp(name, "bcd_coop_min_cols")) ctx->opt_bcd_coop_min_cols = value;
     else if (!strcmp(name, "bcd_flag_barrier")) ctx->opt_bcd_flag_barrier = value;
+    else if (!strcmp(name, "drop_workspace")) {
+        // debug / memory pressure: give the grow-only scratch slots back (they are re-reserved by the next call that needs
+        // them; a graph-replayed step that meets an empty slot falls back to plain launches for that call)
+        MODL_CUDA_TRY(cudaDeviceSynchronize());
+        for (int i = 0; i < WS_COUNT; ++i) {
+            if (i == WS_INFO || !ctx->slot_ptr[i]) continue;
+            MODL_CUDA_TRY(cudaFree(ctx->slot_ptr[i]));
+            ctx->slot_ptr[i] = nullptr;
+            ctx->slot_bytes[i] = 0;
+        }
+        ctx->code_packed = nullptr;
+        ctx->panel_b_ready = 0;
+    }
     else { set_error("unknown option %s", name); return MODL_EINVAL; }
     return MODL_OK;
 }

@@ -459,9 +459,18 @@ def test_c_loop_graph_replay_is_bit_identical(rows, mode):
         for r0, r1 in zip(cuts[:-1], cuts[1:]):
             est.partial_fit(X[r0:r1], np.arange(r0, r1), code_out=out[r0:r1])
         est.synchronize()
-        outs.append(est)
         codes.append(out.numpy().copy())
+        # the scratch slots are given back in mid-fit: they must grow while a call is being captured -> those calls fall
+        # back to plain launches (MODL_EGROW), the next ones replay again
+        before = loop.graph_stats()
+        est._ctx().set_option("drop_workspace", 1)
+        est.partial_fit(X[:4 * b], np.arange(4 * b))
+        est.synchronize()
+        outs.append(est)
         stats.append(loop.graph_stats())
+        if value:
+            assert stats[-1]["fallbacks"] > before["fallbacks"], (before, stats[-1])
+            assert stats[-1]["launches"] > before["launches"], (before, stats[-1])
     assert stats[1]["launches"] == 0
     assert stats[0]["gate_timeouts"] == 0, stats[0]
     assert stats[0]["launches"] >= (4 - mode) * (16 - 4) - stats[0]["fallbacks"] > 0, stats[0]
@@ -470,7 +479,6 @@ def test_c_loop_graph_replay_is_bit_identical(rows, mode):
         np.testing.assert_array_equal(getattr(a, name), getattr(c, name), err_msg=name)
     assert a.n_iter_ == c.n_iter_
     np.testing.assert_array_equal(codes[0], codes[1])
-    np.testing.assert_array_equal(codes[0], a.code_)
 
 
 def test_refit_with_another_dtype():
