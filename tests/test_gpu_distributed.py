@@ -50,5 +50,5 @@ def test_sharded_matches_single_gpu():
         if "ref_D" in r:                                     # the unmodified reference on the same rows, 8 minibatches (f32)
             assert r["ref_n_iter"] == r["n_iter"][0]
             for key in ("ref_D", "ref_C", "ref_B", "ref_code_rank0_rows"):
-                assert r[key] < 2e-3, (name, key, r)
+                assert r[key] < 1e-4, (name, key, r)                # measured: <= 7e-6
         print("sharded vs single GPU / vs reference:", name, r)
