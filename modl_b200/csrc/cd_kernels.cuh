@@ -186,7 +186,7 @@ __device__ __forceinline__ int cd_solve_warp(unsigned sbase, const T *__restrict
                                              T (&w)[TILES], const T (&q)[TILES], T ynorm2, T alpha,
                                              T beta, T tol, int max_iter, bool positive, const T *__restrict__ h_ones = nullptr)
 {
-    T h[TILES], r[TILES], inv[TILES];
+    T h[TILES], r[TILES], inv[TILES], diag[TILES];
     unsigned dead = 0;      // bit J: my coordinate 32 J + lane has a zero diagonal (or is padding)
     // 1 / (Q[c,c] + beta) for my own coordinates, once per sample.  The per-step division of
     // the reference (:372-373) becomes multiply + one Newton correction (correctly rounded in
@@ -199,6 +199,7 @@ __device__ __forceinline__ int cd_solve_warp(unsigned sbase, const T *__restrict
         if (PACKED) dg = lds_real(sbase + (unsigned)sizeof(T) * (unsigned)((cd_tri(J) + J) * CD_TILE_ELEMS + lane * CD_TILE + ((2 * lane) & 31)), T(0));
         else        dg = c < k ? Gs[(int64_t)c * k + c] : T(0);
         if (dg == T(0) || c >= k) dead |= (1u << J);
+        diag[J] = dg;
         inv[J] = T(1) / (dg + beta);
         h[J] = T(0);
     }
@@ -249,23 +250,30 @@ __device__ __forceinline__ int cd_solve_warp(unsigned sbase, const T *__restrict
                 const T mag0 = t_abs(tmp0) - alpha;
                 const bool moves = mag0 > T(0) && !(positive && tmp0 < T(0));
                 const unsigned act = __ballot_sync(kFullMask, my_live && (w[J] != T(0) || moves)) & todo;
+                // The new weight of MY coordinate as if it were the next one visited -- every lane, before the ballot
+                // resolves and before any row is loaded: on the visited lane l the reference's first update
+                // H -= w_old Q[c,:] leaves h[J] = fma(-w[J], Q[c,c], h[J]) (row element r[J] on lane l IS the diagonal, which
+                // the lane keeps in a register), and everything the candidate needs is the lane's own state.  Same
+                // operations on the same operands as computing it after the row arrives (bit-identical), but the
+                // soft threshold and the Newton division now overlap the ballot and the shared-memory row load instead of
+                // following them on the dependent chain.
+                const T hl = fma(-w[J], diag[J], h[J]);
+                const T tmp = q[J] - hl;
+                const T mag = t_abs(tmp) - alpha;
+                T ms = mag > T(0) ? mag : T(0);
+                ms = (tmp < T(0)) ? (positive ? T(0) : -ms) : ms;
+                const T den = diag[J] + beta;
+                T cand = ms * inv[J];
+                cand = fma(fma(-cand, den, ms), inv[J], cand);         // Newton step: ms / den
                 if (act == 0u) break;
                 const int l = __ffs(act) - 1;
                 todo = (l == 31) ? 0u : (kFullMask << (l + 1));
                 if (PACKED) cd_row_packed<T, TILES>(sbase, J, l, lane, r);
                 else        cd_row_global<T, TILES>(Gs, k, J * CD_TILE + l, lane, r);
                 const T w_old = __shfl_sync(kFullMask, w[J], l);
-                // H -= w_old Q[c,:] -- a zero coefficient leaves H bit-unchanged
-                cd_axpy_tiles<TILES>(h, r, -w_old);
-                // candidate for "my" coordinate of tile J; only lane l's value is consumed
-                const T tmp = q[J] - h[J];
-                const T mag = t_abs(tmp) - alpha;
-                T ms = mag > T(0) ? mag : T(0);
-                ms = (tmp < T(0)) ? (positive ? T(0) : -ms) : ms;
-                const T den = r[J] + beta;                             // r[J] on lane l is Q[c,c]
-                T cand = ms * inv[J];
-                cand = fma(fma(-cand, den, ms), inv[J], cand);         // Newton step: ms / den
                 const T w_new = __shfl_sync(kFullMask, cand, l);
+                // H -= w_old Q[c,:] -- a zero coefficient leaves H bit-unchanged; then H += w_new Q[c,:]  [ref: :359-376]
+                cd_axpy_tiles<TILES>(h, r, -w_old);
                 w[J] = (lane == l) ? w_new : w[J];
                 cd_axpy_tiles<TILES>(h, r, w_new);
             }
