@@ -181,11 +181,13 @@ __device__ __forceinline__ void cd_axpy_tiles(double (&h)[TILES], const double (
 }
 
 // One coordinate-descent solve for the sample owned by this warp.
-template <typename T, int TILES, bool PACKED>
+// POS (non-negative codes) is a template parameter: the sign tests sit on the dependent chain of every coordinate step
+template <typename T, int TILES, bool PACKED, bool POS>
 __device__ __forceinline__ int cd_solve_warp(unsigned sbase, const T *__restrict__ Gs, int k, int lane,
                                              T (&w)[TILES], const T (&q)[TILES], T ynorm2, T alpha,
-                                             T beta, T tol, int max_iter, bool positive, const T *__restrict__ h_ones = nullptr)
+                                             T beta, T tol, int max_iter, const T *__restrict__ h_ones = nullptr)
 {
+    constexpr bool positive = POS;
     T h[TILES], r[TILES], inv[TILES], diag[TILES];
     unsigned dead = 0;      // bit J: my coordinate 32 J + lane has a zero diagonal (or is padding)
     // 1 / (Q[c,c] + beta) for my own coordinates, once per sample.  The per-step division of
@@ -357,9 +359,12 @@ __global__ void cd_regression_kernel(const T *__restrict__ G, int64_t g_stride, 
             q[J] = c < k ? qrow[c] : T(0);
         }
         const T *Gs = G + (int64_t)ii * g_stride;
-        const int sw = cd_solve_warp<T, TILES, PACKED>((unsigned)__cvta_generic_to_shared(sG), Gs, k, lane, w, q,
-                                                       xnorm2[ii], alpha, beta, tol, max_iter, positive != 0,
-                                                       PACKED ? G + cd_packed_elems(TILES) : (const T *)nullptr);
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(sG);
+        const T *h_ones = PACKED ? G + cd_packed_elems(TILES) : (const T *)nullptr;
+        const int sw = positive ? cd_solve_warp<T, TILES, PACKED, true>(sbase, Gs, k, lane, w, q, xnorm2[ii], alpha, beta, tol,
+                                                                        max_iter, h_ones)
+                                : cd_solve_warp<T, TILES, PACKED, false>(sbase, Gs, k, lane, w, q, xnorm2[ii], alpha, beta, tol,
+                                                                         max_iter, h_ones);
 #pragma unroll
         for (int J = 0; J < TILES; ++J) {
             const int c = J * CD_TILE + lane;
