@@ -167,6 +167,7 @@ int bcd_update(modl_ctx *ctx, T *Dp, const T *Bp, int64_t lds, const T *C, T *co
         ctx->bcd_timing_k = (int)k;
     }
 
+    ctx->bcd_grid_wide = use_cluster ? 0 : 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(use_pilot == 2 ? BB_THREADS : use_pilot ? BP_THREADS : BCD_THREADS);
     cfg.dynamicSmemBytes = smem; cfg.stream = st;

@@ -115,6 +115,8 @@ struct modl_ctx {
     int opt_bcd_pipeline = 1;     // pilot kernel, L2 ball without positivity: keep two norm exchanges in flight (bcd_pilot.cuh)
     const float *code_packed = nullptr;   // packed code^T (A operand, 128-row blocks) of the current step, or NULL
     int panel_b_ready = 0;        // the B_[:, subset] panel of the current step is complete in WS_PANEL_B[slot]
+    int bcd_grid_wide = 0;        // the last dictionary update ran on the cooperative grid (panel larger than one cluster): the
+                                  // minibatch loop then keeps plain launches (fit_loop.cu)
     int capturing = 0;            // the launches of this call are being captured into a CUDA graph (fit_loop.cu): a workspace
                                   // slot that would have to grow returns MODL_EGROW instead (the step is then run eagerly).
                                   // 1: the mid-call event is one other streams wait for (an event-record node); 2: it is

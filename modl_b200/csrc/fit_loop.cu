@@ -513,7 +513,9 @@ static int partial_fit_impl(modl_fit *f, const modl_fit_params *e, const modl_fi
     for (int64_t i = 0; i < nb; ++i) {
         const int64_t r0 = i * bs, b = (r0 + bs <= n ? bs : n - r0);
         const int slot = (int)(f->step & 1), prev = slot ^ 1;
-        const bool use_graph = overlap && f->graph && f->step >= modl_fit::GRAPH_WARM_STEPS;
+        // (not while the dictionary update runs on the cooperative grid -- panels larger than one cluster: with the side
+        //  stream's graphs beside that kernel the fMRI-shaped step ran 2x slower, profiles/r02_nr_*; plain launches there)
+        const bool use_graph = overlap && f->graph && f->step >= modl_fit::GRAPH_WARM_STEPS && !ctx->bcd_grid_wide;
         // ---- host rows on their way ----
         if (host_x) {
             for (; issued < nb && issued <= i + ahead - 1; ++issued) {

@@ -67,6 +67,10 @@ def bench_fmri(dry):
     dev_s = est.time_
     out.update(value=n / dt, unit="samples/s", seconds=dt, samples=n, partial_fit_device_seconds=dev_s,
                value_partial_fit_only=n / dev_s if dev_s else None, nonzero_fraction=float((comp != 0).mean()))
+    try:
+        out["cuda_graphs"] = est._fit_loop_handle().graph_stats()
+    except Exception as exc:
+        out["cuda_graphs"] = repr(exc)
     # reference arm: same estimator keywords, 1 warm-up + 3 timed minibatches of host rows
     try:
         from modl.decomposition.dict_fact import DictFact as RefDictFact
@@ -113,6 +117,10 @@ def bench_image(dry):
     dev_s = est.time_
     out.update(value=n_patches / dt, unit="samples/s", seconds=dt, samples=n_patches,
                partial_fit_device_seconds=dev_s, value_partial_fit_only=n_patches / dev_s if dev_s else None)
+    try:
+        out["cuda_graphs"] = est._fit_loop_handle().graph_stats()
+    except Exception as exc:
+        out["cuda_graphs"] = repr(exc)
     try:
         from modl.decomposition.dict_fact import DictFact as RefDictFact
         from modl_b200.image import LazyCleanPatchExtractor, _flatten_patches
