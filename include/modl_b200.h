@@ -398,7 +398,8 @@ void modl_fit_destroy(modl_fit *fit);
  * "graph" (on one GPU, after the first four blocks, the launches of a block are stream-captured, folded into the previous
  * block's executable CUDA graph with cudaGraphExecUpdate and launched as a graph -- same kernels, same results:
  * 1 (default) = the three calls of the two-stream schedule as three graphs; 2 = one graph per block on the caller's
- * stream, the full-width product forked inside it; 0 = plain stream launches). */
+ * stream, the full-width product forked inside it; 0 = plain stream launches.  Blocks whose dictionary update runs on the
+ * cooperative grid -- panels larger than one thread-block cluster -- keep plain launches whatever the option). */
 int modl_fit_set_option(modl_fit *fit, const char *name, int value);
 /* h_out[0] = graph launches so far, h_out[1] = executable graphs rebuilt because the block's topology changed,
  * h_out[2] = calls run with plain launches because they could not be captured (a workspace slot had to grow),
