@@ -705,6 +705,9 @@ bcd_blocked_kernel(BcdParams<T> P)
             const T rad_l = cnorm[a_l] + Mfull[(BB_M + (lane & (BB_M - 1))) * BB_MLD + BB_M + (lane & (BB_M - 1))];
             const T rinv_l = rad_l != T(0) ? T(1) / rad_l : T(0);
             T wacc[BB_M], yacc[BB_M];      // lane r's component of w_t and of G w_t, accumulated right-looking
+            T cn_mine = T(0);              // lane t keeps the new comp_norm_ of atom t: ONE store per block after the chain (a
+                                           // store per atom put a shared load -> address -> store sequence in front of every
+                                           // atom's reduction: a warp issues in order)
 #pragma unroll
             for (int t = 0; t < BB_M; ++t) { wacc[t] = (lane == t) ? T(1) : T(0); yacc[t] = Mrow[t]; }
 #pragma unroll
@@ -730,8 +733,10 @@ bcd_blocked_kernel(BcdParams<T> P)
                 }
                 coef[t * BB_NB + lane] = cf;
                 // comp_norm_[k] -= enet_norm(new row) [ref: :690-692]: |n_t|^2 = rn^2 |v_t|^2 (the same value in every CTA)
-                if (g == 0 && lane == 0 && t < mb) P.comp_norm[ord_s[b * BB_M + t]] = radius - (rn * rn) * n2;
+                const T cn_t = radius - (rn * rn) * n2;
+                cn_mine = (lane == t) ? cn_t : cn_mine;
             }
+            if (g == 0 && lane < mb) P.comp_norm[ord_s[b * BB_M + lane]] = cn_mine;
             if (sstamp) sstamp[(int64_t)b * 8 + 7] = clock64();
         }
         __syncthreads();                    // coefficients, look-ahead product of block b+1, operands of blocks b+1 / b+2
